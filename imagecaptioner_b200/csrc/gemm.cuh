@@ -1,0 +1,390 @@
+// Dense contractions of the hot path (kernel (2) of the north star).
+//
+//   C[m,n] = act( alpha * sum_k A(m,k) * B(n,k) + bias[n] ) + beta * C[m,n]
+//
+// Operand "majorness" (row-major storage everywhere):
+//   A K-major : A(m,k) = A[m*lda + k]      A MN-major: A(m,k) = A[k*lda + m]
+//   B K-major : B(n,k) = B[n*ldb + k]      B MN-major: B(n,k) = B[k*ldb + n]
+// so  forward linear  y = x W^T        -> (A K, B K)
+//     data gradient   dx = dy W        -> (A K, B MN)
+//     weight gradient dW = dy^T x      -> (A MN, B MN)
+//
+// Two implementations, both sm_100a CUDA, chosen by the precision mode (not by backend):
+//   * gemm_simt_kernel  — fp32 FFMA tiles; the fp32 parity mode (1e-4 / exact argmax) and any shape
+//                         TMA cannot describe (row pitch not a multiple of 16 bytes).
+//   * gemm_tc_kernel    — bf16 operands staged by TMA (SWIZZLE_128B) into a 4-stage mbarrier ring,
+//                         tcgen05.mma (cta_group::1, M=128, N=64/128/256, K=16) accumulating fp32 in TMEM,
+//                         tcgen05.ld epilogue with fused alpha / bias / ReLU / beta.
+#pragma once
+#include "common.cuh"
+
+namespace b2c {
+
+// ======================================================================================
+// SIMT fp32-accumulate GEMM (any operand type, any majorness)
+// ======================================================================================
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
+
+template <typename TA, typename TB, typename TC>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(int M, int N, int K, float alpha, const TA* __restrict__ A, long lda, int a_mn,
+                 const TB* __restrict__ B, long ldb, int b_mn, float beta, TC* __restrict__ C, long ldc,
+                 const float* __restrict__ bias, int relu) {
+  __shared__ float As[SG_BK][SG_BM + 4];
+  __shared__ float Bs[SG_BK][SG_BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  const int tx = tid & 15, ty = tid >> 4;      // 16 x 16 threads, 4x4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += SG_BK) {
+#pragma unroll
+    for (int it = 0; it < (SG_BM * SG_BK) / 256; ++it) {
+      const int idx = tid + it * 256;
+      int mm, kk;
+      if (a_mn) { kk = idx / SG_BM; mm = idx % SG_BM; } else { mm = idx / SG_BK; kk = idx % SG_BK; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < M && gk < K) v = to_f<TA>(a_mn ? A[(long)gk * lda + gm] : A[(long)gm * lda + gk]);
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int it = 0; it < (SG_BN * SG_BK) / 256; ++it) {
+      const int idx = tid + it * 256;
+      int nn, kk;
+      if (b_mn) { kk = idx / SG_BN; nn = idx % SG_BN; } else { nn = idx / SG_BK; kk = idx % SG_BK; }
+      const int gn = n0 + nn, gk = k0 + kk;
+      float v = 0.f;
+      if (gn < N && gk < K) v = to_f<TB>(b_mn ? B[(long)gk * ldb + gn] : B[(long)gn * ldb + gk]);
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SG_BK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = alpha * acc[i][j];
+      if (bias) v += bias[gn];
+      if (relu) v = fmaxf(v, 0.f);
+      if (beta != 0.f) v += beta * to_f<TC>(C[(long)gm * ldc + gn]);
+      C[(long)gm * ldc + gn] = from_f<TC>(v);
+    }
+  }
+}
+
+// ======================================================================================
+// tcgen05 / TMEM / TMA bf16 GEMM
+// ======================================================================================
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4, TC_THREADS = 192;
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;     // 16 KiB per stage
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               :: "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor (SM100 UMMA), SWIZZLE_128B, version 1.
+//   K-major  tile: rows of 64 bf16 (128 B), 8-row swizzle atoms 1024 B apart      -> SBO = 1024, LBO unused (1)
+//   MN-major tile: K-rows of 64 MN elements (128 B); 8-K-row atoms 1024 B apart (SBO),
+//                  consecutive 64-wide MN chunks `lbo` bytes apart (LBO)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;          // layout type SWIZZLE_128B
+  return d;
+}
+
+template <int BN> struct TcCfg {
+  static constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+  static constexpr uint32_t STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr size_t SMEM_BYTES = (size_t)TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool A_MN, bool B_MN, typename TC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               int M, int N, int K, float alpha, float beta, TC* __restrict__ C, long ldc,
+               const float* __restrict__ bias, int relu) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + (size_t)TC_STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int num_kb = (K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % TC_STAGES; const uint32_t ph = (kb / TC_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        unsigned char* sa = base + (size_t)s * Cfg::STAGE_BYTES;
+        unsigned char* sb = sa + TC_A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        const int k0 = kb * TC_BK;
+        if (!A_MN) {
+          tma_load_2d(sa, &tmA, k0, m0, &full_bar[s]);                      // box {64 k, 128 m}
+        } else {
+#pragma unroll
+          for (int j = 0; j < TC_BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, m0 + j * 64, k0, &full_bar[s]);   // box {64 m, 64 k}
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, &tmB, k0, n0, &full_bar[s]);                      // box {64 k, BN n}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, n0 + j * 64, k0, &full_bar[s]);      // box {64 n, 64 k}
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % TC_STAGES; const uint32_t ph = (kb / TC_STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(base + (size_t)s * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t adesc = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+          tc_mma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);              // frees the smem slot once these MMAs have read it
+      }
+      tc_commit(tmem_full_bar);                // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------ epilogue: warps 2..5 -> TMEM lane quarters (warp % 4)
+    const int q = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = m0 + q * 32 + lane;
+    const bool vec_ok = (((uintptr_t)C) % 16 == 0) && ((ldc * sizeof(TC)) % 16 == 0) && (beta == 0.f);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      const int col0 = n0 + c0;
+      if (row < M && col0 < N) {
+        const bool full = (col0 + 32 <= N);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = alpha * v[j];
+          if (bias && (full || col0 + j < N)) x += bias[col0 + j];
+          if (relu) x = fmaxf(x, 0.f);
+          v[j] = x;
+        }
+        TC* crow = C + (long)row * ldc + col0;
+        if (full && vec_ok) {
+          if (sizeof(TC) == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 o = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(crow) + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(crow) + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        } else {
+          for (int j = 0; j < 32; ++j) {
+            if (col0 + j < N) {
+              float x = v[j];
+              if (beta != 0.f) x += beta * to_f<TC>(crow[j]);
+              crow[j] = from_f<TC>(x);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner (contiguous) extent `inner`, `outer` rows of pitch `ld` elements; box {64, box_outer}.
+inline int make_tmap_bf16(CUtensorMap* map, const void* ptr, long inner, long outer, long ld, int box_outer) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return set_err(B2C_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(B2C_ECUDA, "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%ld outer=%ld ld=%ld box=%d", (int)r, ptr, inner, outer, ld, box_outer);
+  return 0;
+}
+
+struct GemmArgs {
+  int M, N, K;
+  float alpha, beta;
+  const void* A; long lda; int a_mn;
+  const void* B; long ldb; int b_mn;
+  void* C; long ldc;
+  const float* bias; int relu;
+};
+
+inline bool tc_eligible(const GemmArgs& g) {
+  return ((uintptr_t)g.A % 16 == 0) && ((uintptr_t)g.B % 16 == 0) && (g.lda % 8 == 0) && (g.ldb % 8 == 0);
+}
+
+template <int BN, bool A_MN, bool B_MN, typename TC>
+int launch_tc(const GemmArgs& g, cudaStream_t st) {
+  CUtensorMap ta, tb;
+  if (!A_MN) B2C_TRY(make_tmap_bf16(&ta, g.A, g.K, g.M, g.lda, TC_BM)); else B2C_TRY(make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, 64));
+  if (!B_MN) B2C_TRY(make_tmap_bf16(&tb, g.B, g.K, g.N, g.ldb, BN)); else B2C_TRY(make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, 64));
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TC>;
+  static bool attr_set = false;      // per template instantiation
+  if (!attr_set) {
+    B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<BN>::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(g.N, BN), cdiv(g.M, TC_BM));
+  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ta, tb, g.M, g.N, g.K, g.alpha, g.beta, (TC*)g.C, g.ldc, g.bias, g.relu);
+  B2C_LAUNCH_CHECK("gemm_tc_kernel");
+  return 0;
+}
+
+template <int BN, typename TC>
+int launch_tc_major(const GemmArgs& g, cudaStream_t st) {
+  if (!g.a_mn && !g.b_mn) return launch_tc<BN, false, false, TC>(g, st);
+  if (!g.a_mn && g.b_mn) return launch_tc<BN, false, true, TC>(g, st);
+  if (g.a_mn && g.b_mn) return launch_tc<BN, true, true, TC>(g, st);
+  return launch_tc<BN, true, false, TC>(g, st);
+}
+
+// bf16 operands on tensor cores; TC = bf16 or float output.
+template <typename TC>
+int gemm_bf16_tc(const GemmArgs& g, cudaStream_t st) {
+  const long tiles128 = (long)cdiv(g.M, TC_BM) * cdiv(g.N, 128);
+  if (g.N <= 64 || tiles128 < 120) return launch_tc_major<64, TC>(g, st);
+  return launch_tc_major<128, TC>(g, st);
+}
+
+template <typename TA, typename TB, typename TC>
+int gemm_simt(const GemmArgs& g, cudaStream_t st) {
+  dim3 grid(cdiv(g.N, SG_BN), cdiv(g.M, SG_BM));
+  gemm_simt_kernel<TA, TB, TC><<<grid, 256, 0, st>>>(g.M, g.N, g.K, g.alpha, (const TA*)g.A, g.lda, g.a_mn,
+                                                      (const TB*)g.B, g.ldb, g.b_mn, g.beta, (TC*)g.C, g.ldc, g.bias, g.relu);
+  B2C_LAUNCH_CHECK("gemm_simt_kernel");
+  return 0;
+}
+
+// Precision-mode dispatch used by the decoder: T = operand type, TC = output type.
+template <typename T, typename TC> struct Gemm;
+template <typename TC> struct Gemm<float, TC> {
+  static int run(const GemmArgs& g, cudaStream_t st) { return gemm_simt<float, float, TC>(g, st); }
+};
+template <typename TC> struct Gemm<bf16, TC> {
+  static int run(const GemmArgs& g, cudaStream_t st) {
+    if (tc_eligible(g)) return gemm_bf16_tc<TC>(g, st);
+    return gemm_simt<bf16, bf16, TC>(g, st);     // row pitch TMA cannot describe (e.g. odd vocab): CUDA-core tiles
+  }
+};
+
+}  // namespace b2c

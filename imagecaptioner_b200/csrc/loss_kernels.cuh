@@ -1,0 +1,317 @@
+// Kernels (3) and (4) of the hot path: the streaming token-KD + CE pass and the fused
+// feature/hidden KD reduction.  Math: SURVEY.md Appendix A.3, reference
+// src/distillation_utils.py:30-54 (token KD), :154 (CE), :56-94 (feature KD), :96-136 (hidden KD).
+#pragma once
+#include "common.cuh"
+
+namespace b2c {
+
+constexpr int KD_THREADS = 128;
+
+// ---- row IO helpers: G = 8 (vectorised, 16-byte accesses) or G = 1 (any V / alignment) -------------
+template <typename TS, int G> struct RowIO;
+template <> struct RowIO<float, 8> {
+  static __device__ __forceinline__ void load(const float* s, int base, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(s + base), b = *reinterpret_cast<const float4*>(s + base + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store_s(float* s, int base, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(s + base) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(s + base + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  static __device__ __forceinline__ void store_g(float* g, long base, const float (&v)[8]) {
+    uint4 a = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+    uint4 b = make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+    st_na_v4(g + base, a); st_na_v4(g + base + 4, b);
+  }
+};
+template <> struct RowIO<bf16, 8> {
+  static __device__ __forceinline__ void load(const bf16* s, int base, float (&v)[8]) {
+    const uint4 a = *reinterpret_cast<const uint4*>(s + base);
+    v[0] = bf16_lo(a.x); v[1] = bf16_hi(a.x); v[2] = bf16_lo(a.y); v[3] = bf16_hi(a.y);
+    v[4] = bf16_lo(a.z); v[5] = bf16_hi(a.z); v[6] = bf16_lo(a.w); v[7] = bf16_hi(a.w);
+  }
+  static __device__ __forceinline__ void store_g(bf16* g, long base, const float (&v)[8]) {
+    uint4 a = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    st_na_v4(g + base, a);
+  }
+};
+template <typename TS> struct RowIO<TS, 1> {
+  static __device__ __forceinline__ void load(const TS* s, int base, float (&v)[1]) { v[0] = to_f<TS>(s[base]); }
+  static __device__ __forceinline__ void store_s(float* s, int base, const float (&v)[1]) { s[base] = v[0]; }
+  static __device__ __forceinline__ void store_g(TS* g, long base, const float (&v)[1]) { g[base] = from_f<TS>(v[0]); }
+};
+
+__device__ __forceinline__ float block_reduce_sum4(float& a, float& b, float& c, float& d, float* scratch) {
+  // KD_THREADS/32 warps; every thread returns with all four totals
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) { scratch[w * 4 + 0] = a; scratch[w * 4 + 1] = b; scratch[w * 4 + 2] = c; scratch[w * 4 + 3] = d; }
+  __syncthreads();
+  a = b = c = d = 0.f;
+#pragma unroll
+  for (int i = 0; i < KD_THREADS / 32; ++i) { a += scratch[i * 4]; b += scratch[i * 4 + 1]; c += scratch[i * 4 + 2]; d += scratch[i * 4 + 3]; }
+  return a;
+}
+
+// Kernel (3).  One CTA per logits row r = t*B + b (time-major, view(-1,V) of a contiguous (T,B,V)).
+// The row of student logits y and teacher logits z is brought into shared memory ONCE (1-D TMA bulk
+// copies when rows are 16-byte aligned) and all three passes (max, sums, gradient) run out of smem, so
+// HBM traffic is exactly: read y, read z, write dy.
+//   KL_r  = sum_v pT (log pT - log pS),  pS = softmax(y/Temp), pT = softmax(z/Temp)
+//   CE_r  = logsumexp(y) - y[tgt]                       (tgt != PAD)
+//   dy_v  = kd_coef (pS_v - pT_v) + ce_coef (softmax(y)_v - [v == tgt])
+// with kd_coef = alpha*Temp/N and ce_coef = w_ce / n_valid (0 on PAD rows).
+template <typename TS, int G, bool TEMP4>
+__global__ void __launch_bounds__(KD_THREADS)
+kd_token_loss_kernel(const TS* __restrict__ y, const float* __restrict__ z, const int64_t* __restrict__ tgt,
+                     int V, float inv_temp, float kd_coef, float w_ce, const int* __restrict__ n_valid_ptr,
+                     TS* __restrict__ dy, float* __restrict__ row_kl, float* __restrict__ row_ce) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* zs = reinterpret_cast<float*>(smem_raw);                             // V floats
+  TS* ys = reinterpret_cast<TS*>(smem_raw + align_up((size_t)V * 4, 16)); // V TS
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ float scratch[KD_THREADS / 32 * 4];
+
+  const int tid = threadIdx.x;
+  const long r = blockIdx.x;
+  const TS* yg = y + r * (long)V;
+  const float* zg = z + r * (long)V;
+
+  if (G == 8) {
+    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bar, (uint32_t)(V * 4 + V * sizeof(TS)));
+      bulk_g2s(zs, zg, (uint32_t)(V * 4), &bar);
+      bulk_g2s(ys, yg, (uint32_t)(V * sizeof(TS)), &bar);
+    }
+    mbar_wait(&bar, 0);
+  } else {
+    for (int v = tid; v < V; v += KD_THREADS) { zs[v] = zg[v]; ys[v] = yg[v]; }
+    __syncthreads();
+  }
+
+  const long t64 = tgt[r];
+  const bool valid = (t64 != 0) && (t64 > 0) && (t64 < V);
+  const int t_idx = valid ? (int)t64 : 0;
+  const float y_tgt = to_f<TS>(ys[t_idx]);
+  const int groups = V / G;
+
+  // pass 1: row maxima
+  float my = -INFINITY, mz = -INFINITY;
+  for (int g = tid; g < groups; g += KD_THREADS) {
+    float yv[G], zv[G];
+    RowIO<TS, G>::load(ys, g * G, yv);
+    RowIO<float, G>::load(zs, g * G, zv);
+#pragma unroll
+    for (int i = 0; i < G; ++i) { my = fmaxf(my, yv[i]); mz = fmaxf(mz, zv[i]); }
+  }
+  my = warp_max(my); mz = warp_max(mz);
+  {
+    const int w = tid >> 5, l = tid & 31;
+    if (l == 0) { scratch[w * 2] = my; scratch[w * 2 + 1] = mz; }
+    __syncthreads();
+    my = scratch[0]; mz = scratch[1];
+#pragma unroll
+    for (int i = 1; i < KD_THREADS / 32; ++i) { my = fmaxf(my, scratch[i * 2]); mz = fmaxf(mz, scratch[i * 2 + 1]); }
+  }
+
+  // pass 2: partition sums; e^{z'} is written back over z (and e^{y'} over y when y is fp32)
+  float sT = 0.f, sZ = 0.f, sA = 0.f, s1 = 0.f;
+  for (int g = tid; g < groups; g += KD_THREADS) {
+    float yv[G], zv[G];
+    RowIO<TS, G>::load(ys, g * G, yv);
+    RowIO<float, G>::load(zs, g * G, zv);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const float yd = yv[i] - my, zd = (zv[i] - mz) * inv_temp;
+      const float ey = __expf(yd * inv_temp), ez = __expf(zd);
+      float e1;
+      if (TEMP4) { const float e2 = ey * ey; e1 = e2 * e2; } else { e1 = __expf(yd); }
+      sT += ey; sZ += ez; sA += ez * (zd - yd * inv_temp); s1 += e1;
+      zv[i] = ez; yv[i] = ey;
+    }
+    RowIO<float, G>::store_s(zs, g * G, zv);
+    if (sizeof(TS) == 4) RowIO<float, G>::store_s(reinterpret_cast<float*>(ys), g * G, yv);
+  }
+  block_reduce_sum4(sT, sZ, sA, s1, scratch);
+
+  const float inv_sT = 1.0f / sT, inv_sZ = 1.0f / sZ, inv_s1 = 1.0f / s1;
+  const int n_valid = *n_valid_ptr;
+  const float ce_coef = (valid && n_valid > 0) ? w_ce / (float)n_valid : 0.0f;
+  if (tid == 0) {
+    row_kl[r] = sA * inv_sZ - __logf(sZ) + __logf(sT);
+    row_ce[r] = valid ? (__logf(s1) + my - y_tgt) : 0.0f;
+  }
+
+  // pass 3: gradient
+  TS* dyg = dy + r * (long)V;
+  const float a_s = kd_coef * inv_sT, a_t = kd_coef * inv_sZ, a_c = ce_coef * inv_s1;
+  for (int g = tid; g < groups; g += KD_THREADS) {
+    float yv[G], zv[G], o[G];
+    RowIO<TS, G>::load(ys, g * G, yv);
+    RowIO<float, G>::load(zs, g * G, zv);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      float ey, e1;
+      if (sizeof(TS) == 4) { ey = yv[i]; } else { ey = __expf((yv[i] - my) * inv_temp); }
+      if (TEMP4) { const float e2 = ey * ey; e1 = e2 * e2; }
+      else { e1 = (sizeof(TS) == 4) ? __powf(ey, 1.0f / inv_temp) : __expf(yv[i] - my); }
+      float gval = a_s * ey - a_t * zv[i] + a_c * e1;
+      if (g * G + i == t_idx) gval -= ce_coef;
+      o[i] = gval;
+    }
+    RowIO<TS, G>::store_g(dyg, (long)g * G, o);
+  }
+}
+
+__global__ void count_valid_kernel(const int64_t* __restrict__ tgt, long n, int V, int* __restrict__ out) {
+  __shared__ int part[32];
+  int c = 0;
+  for (long i = threadIdx.x; i < n; i += blockDim.x) { const long t = tgt[i]; c += (t > 0 && t < V) ? 1 : 0; }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { int s = 0; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += part[i]; *out = s; }
+}
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+// Kernel (4).  blockIdx < B : feature KD for sample b (256 threads);  blockIdx >= B : hidden KD, one warp per
+// (t,b) row.  Gradients already carry beta / gamma; loss partials go to workspace for the finalize kernel.
+template <typename TF, typename TH>
+__global__ void __launch_bounds__(256)
+aux_loss_kernel(const TF* __restrict__ fs, const float* __restrict__ ft, int B, int Ss, int St, int E,
+                const TH* __restrict__ hs, const float* __restrict__ ht, int n_hid_rows /*Th*B*/, int n_all_rows /*T*B*/,
+                int H, int Th, float beta, float gamma,
+                float* __restrict__ dfs, float* __restrict__ dft, TH* __restrict__ dhs,
+                float* __restrict__ feat_part /*B*2*/, float* __restrict__ hid_part /*n_hid_rows*2*/) {
+  extern __shared__ float sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  if ((int)blockIdx.x < B) {
+    if (fs == nullptr) return;
+    const int b = blockIdx.x;
+    const TF* S = fs + (long)b * Ss * E;
+    const float* Tp = ft + (long)b * St * E;
+    float* ps = sm;             // Ss   softmax weights (student)
+    float* pt = ps + Ss;        // St
+    float* dg = pt + St;        // E    delta of global means
+    float* da = dg + E;         // E    delta of attention-pooled
+    float* qs = da + E;         // Ss
+    float* qt = qs + Ss;        // St
+    __shared__ float red[16];
+    // 1. token row sums
+    for (int l = warp; l < Ss; l += nwarp) { float a = 0.f; for (int e = lane; e < E; e += 32) a += to_f<TF>(S[(long)l * E + e]); a = warp_sum(a); if (lane == 0) ps[l] = a; }
+    for (int l = warp; l < St; l += nwarp) { float a = 0.f; for (int e = lane; e < E; e += 32) a += Tp[(long)l * E + e]; a = warp_sum(a); if (lane == 0) pt[l] = a; }
+    __syncthreads();
+    // 2. softmax over tokens (warp 0: student, warp 1: teacher)
+    if (warp < 2) {
+      float* p = warp == 0 ? ps : pt; const int n = warp == 0 ? Ss : St;
+      float m = -INFINITY; for (int l = lane; l < n; l += 32) m = fmaxf(m, p[l]); m = warp_max(m);
+      float s = 0.f; for (int l = lane; l < n; l += 32) { const float e = expf(p[l] - m); p[l] = e; s += e; } s = warp_sum(s);
+      const float inv = 1.0f / s; for (int l = lane; l < n; l += 32) p[l] *= inv;
+    }
+    __syncthreads();
+    // 3. pooled vectors and their deltas
+    float acc_g = 0.f, acc_a = 0.f;
+    for (int e = tid; e < E; e += blockDim.x) {
+      float gs = 0.f, as = 0.f, gt = 0.f, at = 0.f;
+      for (int l = 0; l < Ss; ++l) { const float v = to_f<TF>(S[(long)l * E + e]); gs += v; as += ps[l] * v; }
+      for (int l = 0; l < St; ++l) { const float v = Tp[(long)l * E + e]; gt += v; at += pt[l] * v; }
+      const float d_g = gs / (float)Ss - gt / (float)St, d_a = as - at;
+      dg[e] = d_g; da[e] = d_a; acc_g += d_g * d_g; acc_a += d_a * d_a;
+    }
+    acc_g = warp_sum(acc_g); acc_a = warp_sum(acc_a);
+    if (lane == 0) { red[warp * 2] = acc_g; red[warp * 2 + 1] = acc_a; }
+    __syncthreads();
+    if (tid == 0) { float g = 0.f, a = 0.f; for (int i = 0; i < nwarp; ++i) { g += red[i * 2]; a += red[i * 2 + 1]; } feat_part[b * 2] = g; feat_part[b * 2 + 1] = a; }
+    // 4. gradients
+    const float inv_be = 1.0f / ((float)B * (float)E);
+    const float ca = 0.4f * 2.0f * inv_be, cg = 0.6f * 2.0f * inv_be;
+    for (int l = warp; l < Ss; l += nwarp) { float a = 0.f; for (int e = lane; e < E; e += 32) a += da[e] * to_f<TF>(S[(long)l * E + e]); a = warp_sum(a); if (lane == 0) qs[l] = ca * a; }
+    for (int l = warp; l < St; l += nwarp) { float a = 0.f; for (int e = lane; e < E; e += 32) a += da[e] * Tp[(long)l * E + e]; a = warp_sum(a); if (lane == 0) qt[l] = ca * a; }
+    __syncthreads();
+    float qsbar = 0.f, qtbar = 0.f;
+    for (int l = 0; l < Ss; ++l) qsbar += ps[l] * qs[l];
+    for (int l = 0; l < St; ++l) qtbar += pt[l] * qt[l];
+    if (dfs != nullptr) {
+      float* D = dfs + (long)b * Ss * E;
+      for (int i = tid; i < Ss * E; i += blockDim.x) {
+        const int l = i / E, e = i - l * E;
+        D[i] = beta * (cg / (float)Ss * dg[e] + ca * da[e] * ps[l] + ps[l] * (qs[l] - qsbar));
+      }
+    }
+    if (dft != nullptr) {
+      float* D = dft + (long)b * St * E;
+      for (int i = tid; i < St * E; i += blockDim.x) {
+        const int l = i / E, e = i - l * E;
+        D[i] = -beta * (cg / (float)St * dg[e] + ca * da[e] * pt[l] + pt[l] * (qt[l] - qtbar));
+      }
+    }
+  } else {
+    if (hs == nullptr) return;
+    const long row = (long)(blockIdx.x - B) * nwarp + warp;
+    if (row >= n_all_rows) return;
+    const TH* s = hs + row * H;
+    TH* d = dhs ? dhs + row * H : nullptr;
+    if (row >= n_hid_rows) {                     // student steps beyond the teacher's list: no loss, zero grad
+      if (d) for (int h = lane; h < H; h += 32) d[h] = from_f<TH>(0.f);
+      return;
+    }
+    const float* t = ht + row * H;
+    float sq = 0.f, dot = 0.f, ns = 0.f, nt = 0.f;
+    for (int h = lane; h < H; h += 32) { const float a = to_f<TH>(s[h]), c = t[h]; const float df = a - c; sq += df * df; dot += a * c; ns += a * a; nt += c * c; }
+    sq = warp_sum(sq); dot = warp_sum(dot); ns = warp_sum(ns); nt = warp_sum(nt);
+    const float eps = 1e-12f;
+    const float nse = ns + eps, nte = nt + eps;
+    const float inv_norm = rsqrtf(nse * nte);
+    const float cosv = dot * inv_norm;
+    if (lane == 0) { hid_part[row * 2] = sq; hid_part[row * 2 + 1] = 1.0f - cosv; }
+    if (d) {
+      const float c_mse = gamma / (float)Th * 0.7f * 2.0f / ((float)B * (float)H);
+      const float c_cos = gamma / (float)Th * 0.3f / (float)B;
+      for (int h = lane; h < H; h += 32) {
+        const float a = to_f<TH>(s[h]), c = t[h];
+        d[h] = from_f<TH>(c_mse * (a - c) - c_cos * (c * inv_norm - cosv * a / nse));
+      }
+    }
+  }
+}
+
+// Deterministic fixed-order reduction of all loss partials -> out5 = {total, ce, token_kd, feature_kd, hidden_kd}.
+__global__ void __launch_bounds__(1024)
+loss_finalize_kernel(const float* __restrict__ row_kl, const float* __restrict__ row_ce, long N, const int* __restrict__ n_valid_ptr,
+                     const float* __restrict__ feat_part, int B, int E, int has_feat,
+                     const float* __restrict__ hid_part, long n_hid_rows, int H, int Th, int has_hid,
+                     float temperature, float alpha, float beta, float gamma, float w_ce, float* __restrict__ out5) {
+  __shared__ double red[32][5];
+  double kl = 0, ce = 0, fg = 0, fa = 0, hm = 0, hc = 0;
+  for (long i = threadIdx.x; i < N; i += blockDim.x) { kl += row_kl[i]; ce += row_ce[i]; }
+  if (has_feat) for (long i = threadIdx.x; i < B; i += blockDim.x) { fg += feat_part[i * 2]; fa += feat_part[i * 2 + 1]; }
+  if (has_hid) for (long i = threadIdx.x; i < n_hid_rows; i += blockDim.x) { hm += hid_part[i * 2]; hc += hid_part[i * 2 + 1]; }
+  double v[5] = {kl, ce, 0.6 * fg + 0.4 * fa, hm, hc};
+  for (int k = 0; k < 5; ++k) for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  if ((threadIdx.x & 31) == 0) for (int k = 0; k < 5; ++k) red[threadIdx.x >> 5][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s[5] = {0, 0, 0, 0, 0};
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) for (int k = 0; k < 5; ++k) s[k] += red[w][k];
+    const int nv = *n_valid_ptr;
+    const double kd_l = (double)temperature * temperature * s[0] / (double)N;
+    const double ce_l = s[1] / (double)nv;                       // 0/0 -> NaN like the reference when every target is PAD
+    const double ft_l = has_feat ? s[2] / ((double)B * E) : 0.0;
+    const double hd_l = has_hid ? (0.7 * s[3] / ((double)B * H) + 0.3 * s[4] / (double)B) / (double)Th : 0.0;
+    out5[0] = (float)((double)w_ce * ce_l + (double)alpha * kd_l + (double)beta * ft_l + (double)gamma * hd_l);
+    out5[1] = (float)ce_l; out5[2] = (float)kd_l; out5[3] = (float)ft_l; out5[4] = (float)hd_l;
+  }
+}
+
+// y *= *scale (device scalar): applies autograd's incoming grad_output to a precomputed gradient.
+template <typename T>
+__global__ void scale_inplace_kernel(T* __restrict__ p, long n, const float* __restrict__ scale) {
+  const float s = *scale;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = from_f<T>(to_f<T>(p[i]) * s);
+}
+
+}  // namespace b2c
