@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""KD train-step throughput of the B200-native hot path (BASELINE.json metric: KD train samples/sec).
+
+One "step" = one pass of the hot path over one synthetic batch, replaying the reference's training step
+(src/train_student_kd.py:262-303) with the encoders outside the path: refinement + attention-LSTM decoder
+forward, FeatureProjector, DistillationLoss (all four terms), backward to every decoder / refinement /
+projector parameter and the encoder features, gradient all-reduce (N>1), global-norm clip and AdamW.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]              # our arm  (torchrun launches N>1)
+  python bench.py --impl reference ...                             # the reference algorithm on the host CPU cores
+
+Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM; `e2e` = the same step through the
+public modules with every step's inputs copied from pinned host memory and the loss read back.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# BASELINE.json configs[1]: default student, batch 512 per GPU, len 20, vocab 5000, ViT-small teacher features 197x384
+CFG = dict(B=512, T=20, V=5000, E=256, H=512, L=2, S=49, St=197, Et=384)
+METRIC = "kd_train_samples_per_sec"
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(cfg, seed, dtype_teacher=torch.float32):
+    from oracle import kd_oracle as O   # synthetic-input generator shared with the tests (data only, no compute)
+    return O.synthetic_batch(cfg["B"], cfg["T"], cfg["V"], cfg["E"], cfg["H"], cfg["S"], cfg["St"], cfg["Et"], seed=seed)
+
+
+# ---------------------------------------------------------------------------------------------- reference arm (CPU)
+def run_reference(args):
+    """The reference algorithm (oracle port: plain tensor arithmetic + autograd on the host CPU) for the same step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import kd_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    Bs = 16                                                   # bounded sample: BASELINE configs[0] batch (the reference loader's own cap)
+    cfg = dict(CFG, B=Bs)
+    params = O.init_student_params(cfg["V"], cfg["E"], cfg["H"], cfg["L"], True, seed=0)
+    pparams = O.init_projector_params(cfg["Et"], cfg["E"], seed=1)
+    batch = make_batch(cfg, 1234)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in {**params, **{"proj." + k: v for k, v in pparams.items()}}.items()}
+    opt = torch.optim.AdamW(list(leaves.values()), lr=1e-4, weight_decay=0.01)
+
+    def step():
+        P = {k: v for k, v in leaves.items() if not k.startswith("proj.")}
+        Q = {k[5:]: v for k, v in leaves.items() if k.startswith("proj.")}
+        feats = batch["encoder_features"].clone().requires_grad_(True)
+        outputs, enc, hids, _ = O.student_forward(P, feats, batch["captions_input"], True)
+        tproj = O.feature_projector(Q, batch["teacher_features"], cfg["S"])
+        th = batch["teacher_hiddens"]
+        total, _ = O.distillation_loss({"logits": outputs, "encoder_features": enc, "hidden_states": hids},
+                                       {"logits": batch["teacher_logits"], "encoder_features": tproj,
+                                        "hidden_states": [th[t] for t in range(th.shape[0])]}, batch["targets"])
+        opt.zero_grad(set_to_none=True)
+        total.backward()
+        torch.nn.utils.clip_grad_norm_(list(leaves.values()), 1.0)
+        opt.step()
+        return float(total.detach())
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = Bs / dt
+    sample = f"B={Bs} (configs[0] batch) of the configs[1] model, T=20 V=5000, fp32, {threads} threads, per-sample rate"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": "BASELINE configs[1]: CaptioningStudent default (E256 H512 2-layer LSTM, 49x256 feats, refinement) KD train step, "
+                        "batch 512/GPU, len 20, vocab 5000, synthetic ViT-small teacher logits + 197x384 features + hidden states, bf16 compute / fp32 master",
+            "per_gpu_batch": CFG["B"], "global_batch": CFG["B"] * n, "seq_len": CFG["T"], "vocab": CFG["V"], "parallelism": f"dp{n}",
+            "step": "refinement+decoder fwd, projector, 4-term KD loss, bwd, grad allreduce, clip, AdamW",
+            "l2_policy": "inputs per step (~410 MB logits+teacher) exceed the 126 MB L2; no explicit flush"}
+
+
+# ---------------------------------------------------------------------------------------------- our arm (GPU)
+def cpu_baseline(budget_s=20.0):
+    """Oracle port on the host cores, bounded sample (rank 0, N=1 only)."""
+    from oracle import kd_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = dict(CFG, B=16)
+    params = O.init_student_params(cfg["V"], cfg["E"], cfg["H"], cfg["L"], True, seed=0)
+    pparams = O.init_projector_params(cfg["Et"], cfg["E"], seed=1)
+    batch = make_batch(cfg, 1234)
+    O.kd_step(params, pparams, batch)                       # warm-up
+    t0, n = time.perf_counter(), 0
+    while n < 3 or (time.perf_counter() - t0 < budget_s and n < 40):
+        O.kd_step(params, pparams, batch); n += 1
+    dt = (time.perf_counter() - t0) / n
+    return {"value": 16 / dt, "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"{n} fwd+loss+bwd steps of B=16 (configs[0]) T=20 V=5000 fp32 with the oracle port, {threads} threads; per-sample rate"}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from imagecaptioner_b200 import _ops
+    from imagecaptioner_b200.ddp import FlatGradAllReducer, attach_loss_group
+    from imagecaptioner_b200.distillation_utils import DistillationLoss
+    from oracle import kd_oracle as O
+    from tests.harness import build_student
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N>1"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _ops.load_library()
+    cfg = CFG
+    B, T, V, E, H, L = cfg["B"], cfg["T"], cfg["V"], cfg["E"], cfg["H"], cfg["L"]
+    params = O.init_student_params(V, E, H, L, True, seed=0)
+    pparams = O.init_projector_params(cfg["Et"], E, seed=1)
+    model, projector = build_student(params, pparams, V, E, H, L, True, cfg["Et"], dev)   # eval(): dropout off (parity config)
+    model.decoder.compute_dtype = torch.bfloat16
+    loss_mod = DistillationLoss(0.7, 0.2, 0.1, 4.0, vocab_size=V)
+    attach_loss_group(loss_mod)
+    trainable = [p for p in list(model.parameters()) + list(projector.parameters()) if p.requires_grad]
+    reducer = FlatGradAllReducer(trainable)
+    opt = torch.optim.AdamW(trainable, lr=1e-4, weight_decay=0.01, fused=True)
+
+    host = make_batch(cfg, 1234 + rank)
+    keys = ["encoder_features", "captions_input", "targets", "teacher_logits", "teacher_features", "teacher_hiddens"]
+    pinned = {k: host[k].pin_memory() for k in keys}
+    resident = {k: pinned[k].to(dev, non_blocking=True) for k in keys}
+    h2d_bytes = sum(pinned[k].numel() * pinned[k].element_size() for k in keys)
+    loss_host = torch.zeros(5, dtype=torch.float32).pin_memory()
+
+    def step(inp):
+        feats = inp["encoder_features"].requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):             # the reference's loop runs under autocast (train_student_kd.py:271)
+            outputs, enc, hids, _ = model(feats, inp["captions_input"])
+            tproj = projector(inp["teacher_features"])
+        th = inp["teacher_hiddens"]
+        loss, out5 = loss_mod.forward_device({"logits": outputs, "encoder_features": enc, "hidden_states": hids},
+                                             {"logits": inp["teacher_logits"], "encoder_features": tproj, "hidden_states": th}, inp["targets"])
+        reducer.zero_grad()
+        loss.backward()
+        reducer.allreduce()
+        gn = reducer.flat.norm()
+        reducer.flat.mul_(torch.clamp(1.0 / (gn + 1e-6), max=1.0))           # clip_grad_norm_(.., 1.0) on the flat buffer, no host sync
+        opt.step()
+        return out5
+
+    def barrier_sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM
+    for _ in range(max(args.warmup, 3)):
+        step({k: (v.detach().clone() if k == "encoder_features" else v) for k, v in resident.items()})
+    barrier_sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.b2c_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier_sync()
+    ev0.record()
+    for _ in range(args.steps):
+        out5 = step({k: (v.detach() if k == "encoder_features" else v) for k, v in resident.items()})
+    ev1.record()
+    barrier_sync()
+    ms = ev0.elapsed_time(ev1)
+    launches = (lib.b2c_launch_count() - n0)
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / args.steps
+    value = B * world / (ms_step * 1e-3)
+    final_loss = out5.tolist()
+
+    # ---- e2e: every step's inputs come from pinned host memory, the loss goes back to the host
+    copy_stream = torch.cuda.Stream()
+
+    def upload():
+        with torch.cuda.stream(copy_stream):
+            bufs = {k: pinned[k].to(dev, non_blocking=True) for k in keys}
+            evt = torch.cuda.Event(); evt.record(copy_stream)
+        return bufs, evt
+
+    def e2e_loop(n):
+        nxt = upload()
+        for i in range(n):
+            bufs, evt = nxt
+            torch.cuda.current_stream().wait_event(evt)
+            for b in bufs.values():
+                b.record_stream(torch.cuda.current_stream())
+            if i + 1 < n:
+                nxt = upload()                                     # prefetch the next step's inputs behind this step's compute
+            o5 = step(bufs)
+            loss_host.copy_(o5, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_loop(2)
+    barrier_sync()
+    t0 = time.perf_counter()
+    ev0.record()
+    e2e_loop(args.steps)
+    ev1.record()
+    barrier_sync()
+    e_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = B * world / (float(e_ms.item()) / args.steps * 1e-3)
+
+    # ---- roofline of the named kernels, timed live with CUDA events on the launching stream
+    peaks = read_peaks()
+    roof, extra = None, {}
+    if rank == 0:
+        roof, extra = kernel_rooflines(lib, _ops, dev, cfg, peaks)
+    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 20},
+            "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+            "roofline": roof, "kernels": extra, "loss": final_loss}
+    if rank == 0:
+        line["cpu_baseline"] = cpu_baseline() if world == 1 and not args.no_cpu_baseline else None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_rooflines(lib, _ops, dev, cfg, peaks):
+    """Per-kernel achieved bandwidth / FLOP rate: algorithmic bytes / CUDA-event time per launch."""
+    B, T, V, E, H = cfg["B"], cfg["T"], cfg["V"], cfg["E"], cfg["H"]
+    N = T * B
+    st = torch.cuda.current_stream().cuda_stream
+    y = torch.randn(N, V, device=dev).bfloat16()
+    z = torch.randn(N, V, device=dev) * 2
+    tgt = torch.randint(1, V, (N,), device=dev)
+    nval = torch.tensor([N], dtype=torch.int32, device=dev)
+    dy = torch.empty_like(y)
+    rows = torch.empty(2, N, device=dev)
+
+    def kd():
+        rc = lib.b2c_kd_token_loss(y.data_ptr(), z.data_ptr(), tgt.data_ptr(), N, V, 4.0, 0.7, 0.0, 1.0, nval.data_ptr(), dy.data_ptr(),
+                                   rows[0].data_ptr(), rows[1].data_ptr(), _ops.B2C_BF16, st)
+        assert rc == 0
+
+    def timeit(fn, reps=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+
+    t_kd = timeit(kd)
+    kd_bytes = N * V * (2 + 4 + 2) + 8 * N                     # read bf16 student + fp32 teacher, write bf16 dlogits, read targets
+    roof = {"kernel": "kd_token_loss_kernel<bf16> (b2c_kd_token_loss)", "bound": "hbm", "achieved": kd_bytes / t_kd / 1e9, "peak": peaks["hbm"],
+            "unit": "GB/s", "frac": kd_bytes / t_kd / 1e9 / peaks["hbm"], "traffic": None, "peak_source": peaks["src"] + " (MEASURED_PEAKS.json hbm_gbs)",
+            "algorithmic_bytes_per_launch": kd_bytes, "us_per_launch": t_kd * 1e6}
+    # vocabulary head GEMM (time-batched, tcgen05): logits = o1 W2^T, M = T*B, N = V, K = E
+    A = torch.randn(N, E, device=dev).bfloat16(); W = torch.randn(V, E, device=dev).bfloat16(); C = torch.empty(N, V, device=dev, dtype=torch.bfloat16)
+    t_g = timeit(lambda: _ops.gemm(A, W, N, V, E, C=C))
+    fl = 2.0 * N * V * E
+    # recurrent gate GEMM of one step (serial part): M = B, N = 4H, K = E+H
+    A2 = torch.randn(B, E + H, device=dev).bfloat16(); W2 = torch.randn(4 * H, E + H, device=dev).bfloat16(); C2 = torch.empty(B, 4 * H, device=dev)
+    t_g2 = timeit(lambda: _ops.gemm(A2, W2, B, 4 * H, E + H, C=C2))
+    fl2 = 2.0 * B * 4 * H * (E + H)
+    extra = {"vocab_head_gemm_tcgen05": {"bound": "tensor", "achieved": fl / t_g / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                                         "frac": fl / t_g / 1e12 / peaks["tf_burst"], "us_per_launch": t_g * 1e6, "shape": [N, V, E]},
+             "lstm_gate_gemm_tcgen05": {"bound": "tensor", "achieved": fl2 / t_g2 / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                                        "frac": fl2 / t_g2 / 1e12 / peaks["tf_burst"], "us_per_launch": t_g2 * 1e6, "shape": [B, 4 * H, E + H]}}
+    return roof, extra
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b2c", choices=["b2c", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,342 @@
+"""ctypes binding of the b2c C ABI (include/b2c.h) + the autograd Functions built on it.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every arithmetic
+operation of the hot path runs in the hand-written sm_100a kernels of ``lib/libb2c.so``.
+There is no CPU or eager fallback: a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb2c.so")
+
+B2C_MAX_LAYERS = 4
+B2C_F32, B2C_BF16 = 0, 1
+B2C_WS_TRAIN, B2C_WS_DECODE, B2C_WS_ATTN = 0, 1, 2
+ABI_VERSION = 1
+
+c_f32p = ctypes.c_void_p
+
+
+class B2CShape(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "T", "S", "E", "H", "L", "V")]
+
+
+_PARAM_FIELDS = (
+    [("embedding", c_f32p), ("attn_w", c_f32p), ("attn_b", c_f32p), ("comb_w", c_f32p), ("comb_b", c_f32p)]
+    + [(n, c_f32p * B2C_MAX_LAYERS) for n in ("w_ih", "w_hh", "b_ih", "b_hh")]
+    + [("out0_w", c_f32p), ("out0_b", c_f32p), ("out3_w", c_f32p), ("out3_b", c_f32p)]
+)
+
+
+class B2CParams(ctypes.Structure):
+    _fields_ = _PARAM_FIELDS
+
+
+class B2CGrads(ctypes.Structure):
+    _fields_ = _PARAM_FIELDS
+
+
+class B2CDropout(ctypes.Structure):
+    _fields_ = [("p", ctypes.c_float), ("seed", ctypes.c_uint64)]
+
+
+# every symbol include/b2c.h declares: name -> (restype, argtypes)
+_vp, _i32, _i64, _f, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+_SHP, _PRM, _GRD, _DRP = ctypes.POINTER(B2CShape), ctypes.POINTER(B2CParams), ctypes.POINTER(B2CGrads), ctypes.POINTER(B2CDropout)
+SYMBOLS = {
+    "b2c_abi_version": (ctypes.c_int, []),
+    "b2c_last_error": (ctypes.c_char_p, []),
+    "b2c_launch_count": (ctypes.c_uint64, []),
+    "b2c_workspace_bytes": (_sz, [_SHP, ctypes.c_int, ctypes.c_int]),
+    "b2c_decoder_forward": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
+    "b2c_decoder_backward": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _GRD, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
+    "b2c_greedy_decode": (ctypes.c_int, [_SHP, _PRM, _vp, _i64, _i64, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
+    "b2c_attention_step": (ctypes.c_int, [_SHP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
+    "b2c_count_valid": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "b2c_kd_token_loss": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _f, _f, _f, _f, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
+    "b2c_aux_loss": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _f, _f, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
+    "b2c_loss_finalize": (ctypes.c_int, [_vp, _vp, _i64, _vp, _f, _vp, _i32, _i32, _vp, _i32, _i32, _f, _f, _f, _f, _f, _vp, _vp]),
+    "b2c_scale_inplace": (ctypes.c_int, [_vp, _i64, ctypes.c_int, _vp, _vp]),
+    "b2c_gemm": (ctypes.c_int, [_i32, _i32, _i32, _f, _vp, _i64, ctypes.c_int, _vp, _i64, ctypes.c_int, _f, _vp, _i64, _vp,
+                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+}
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load lib/libb2c.so (built by __graft_entry__.build()).  Fails loudly: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"b2c CUDA extension not built: {LIB_PATH} is missing. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "from the repo root (needs nvcc). There is no CPU/eager fallback for the hot path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
+        fn.restype, fn.argtypes = res, args
+    if lib.b2c_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libb2c.so ABI {lib.b2c_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_library().b2c_last_error().decode("utf-8", "replace")
+        exc = ValueError if rc == -1 else RuntimeError
+        raise exc(f"{what} failed (code {rc}): {msg}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} is on {t.device}: the b2c hot path runs only on a CUDA (sm_100a) device; there is no CPU fallback")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return B2C_F32
+    if dt == torch.bfloat16:
+        return B2C_BF16
+    raise ValueError(f"unsupported compute dtype {dt} (use torch.float32 or torch.bfloat16)")
+
+
+def param_order(L: int) -> List[str]:
+    """LSTMDecoder state_dict keys in the order DecoderFunction takes its parameter tensors."""
+    names = ["embedding.weight", "attention.weight", "attention.bias", "attention_combine.weight", "attention_combine.bias"]
+    for k in range(L):
+        names += [f"lstm.weight_ih_l{k}", f"lstm.weight_hh_l{k}", f"lstm.bias_ih_l{k}", f"lstm.bias_hh_l{k}"]
+    names += ["output_projection.0.weight", "output_projection.0.bias", "output_projection.3.weight", "output_projection.3.bias"]
+    return names
+
+
+def _fill_struct(st, tensors: Sequence[torch.Tensor], L: int):
+    it = iter(tensors)
+    st.embedding = next(it).data_ptr(); st.attn_w = next(it).data_ptr(); st.attn_b = next(it).data_ptr()
+    st.comb_w = next(it).data_ptr(); st.comb_b = next(it).data_ptr()
+    for k in range(L):
+        st.w_ih[k] = next(it).data_ptr(); st.w_hh[k] = next(it).data_ptr()
+        st.b_ih[k] = next(it).data_ptr(); st.b_hh[k] = next(it).data_ptr()
+    st.out0_w = next(it).data_ptr(); st.out0_b = next(it).data_ptr(); st.out3_w = next(it).data_ptr(); st.out3_b = next(it).data_ptr()
+    return st
+
+
+def _master(params: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    out = []
+    for p in params:
+        q = p.detach()
+        if q.dtype != torch.float32 or not q.is_contiguous():
+            q = q.float().contiguous()
+        out.append(q)
+    return out
+
+
+def workspace_bytes(shape: B2CShape, code: int, mode: int) -> int:
+    lib = load_library()
+    n = lib.b2c_workspace_bytes(ctypes.byref(shape), code, mode)
+    if n == 0:
+        _check(-1, "b2c_workspace_bytes")
+    return n
+
+
+class DecoderFunction(torch.autograd.Function):
+    """LSTMDecoder.forward (reference src/student_model.py:205-256) as one C-ABI call each way."""
+
+    @staticmethod
+    def forward(ctx, feats, captions, compute_dtype, dropout_p, seed, L, *params):
+        lib = load_library()
+        _require_cuda(feats, "image_features")
+        B, S, E = feats.shape
+        T = captions.shape[0]
+        H = params[1].shape[1] - E      # attention.weight is (E, H+E)
+        V = params[0].shape[0]
+        shape = B2CShape(B, T, S, E, H, L, V)
+        code = dtype_code(compute_dtype)
+        f = feats.detach().to(compute_dtype).contiguous()
+        cap = captions.detach().to(device=feats.device, dtype=torch.int64).contiguous()
+        master = _master(params)
+        ws = torch.empty(workspace_bytes(shape, code, B2C_WS_TRAIN), dtype=torch.uint8, device=feats.device)
+        logits = torch.empty(T, B, V, dtype=compute_dtype, device=feats.device)
+        hid = torch.empty(T, B, H, dtype=compute_dtype, device=feats.device)
+        attw = torch.empty(T, B, S, dtype=torch.float32, device=feats.device)
+        prm = _fill_struct(B2CParams(), master, L)
+        drop = B2CDropout(float(dropout_p), int(seed))
+        _check(lib.b2c_decoder_forward(ctypes.byref(shape), ctypes.byref(prm), f.data_ptr(), cap.data_ptr(), logits.data_ptr(),
+                                       hid.data_ptr(), attw.data_ptr(), ws.data_ptr(), ws.numel(), code, ctypes.byref(drop), _stream()),
+               "b2c_decoder_forward")
+        ctx.b2c = (shape, code, drop, L, ws, f, cap, master, hid, attw, feats.dtype, [p.dtype for p in params])
+        ctx.mark_non_differentiable(attw)
+        return logits, hid, attw
+
+    @staticmethod
+    def backward(ctx, dlogits, dhid, _dattw):
+        lib = load_library()
+        shape, code, drop, L, ws, f, cap, master, hid, attw, feats_dtype, pdtypes = ctx.b2c
+        cdt = f.dtype
+        if dlogits is None:
+            dlogits = torch.zeros(shape.T, shape.B, shape.V, dtype=cdt, device=f.device)
+        dlogits = dlogits.to(cdt).contiguous()
+        if dhid is not None:
+            dhid = dhid.to(cdt).contiguous()
+        grads = [torch.empty_like(m) for m in master]
+        dfeats = torch.empty(shape.B, shape.S, shape.E, dtype=torch.float32, device=f.device)
+        prm = _fill_struct(B2CParams(), master, L)
+        grd = _fill_struct(B2CGrads(), grads, L)
+        _check(lib.b2c_decoder_backward(ctypes.byref(shape), ctypes.byref(prm), f.data_ptr(), cap.data_ptr(), hid.data_ptr(), attw.data_ptr(),
+                                        dlogits.data_ptr(), _ptr(dhid), ctypes.byref(grd), dfeats.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        code, ctypes.byref(drop), _stream()),
+               "b2c_decoder_backward")
+        grads = [g if g.dtype == dt else g.to(dt) for g, dt in zip(grads, pdtypes)]
+        dfe = dfeats if feats_dtype == torch.float32 else dfeats.to(feats_dtype)
+        return (dfe, None, None, None, None, None, *grads)
+
+
+def greedy_decode(feats: torch.Tensor, params: Sequence[torch.Tensor], L: int, max_len: int, start_id: int, end_id: int,
+                  compute_dtype: torch.dtype = torch.float32):
+    """Batched greedy decode on the device: returns tokens (max_len,B) int64, lengths (B) int32."""
+    lib = load_library()
+    _require_cuda(feats, "image_features")
+    B, S, E = feats.shape
+    H = params[1].shape[1] - E
+    V = params[0].shape[0]
+    shape = B2CShape(B, max_len, S, E, H, L, V)
+    code = dtype_code(compute_dtype)
+    f = feats.detach().to(compute_dtype).contiguous()
+    master = _master(params)
+    ws = torch.empty(workspace_bytes(shape, code, B2C_WS_DECODE), dtype=torch.uint8, device=feats.device)
+    tokens = torch.empty(max_len, B, dtype=torch.int64, device=feats.device)
+    lengths = torch.empty(B, dtype=torch.int32, device=feats.device)
+    prm = _fill_struct(B2CParams(), master, L)
+    _check(lib.b2c_greedy_decode(ctypes.byref(shape), ctypes.byref(prm), f.data_ptr(), int(start_id), int(end_id), tokens.data_ptr(),
+                                 lengths.data_ptr(), ws.data_ptr(), ws.numel(), code, _stream()), "b2c_greedy_decode")
+    return tokens, lengths
+
+
+def attention_step(hidden: torch.Tensor, feats: torch.Tensor, attn_w: torch.Tensor, attn_b: torch.Tensor,
+                   compute_dtype: torch.dtype = torch.float32):
+    """LSTMDecoder.attention_mechanism as a stand-alone call: context (B,E), weights (B,S)."""
+    lib = load_library()
+    _require_cuda(feats, "image_features")
+    B, S, E = feats.shape
+    H = hidden.shape[1]
+    shape = B2CShape(B, 1, S, E, H, 1, 2)
+    code = dtype_code(compute_dtype)
+    f = feats.detach().to(compute_dtype).contiguous()
+    h = hidden.detach().to(device=feats.device, dtype=compute_dtype).contiguous()
+    wa, ba = _master([attn_w, attn_b])
+    ws = torch.empty(workspace_bytes(shape, code, B2C_WS_ATTN), dtype=torch.uint8, device=feats.device)
+    ctx = torch.empty(B, E, dtype=compute_dtype, device=feats.device)
+    wts = torch.empty(B, S, dtype=torch.float32, device=feats.device)
+    _check(lib.b2c_attention_step(ctypes.byref(shape), wa.data_ptr(), ba.data_ptr(), h.data_ptr(), f.data_ptr(), ctx.data_ptr(),
+                                  wts.data_ptr(), ws.data_ptr(), ws.numel(), code, _stream()), "b2c_attention_step")
+    return ctx, wts
+
+
+class KDLossFunction(torch.autograd.Function):
+    """DistillationLoss.forward (reference src/distillation_utils.py:138-200): the token pass, the fused
+    feature/hidden reduction and the weighting, with all gradients produced during the forward."""
+
+    @staticmethod
+    def forward(ctx, logits, teacher_logits, targets, feats_s, feats_t, hid_s, hid_t, cfg):
+        lib = load_library()
+        _require_cuda(logits, "student logits")
+        alpha, beta, gamma, temperature, w_ce, ce_mult, group = cfg
+        T, B, V = logits.shape
+        N = T * B
+        dev = logits.device
+        cdt = logits.dtype if logits.dtype in (torch.float32, torch.bfloat16) else torch.float32
+        code = dtype_code(cdt)
+        y = logits.detach().to(cdt).contiguous()
+        z = teacher_logits.detach().to(device=dev, dtype=torch.float32).contiguous()
+        tg = targets.detach().to(device=dev, dtype=torch.int64).contiguous()
+        st = _stream()
+        nval = torch.empty(1, dtype=torch.int32, device=dev)
+        _check(lib.b2c_count_valid(tg.data_ptr(), N, V, nval.data_ptr(), st), "b2c_count_valid")
+        if group is not None:                      # data parallel: the CE normaliser is the GLOBAL non-PAD count
+            torch.distributed.all_reduce(nval, group=group)
+        dlogits = torch.empty_like(y)
+        rows = torch.empty(2, N, dtype=torch.float32, device=dev)
+        _check(lib.b2c_kd_token_loss(y.data_ptr(), z.data_ptr(), tg.data_ptr(), N, V, float(temperature), float(alpha), float(w_ce),
+                                     float(ce_mult), nval.data_ptr(), dlogits.data_ptr(), rows[0].data_ptr(), rows[1].data_ptr(), code, st),
+               "b2c_kd_token_loss")
+        fs = ft = hs = ht = dfs = dft = dhs = feat_part = hid_part = None
+        Ss = St = E = H = Th = 0
+        if feats_s is not None and feats_t is not None:
+            fs = feats_s.detach().to(cdt).contiguous()
+            ft = feats_t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            _, Ss, E = fs.shape
+            St = ft.shape[1]
+            dfs = torch.empty(B, Ss, E, dtype=torch.float32, device=dev)
+            dft = torch.empty(B, St, E, dtype=torch.float32, device=dev)
+            feat_part = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        if hid_s is not None and hid_t is not None:
+            hs = hid_s.detach().to(cdt).contiguous()
+            ht = hid_t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            Th, H = ht.shape[0], ht.shape[2]
+            dhs = torch.empty_like(hs)
+            hid_part = torch.empty(Th * B, 2, dtype=torch.float32, device=dev)
+        if fs is not None or hs is not None:
+            _check(lib.b2c_aux_loss(_ptr(fs), _ptr(ft), B, Ss, St, E, _ptr(hs), _ptr(ht), hs.shape[0] if hs is not None else 0, Th, H,
+                                    float(beta), float(gamma), _ptr(dfs), _ptr(dft), _ptr(dhs), _ptr(feat_part), _ptr(hid_part), code, st),
+                   "b2c_aux_loss")
+        out5 = torch.empty(5, dtype=torch.float32, device=dev)
+        _check(lib.b2c_loss_finalize(rows[0].data_ptr(), rows[1].data_ptr(), N, nval.data_ptr(), float(ce_mult), _ptr(feat_part), B, E,
+                                     _ptr(hid_part), Th, H, float(temperature), float(alpha), float(beta), float(gamma), float(w_ce),
+                                     out5.data_ptr(), st), "b2c_loss_finalize")
+        ctx.b2c = dict(dlogits=dlogits, dfs=dfs, dft=dft, dhs=dhs, code=code, used=False,
+                       dtypes=(logits.dtype, None if feats_s is None else feats_s.dtype,
+                               None if feats_t is None else feats_t.dtype, None if hid_s is None else hid_s.dtype))
+        ctx.mark_non_differentiable(out5)
+        return out5[0].clone(), out5
+
+    @staticmethod
+    def backward(ctx, grad_loss, _g5):
+        lib = load_library()
+        sv = ctx.b2c
+        if sv["used"]:
+            raise RuntimeError("KDLossFunction.backward ran twice: its gradients are scaled in place (retain_graph is not supported)")
+        sv["used"] = True
+        scale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        st = _stream()
+        for key, code in (("dlogits", sv["code"]), ("dfs", B2C_F32), ("dft", B2C_F32), ("dhs", sv["code"])):
+            t = sv[key]
+            if t is not None:
+                _check(lib.b2c_scale_inplace(t.data_ptr(), t.numel(), code, scale.data_ptr(), st), "b2c_scale_inplace")
+        dt_l, dt_fs, dt_ft, dt_hs = sv["dtypes"]
+
+        def cast(t, dt):
+            return None if t is None else (t if t.dtype == dt else t.to(dt))
+
+        return cast(sv["dlogits"], dt_l), None, None, cast(sv["dfs"], dt_fs), cast(sv["dft"], dt_ft), cast(sv["dhs"], dt_hs), None, None
+
+
+def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
+         out_dtype: torch.dtype = torch.float32, bias: Optional[torch.Tensor] = None, relu: bool = False,
+         alpha: float = 1.0, beta: float = 0.0, C: Optional[torch.Tensor] = None, impl: int = 0,
+         lda: Optional[int] = None, ldb: Optional[int] = None) -> torch.Tensor:
+    """Test hook for the contraction tiles (tcgen05 for bf16 operands, FFMA for fp32)."""
+    lib = load_library()
+    _require_cuda(A, "A")
+    lda = lda if lda is not None else A.stride(0)
+    ldb = ldb if ldb is not None else Bm.stride(0)
+    if C is None:
+        C = torch.zeros(M, N, dtype=out_dtype, device=A.device)
+    _check(lib.b2c_gemm(M, N, K, float(alpha), A.data_ptr(), lda, int(a_mn), Bm.data_ptr(), ldb, int(b_mn), float(beta), C.data_ptr(),
+                        C.stride(0), _ptr(bias), int(relu), dtype_code(A.dtype), dtype_code(C.dtype), impl, _stream()), "b2c_gemm")
+    return C

@@ -1,0 +1,548 @@
+// b2c C ABI: host-side orchestration of the decoder / loss kernels.  See include/b2c.h for the contract and
+// oracle/manual_backward.py for the (CPU, test-only) blueprint of exactly this dataflow.
+#include "gemm.cuh"
+#include "loss_kernels.cuh"
+#include "decoder_kernels.cuh"
+
+using namespace b2c;
+
+namespace {
+
+constexpr int MAXL = B2C_MAX_LAYERS;
+constexpr int COLSUM_RS = 32;
+
+// ------------------------------------------------------------------ device check (sm_100 only, no fallback)
+int check_device() {
+  static int cached = 1;   // 1 = not checked, 0 = ok, <0 error
+  if (cached <= 0) return cached;
+  int dev = 0;
+  B2C_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  B2C_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) { cached = B2C_EARCH; return set_err(B2C_EARCH, "b2c kernels are built for sm_100a only; device has compute capability major %d", major); }
+  cached = 0;
+  return 0;
+}
+
+struct Carver {
+  unsigned char* base; size_t off;
+  template <typename U> U* take(size_t n) {
+    off = align_up(off, 256);
+    U* p = base ? reinterpret_cast<U*>(base + off) : reinterpret_cast<U*>((uintptr_t)0);
+    off += n * sizeof(U);
+    return p;
+  }
+};
+
+inline int in_dim(const B2CShape& s, int k) { return k == 0 ? s.E : s.H; }
+
+int check_shape(const B2CShape* s) {
+  B2C_CHECK_ARG(s != nullptr, "shape is NULL");
+  B2C_CHECK_ARG(s->B > 0 && s->T > 0 && s->S > 0 && s->V > 1, "bad shape B=%d T=%d S=%d V=%d", s->B, s->T, s->S, s->V);
+  B2C_CHECK_ARG(s->L >= 1 && s->L <= MAXL, "L=%d outside [1,%d]", s->L, MAXL);
+  B2C_CHECK_ARG(s->E > 0 && s->E % 8 == 0 && s->H > 0 && s->H % 8 == 0, "E=%d and H=%d must be positive multiples of 8", s->E, s->H);
+  return 0;
+}
+
+// ------------------------------------------------------------------ packed operand weights (compute type)
+template <typename T> struct Weights {
+  T *Wf, *Wh, *Wce, *Wcc, *W1, *W2; T* Wcat[MAXL]; float* bcat[MAXL];
+  void carve(Carver& c, const B2CShape& s) {
+    Wf = c.take<T>((size_t)s.E * s.E); Wh = c.take<T>((size_t)s.E * s.H);
+    Wce = c.take<T>((size_t)s.E * s.E); Wcc = c.take<T>((size_t)s.E * s.E);
+    W1 = c.take<T>((size_t)s.E * s.H); W2 = c.take<T>((size_t)s.V * s.E);
+    for (int k = 0; k < s.L; ++k) { Wcat[k] = c.take<T>((size_t)4 * s.H * (in_dim(s, k) + s.H)); bcat[k] = c.take<float>((size_t)4 * s.H); }
+  }
+};
+
+template <typename T>
+int pack_params(const B2CShape& s, const B2CParams& p, const Weights<T>& w, cudaStream_t st) {
+  B2C_CHECK_ARG(p.embedding && p.attn_w && p.attn_b && p.comb_w && p.comb_b && p.out0_w && p.out0_b && p.out3_w && p.out3_b, "NULL parameter pointer");
+  PackTable tab; tab.n = 0;
+  auto add = [&](const float* src, void* dst, int rows, int cols, long lds, long ldd, const float* src2 = nullptr, int as_float = 0) {
+    PackSeg& g = tab.seg[tab.n++]; g.src = src; g.dst = dst; g.src2 = src2; g.rows = rows; g.cols = cols; g.lds = lds; g.ldd = ldd; g.as_float = as_float;
+  };
+  const int E = s.E, H = s.H;
+  add(p.attn_w, w.Wh, E, H, H + E, H);
+  add(p.attn_w + H, w.Wf, E, E, H + E, E);
+  add(p.comb_w, w.Wce, E, E, 2 * E, E);
+  add(p.comb_w + E, w.Wcc, E, E, 2 * E, E);
+  add(p.out0_w, w.W1, E, H, H, H);
+  add(p.out3_w, w.W2, s.V, E, E, E);
+  for (int k = 0; k < s.L; ++k) {
+    B2C_CHECK_ARG(p.w_ih[k] && p.w_hh[k] && p.b_ih[k] && p.b_hh[k], "NULL LSTM parameter pointer (layer %d)", k);
+    const int in = in_dim(s, k);
+    add(p.w_ih[k], w.Wcat[k], 4 * H, in, in, in + H);
+    add(p.w_hh[k], w.Wcat[k] + in, 4 * H, H, H, in + H);
+    add(p.b_ih[k], w.bcat[k], 1, 4 * H, 4 * H, 4 * H, p.b_hh[k], 1);
+  }
+  pack_params_kernel<T><<<dim3(96, tab.n), 256, 0, st>>>(tab);
+  B2C_LAUNCH_CHECK("pack_params_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------ workspaces
+template <typename T> struct TrainWs {
+  Weights<T> w;
+  T *P, *emb, *u, *ctx, *o1; T* xh[MAXL]; T* gates[MAXL]; float* c[MAXL]; float* pre;
+  T* dgates[MAXL]; T* dxh0; T* dxh[MAXL]; float* dc[MAXL]; T* do1; float* dHext; T* dctx; float* ds; T* du; T* dq; T* dP; float* demb; float* partial;
+  size_t bytes;
+  void carve(void* base, const B2CShape& s) {
+    Carver c{reinterpret_cast<unsigned char*>(base), 0};
+    const size_t B = s.B, Tn = s.T, S = s.S, E = s.E, H = s.H, TB = Tn * B;
+    w.carve(c, s);
+    P = c.take<T>(B * S * E); emb = c.take<T>(TB * E); u = c.take<T>(TB * E); ctx = c.take<T>(TB * E); o1 = c.take<T>(TB * E);
+    for (int k = 0; k < s.L; ++k) {
+      xh[k] = c.take<T>((Tn + 1) * B * (in_dim(s, k) + H));
+      gates[k] = c.take<T>(TB * 4 * H);
+      this->c[k] = c.take<float>((Tn + 1) * B * H);
+    }
+    pre = c.take<float>(B * 4 * H);
+    for (int k = 0; k < s.L; ++k) {
+      dgates[k] = c.take<T>(TB * 4 * H);
+      dxh[k] = k == 0 ? nullptr : c.take<T>(B * 2 * H);
+      dc[k] = c.take<float>(B * H);
+    }
+    dxh0 = c.take<T>(TB * (E + H));
+    do1 = c.take<T>(TB * E); dHext = c.take<float>(TB * H); dctx = c.take<T>(TB * E); ds = c.take<float>(TB * S);
+    du = c.take<T>(TB * E); dq = c.take<T>(B * H); dP = c.take<T>(B * S * E); demb = c.take<float>(TB * E);
+    size_t mc = (size_t)s.V; if ((size_t)4 * H > mc) mc = 4 * H; if (E > mc) mc = E;
+    partial = c.take<float>((size_t)COLSUM_RS * mc);
+    bytes = align_up(c.off, 256);
+  }
+};
+
+template <typename T> struct DecodeWs {
+  Weights<T> w;
+  T *P, *emb, *u, *ctx, *o1; T* xh[MAXL]; float* c[MAXL]; float* pre; float* logits; int64_t* cur; int32_t* done;
+  size_t bytes;
+  void carve(void* base, const B2CShape& s) {
+    Carver c{reinterpret_cast<unsigned char*>(base), 0};
+    const size_t B = s.B, S = s.S, E = s.E, H = s.H;
+    w.carve(c, s);
+    P = c.take<T>(B * S * E); emb = c.take<T>(B * E); u = c.take<T>(B * E); ctx = c.take<T>(B * E); o1 = c.take<T>(B * E);
+    for (int k = 0; k < s.L; ++k) { xh[k] = c.take<T>(B * (in_dim(s, k) + H)); this->c[k] = c.take<float>(B * H); }
+    pre = c.take<float>(B * 4 * H); logits = c.take<float>(B * (size_t)s.V); cur = c.take<int64_t>(B); done = c.take<int32_t>(B);
+    bytes = align_up(c.off, 256);
+  }
+};
+
+// ------------------------------------------------------------------ launch helpers
+template <typename T, typename TC>
+int gemm(cudaStream_t st, int M, int N, int K, const T* A, long lda, int a_mn, const T* B, long ldb, int b_mn,
+         TC* C, long ldc, float beta = 0.f, const float* bias = nullptr, int relu = 0, float alpha = 1.f) {
+  GemmArgs g{M, N, K, alpha, beta, A, lda, a_mn, B, ldb, b_mn, C, ldc, bias, relu};
+  return Gemm<T, TC>::run(g, st);
+}
+
+inline int ew_grid(long n) { long g = (n + 255) / 256; if (g > 148 * 8) g = 148 * 8; if (g < 1) g = 1; return (int)g; }
+
+template <typename T>
+int colsum(cudaStream_t st, const T* A, long rows, int cols, long ld, float* partial, float* out, float* out2 = nullptr) {
+  int rs = (int)((rows + 255) / 256); if (rs > COLSUM_RS) rs = COLSUM_RS; if (rs < 1) rs = 1;
+  colsum_partial_kernel<T><<<dim3(cdiv(cols, 32), rs), 256, 0, st>>>(A, rows, cols, ld, partial);
+  B2C_LAUNCH_CHECK("colsum_partial_kernel");
+  colsum_final_kernel<<<cdiv(cols, 256), 256, 0, st>>>(partial, rs, cols, out, out2);
+  B2C_LAUNCH_CHECK("colsum_final_kernel");
+  return 0;
+}
+
+template <typename K> int set_smem(K kern, size_t bytes) {
+  B2C_CHECK_ARG(bytes <= 227 * 1024, "kernel needs %zu bytes of shared memory (> 227 KB): shape too large for this path", bytes);
+  if (bytes > 48 * 1024) B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+template <typename T>
+int attn_fwd(cudaStream_t st, const B2CShape& s, const T* P, const T* F, const T* u, T* ctx, float* attw) {
+  const size_t smem = (size_t)2 * s.S * s.E * sizeof(T) + (size_t)(s.E + s.S) * 4;
+  B2C_TRY(set_smem(attn_step_fwd_kernel<T>, smem));
+  attn_step_fwd_kernel<T><<<s.B, ATT_THREADS, smem, st>>>(P, F, u, s.E, s.S, s.E, ctx, s.E, attw);
+  B2C_LAUNCH_CHECK("attn_step_fwd_kernel");
+  return 0;
+}
+
+// one LSTM layer step: pre = [in;h] Wcat^T + b, then the cell pointwise
+template <typename T>
+int lstm_layer_fwd(cudaStream_t st, const B2CShape& s, const Weights<T>& w, int k, const T* xh_t, float* pre,
+                   const float* c_prev, float* c_out, T* gates_out, T* h_rec, T* h_next, T* h_top,
+                   const B2CDropout& dr, long row_base) {
+  const int in = in_dim(s, k), ld = in + s.H;
+  B2C_TRY((gemm<T, float>(st, s.B, 4 * s.H, ld, xh_t, ld, 0, w.Wcat[k], ld, 0, pre, 4 * s.H, 0.f, w.bcat[k])));
+  lstm_pointwise_fwd_kernel<T><<<ew_grid((long)s.B * s.H), 256, 0, st>>>(pre, c_prev, c_out, gates_out, h_rec, ld, h_next, 2 * s.H, h_top, s.H,
+                                                                       s.B, s.H, dr.p, dr.seed, (uint32_t)k, row_base);
+  B2C_LAUNCH_CHECK("lstm_pointwise_fwd_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------ decoder forward (teacher forced)
+template <typename T>
+int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, const int64_t* cap, T* logits, T* hid_top,
+                         float* attw, void* ws, size_t ws_bytes, const B2CDropout& dr, cudaStream_t st) {
+  TrainWs<T> W; W.carve(ws, s);
+  B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
+  const int B = s.B, Tn = s.T, S = s.S, E = s.E, H = s.H, L = s.L, V = s.V;
+  const long TB = (long)Tn * B;
+  B2C_TRY(pack_params<T>(s, p, W.w, st));
+  // time-invariant half of the attention projection: P = F W_f^T + b_a
+  B2C_TRY((gemm<T, T>(st, B * S, E, E, feats, E, 0, W.w.Wf, E, 0, W.P, E, 0.f, p.attn_b)));
+  embedding_gather_kernel<T><<<ew_grid(TB * E / 4), 256, 0, st>>>(p.embedding, cap, TB, E, V, W.emb, E);
+  B2C_LAUNCH_CHECK("embedding_gather_kernel");
+  for (int k = 0; k < L; ++k) {
+    B2C_CUDA(cudaMemsetAsync(W.xh[k], 0, (size_t)B * (in_dim(s, k) + H) * sizeof(T), st));   // h_{-1} = 0
+    B2C_CUDA(cudaMemsetAsync(W.c[k], 0, (size_t)B * H * sizeof(float), st));                  // c_{-1} = 0
+  }
+  // embedding half of attention_combine for all steps, straight into layer 0's input slots
+  B2C_TRY((gemm<T, T>(st, (int)TB, E, E, W.emb, E, 0, W.w.Wce, E, 0, W.xh[0], E + H, 0.f, p.comb_b)));
+  const int inL = in_dim(s, L - 1), ldL = inL + H;
+  for (int t = 0; t < Tn; ++t) {
+    const T* q = W.xh[L - 1] + (long)t * B * ldL + inL;
+    T* u_t = W.u + (long)t * B * E;
+    T* ctx_t = W.ctx + (long)t * B * E;
+    B2C_TRY((gemm<T, T>(st, B, E, H, q, ldL, 0, W.w.Wh, H, 0, u_t, E)));
+    B2C_TRY(attn_fwd<T>(st, s, W.P, feats, u_t, ctx_t, attw + (long)t * B * S));
+    B2C_TRY((gemm<T, T>(st, B, E, E, ctx_t, E, 0, W.w.Wcc, E, 0, W.xh[0] + (long)t * B * (E + H), E + H, 1.f)));
+    for (int k = 0; k < L; ++k) {
+      const int in = in_dim(s, k), ld = in + H;
+      B2C_TRY(lstm_layer_fwd<T>(st, s, W.w, k, W.xh[k] + (long)t * B * ld, W.pre, W.c[k] + (long)t * B * H, W.c[k] + (long)(t + 1) * B * H,
+                                W.gates[k] + (long)t * B * 4 * H, W.xh[k] + (long)(t + 1) * B * ld + in,
+                                k + 1 < L ? W.xh[k + 1] + (long)t * B * 2 * H : nullptr, k == L - 1 ? hid_top + (long)t * B * H : nullptr,
+                                dr, (long)t * B));
+    }
+  }
+  // output head, time-batched: y = W2 Drop(ReLU(W1 h + b1)) + b2
+  B2C_TRY((gemm<T, T>(st, (int)TB, E, H, hid_top, H, 0, W.w.W1, H, 0, W.o1, E, 0.f, p.out0_b, 1)));
+  if (dr.p > 0.f) {
+    dropout_inplace_kernel<T><<<ew_grid(TB * E), 256, 0, st>>>(W.o1, TB * E, dr.p, dr.seed, 100u);
+    B2C_LAUNCH_CHECK("dropout_inplace_kernel");
+  }
+  B2C_TRY((gemm<T, T>(st, (int)TB, V, E, W.o1, E, 0, W.w.W2, E, 0, logits, V, 0.f, p.out3_b)));
+  return 0;
+}
+
+// ------------------------------------------------------------------ decoder backward (BPTT)
+template <typename T>
+int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats, const int64_t* cap, const T* hid_top,
+                          const float* attw, const T* dlogits, const T* dhid, const B2CGrads& g, float* dfeats,
+                          void* ws, size_t ws_bytes, const B2CDropout& dr, cudaStream_t st) {
+  (void)p;
+  TrainWs<T> W; W.carve(ws, s);
+  B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
+  B2C_CHECK_ARG(g.embedding && g.attn_w && g.attn_b && g.comb_w && g.comb_b && g.out0_w && g.out0_b && g.out3_w && g.out3_b && dfeats, "NULL gradient pointer");
+  const int B = s.B, Tn = s.T, S = s.S, E = s.E, H = s.H, L = s.L, V = s.V;
+  const long TB = (long)Tn * B;
+  const float inv_keep = dr.p > 0.f ? 1.0f / (1.0f - dr.p) : 1.0f;
+  // ---- output head (time-batched)
+  B2C_TRY((gemm<T, T>(st, (int)TB, E, V, dlogits, V, 0, W.w.W2, E, 1, W.do1, E)));
+  relu_bwd_inplace_kernel<T><<<ew_grid(TB * E), 256, 0, st>>>(W.do1, W.o1, TB * E, inv_keep);
+  B2C_LAUNCH_CHECK("relu_bwd_inplace_kernel");
+  B2C_TRY((gemm<T, float>(st, V, E, (int)TB, dlogits, V, 1, W.o1, E, 1, g.out3_w, E)));
+  B2C_TRY(colsum<T>(st, dlogits, TB, V, V, W.partial, g.out3_b));
+  B2C_TRY((gemm<T, float>(st, (int)TB, H, E, W.do1, E, 0, W.w.W1, H, 1, W.dHext, H)));
+  B2C_TRY((gemm<T, float>(st, E, H, (int)TB, W.do1, E, 1, hid_top, H, 1, g.out0_w, H)));
+  B2C_TRY(colsum<T>(st, W.do1, TB, E, E, W.partial, g.out0_b));
+  // ---- reverse time loop
+  const size_t att_smem = (size_t)2 * S * E * sizeof(T) + (size_t)(2 * E + S) * 4;
+  B2C_TRY(set_smem(attn_step_bwd_kernel<T>, att_smem));
+  for (int t = Tn - 1; t >= 0; --t) {
+    const bool last = (t == Tn - 1);
+    for (int k = L - 1; k >= 0; --k) {
+      B2C_CHECK_ARG(g.w_ih[k] && g.w_hh[k] && g.b_ih[k] && g.b_hh[k], "NULL LSTM gradient pointer (layer %d)", k);
+      const int in = in_dim(s, k), ld = in + H;
+      const T* carry = last ? nullptr : (k == 0 ? W.dxh0 + (long)(t + 1) * B * (E + H) + E : W.dxh[k] + H);
+      const T* above = (k < L - 1) ? W.dxh[k + 1] : nullptr;
+      const bool top = (k == L - 1);
+      lstm_pointwise_bwd_kernel<T><<<ew_grid((long)B * H), 256, 0, st>>>(
+          W.gates[k] + (long)t * B * 4 * H, W.c[k] + (long)t * B * H, W.c[k] + (long)(t + 1) * B * H, W.dc[k], last ? 1 : 0,
+          carry, ld, above, 2 * H, top ? W.dHext + (long)t * B * H : nullptr, (top && dhid) ? dhid + (long)t * B * H : nullptr,
+          (top && !last) ? W.dq : nullptr, H, W.dgates[k] + (long)t * B * 4 * H, B, H, dr.p, dr.seed, (uint32_t)k, (long)t * B);
+      B2C_LAUNCH_CHECK("lstm_pointwise_bwd_kernel");
+      T* out = (k == 0) ? W.dxh0 + (long)t * B * (E + H) : W.dxh[k];
+      B2C_TRY((gemm<T, T>(st, B, ld, 4 * H, W.dgates[k] + (long)t * B * 4 * H, 4 * H, 0, W.w.Wcat[k], ld, 1, out, ld)));
+    }
+    const T* dx = W.dxh0 + (long)t * B * (E + H);
+    T* dctx_t = W.dctx + (long)t * B * E;
+    T* du_t = W.du + (long)t * B * E;
+    B2C_TRY((gemm<T, T>(st, B, E, E, dx, E + H, 0, W.w.Wcc, E, 1, dctx_t, E)));
+    attn_step_bwd_kernel<T><<<B, ATT_THREADS, att_smem, st>>>(W.P, feats, W.u + (long)t * B * E, E, attw + (long)t * B * S, dctx_t, E,
+                                                             S, E, W.ds + (long)t * B * S, du_t, E);
+    B2C_LAUNCH_CHECK("attn_step_bwd_kernel");
+    if (t > 0) B2C_TRY((gemm<T, T>(st, B, H, E, du_t, E, 0, W.w.Wh, H, 1, W.dq, H)));
+  }
+  // ---- post-loop, time-batched weight gradients
+  for (int k = 0; k < L; ++k) {
+    const int in = in_dim(s, k), ld = in + H;
+    B2C_TRY((gemm<T, float>(st, 4 * H, in, (int)TB, W.dgates[k], 4 * H, 1, W.xh[k], ld, 1, g.w_ih[k], in)));
+    B2C_TRY((gemm<T, float>(st, 4 * H, H, (int)TB, W.dgates[k], 4 * H, 1, W.xh[k] + in, ld, 1, g.w_hh[k], H)));
+    B2C_TRY(colsum<T>(st, W.dgates[k], TB, 4 * H, 4 * H, W.partial, g.b_ih[k], g.b_hh[k]));
+  }
+  const int inL = in_dim(s, L - 1), ldL = inL + H;
+  B2C_TRY((gemm<T, float>(st, E, H, (int)TB, W.du, E, 1, W.xh[L - 1] + inL, ldL, 1, g.attn_w, H + E)));          // dW_a[:, :H]
+  {
+    const size_t smem = (size_t)Tn * (2 * E + 2 * S) * 4;
+    B2C_TRY(set_smem(attn_post_kernel<T>, smem));
+    attn_post_kernel<T><<<B, ATT_THREADS, smem, st>>>(W.P, W.u, W.dctx, attw, W.ds, Tn, B, S, E, W.dP, dfeats);
+    B2C_LAUNCH_CHECK("attn_post_kernel");
+  }
+  B2C_TRY((gemm<T, float>(st, E, E, B * S, W.dP, E, 1, feats, E, 1, g.attn_w + H, H + E)));                        // dW_a[:, H:]
+  B2C_TRY(colsum<T>(st, W.dP, (long)B * S, E, E, W.partial, g.attn_b));
+  B2C_TRY((gemm<T, float>(st, B * S, E, E, W.dP, E, 0, W.w.Wf, E, 1, dfeats, E, 1.f)));                             // dF += dP W_f
+  B2C_TRY((gemm<T, float>(st, E, E, (int)TB, W.dxh0, E + H, 1, W.emb, E, 1, g.comb_w, 2 * E)));                    // dW_c[:, :E]
+  B2C_TRY((gemm<T, float>(st, E, E, (int)TB, W.dxh0, E + H, 1, W.ctx, E, 1, g.comb_w + E, 2 * E)));                // dW_c[:, E:]
+  B2C_TRY(colsum<T>(st, W.dxh0, TB, E, E + H, W.partial, g.comb_b));
+  B2C_TRY((gemm<T, float>(st, (int)TB, E, E, W.dxh0, E + H, 0, W.w.Wce, E, 1, W.demb, E)));
+  B2C_CUDA(cudaMemsetAsync(g.embedding, 0, (size_t)V * E * sizeof(float), st));
+  embedding_scatter_add_kernel<<<ew_grid(TB * E), 256, 0, st>>>(W.demb, cap, TB, E, V, g.embedding);
+  B2C_LAUNCH_CHECK("embedding_scatter_add_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------ greedy decode (eval, argmax fed back on device)
+template <typename T>
+int greedy_decode_impl(const B2CShape& s, const B2CParams& p, const T* feats, int64_t start_id, int64_t end_id,
+                       int64_t* tokens, int32_t* lengths, void* ws, size_t ws_bytes, cudaStream_t st) {
+  DecodeWs<T> W; W.carve(ws, s);
+  B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
+  const int B = s.B, Tn = s.T, S = s.S, E = s.E, H = s.H, L = s.L, V = s.V;
+  const B2CDropout nodrop{0.f, 0};
+  B2C_TRY(pack_params<T>(s, p, W.w, st));
+  B2C_TRY((gemm<T, T>(st, B * S, E, E, feats, E, 0, W.w.Wf, E, 0, W.P, E, 0.f, p.attn_b)));
+  for (int k = 0; k < L; ++k) {
+    B2C_CUDA(cudaMemsetAsync(W.xh[k], 0, (size_t)B * (in_dim(s, k) + H) * sizeof(T), st));
+    B2C_CUDA(cudaMemsetAsync(W.c[k], 0, (size_t)B * H * sizeof(float), st));
+  }
+  fill_i64_kernel<<<ew_grid(B), 256, 0, st>>>(W.cur, B, start_id);
+  B2C_LAUNCH_CHECK("fill_i64_kernel");
+  const int inL = in_dim(s, L - 1), ldL = inL + H;
+  for (int t = 0; t < Tn; ++t) {
+    embedding_gather_kernel<T><<<ew_grid((long)B * E / 4), 256, 0, st>>>(p.embedding, W.cur, B, E, V, W.emb, E);
+    B2C_LAUNCH_CHECK("embedding_gather_kernel");
+    B2C_TRY((gemm<T, T>(st, B, E, E, W.emb, E, 0, W.w.Wce, E, 0, W.xh[0], E + H, 0.f, p.comb_b)));
+    B2C_TRY((gemm<T, T>(st, B, E, H, W.xh[L - 1] + inL, ldL, 0, W.w.Wh, H, 0, W.u, E)));
+    B2C_TRY(attn_fwd<T>(st, s, W.P, feats, W.u, W.ctx, nullptr));
+    B2C_TRY((gemm<T, T>(st, B, E, E, W.ctx, E, 0, W.w.Wcc, E, 0, W.xh[0], E + H, 1.f)));
+    for (int k = 0; k < L; ++k) {
+      const int in = in_dim(s, k);
+      B2C_TRY(lstm_layer_fwd<T>(st, s, W.w, k, W.xh[k], W.pre, W.c[k], W.c[k], (T*)nullptr, W.xh[k] + in,
+                                k + 1 < L ? W.xh[k + 1] : nullptr, (T*)nullptr, nodrop, 0));
+    }
+    B2C_TRY((gemm<T, T>(st, B, E, H, W.xh[L - 1] + inL, ldL, 0, W.w.W1, H, 0, W.o1, E, 0.f, p.out0_b, 1)));
+    B2C_TRY((gemm<T, float>(st, B, V, E, W.o1, E, 0, W.w.W2, E, 0, W.logits, V, 0.f, p.out3_b)));
+    argmax_feedback_kernel<<<B, 256, 0, st>>>(W.logits, V, V, end_id, t, W.cur, tokens + (long)t * B, lengths, W.done);
+    B2C_LAUNCH_CHECK("argmax_feedback_kernel");
+  }
+  finish_lengths_kernel<<<cdiv(B, 256), 256, 0, st>>>(lengths, B, Tn);
+  B2C_LAUNCH_CHECK("finish_lengths_kernel");
+  return 0;
+}
+
+template <typename T> struct AttnWs {
+  T *Wh, *Wf, *P, *u; size_t bytes;
+  void carve(void* base, const B2CShape& s) {
+    Carver c{reinterpret_cast<unsigned char*>(base), 0};
+    Wh = c.take<T>((size_t)s.E * s.H); Wf = c.take<T>((size_t)s.E * s.E);
+    P = c.take<T>((size_t)s.B * s.S * s.E); u = c.take<T>((size_t)s.B * s.E);
+    bytes = align_up(c.off, 256);
+  }
+};
+
+template <typename T>
+int attention_step_impl(const B2CShape& s, const float* attn_w, const float* attn_b, const T* hidden, const T* feats,
+                        T* context, float* weights, void* ws, size_t ws_bytes, cudaStream_t st) {
+  AttnWs<T> W; W.carve(ws, s);
+  B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
+  const int B = s.B, S = s.S, E = s.E, H = s.H;
+  PackTable tab; tab.n = 2;
+  tab.seg[0] = PackSeg{attn_w, W.Wh, nullptr, E, H, (long)H + E, (long)H, 0};
+  tab.seg[1] = PackSeg{attn_w + H, W.Wf, nullptr, E, E, (long)H + E, (long)E, 0};
+  pack_params_kernel<T><<<dim3(32, 2), 256, 0, st>>>(tab);
+  B2C_LAUNCH_CHECK("pack_params_kernel");
+  B2C_TRY((gemm<T, T>(st, B * S, E, E, feats, E, 0, W.Wf, E, 0, W.P, E, 0.f, attn_b)));
+  B2C_TRY((gemm<T, T>(st, B, E, H, hidden, H, 0, W.Wh, H, 0, W.u, E)));
+  return attn_fwd<T>(st, s, W.P, feats, W.u, context, weights);
+}
+
+template <typename TS>
+int kd_token_loss_impl(const TS* y, const float* z, const int64_t* tgt, long N, int V, float temperature, float alpha,
+                       float w_ce_eff, const int* n_valid, TS* dy, float* row_kl, float* row_ce, cudaStream_t st) {
+  const bool vec = (V % 8 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)z % 16 == 0) && ((uintptr_t)dy % 16 == 0);
+  const bool t4 = (temperature == 4.0f);
+  const size_t smem = align_up((size_t)V * 4, 16) + align_up((size_t)V * sizeof(TS), 16);
+  const float inv_temp = 1.0f / temperature, kd_coef = alpha * temperature / (float)N;
+#define B2C_KD_LAUNCH(G, T4)                                                                                             \
+  do {                                                                                                                   \
+    B2C_TRY(set_smem(kd_token_loss_kernel<TS, G, T4>, smem));                                                            \
+    kd_token_loss_kernel<TS, G, T4><<<(unsigned)N, KD_THREADS, smem, st>>>(y, z, tgt, V, inv_temp, kd_coef, w_ce_eff, n_valid, dy, row_kl, row_ce); \
+  } while (0)
+  if (vec && t4) B2C_KD_LAUNCH(8, true);
+  else if (vec) B2C_KD_LAUNCH(8, false);
+  else if (t4) B2C_KD_LAUNCH(1, true);
+  else B2C_KD_LAUNCH(1, false);
+#undef B2C_KD_LAUNCH
+  B2C_LAUNCH_CHECK("kd_token_loss_kernel");
+  return 0;
+}
+
+template <typename TF>
+int aux_loss_impl(const TF* fs, const float* ft, int B, int Ss, int St, int E, const TF* hs, const float* ht, int Tn, int Th, int H,
+                  float beta, float gamma, float* dfs, float* dft, TF* dhs, float* feat_part, float* hid_part, cudaStream_t st) {
+  const int nfb = fs ? B : 0;
+  const long all_rows = hs ? (long)Tn * B : 0;
+  const int hid_blocks = (int)((all_rows + 7) / 8);
+  if (nfb + hid_blocks == 0) return 0;
+  const size_t smem = fs ? (size_t)(2 * Ss + 2 * St + 2 * E) * 4 : 0;
+  B2C_TRY(set_smem(aux_loss_kernel<TF, TF>, smem));
+  aux_loss_kernel<TF, TF><<<nfb + hid_blocks, 256, smem, st>>>(fs, ft, nfb, B, Ss, St, E, hs, ht, (int)((long)Th * B), (int)all_rows, H, Th, beta, gamma,
+                                                               dfs, dft, dhs, feat_part, hid_part);
+  B2C_LAUNCH_CHECK("aux_loss_kernel");
+  return 0;
+}
+
+}  // namespace
+
+// ====================================================================================== extern "C"
+extern "C" {
+
+int b2c_abi_version(void) { return B2C_ABI_VERSION; }
+const char* b2c_last_error(void) { return err_buf(); }
+uint64_t b2c_launch_count(void) { return (uint64_t)launch_counter(); }
+
+size_t b2c_workspace_bytes(const B2CShape* shape, int dtype, int mode) {
+  if (check_shape(shape) != 0) return 0;
+  if (mode == B2C_WS_TRAIN) {
+    if (dtype == B2C_F32) { TrainWs<float> w; w.carve(nullptr, *shape); return w.bytes; }
+    if (dtype == B2C_BF16) { TrainWs<bf16> w; w.carve(nullptr, *shape); return w.bytes; }
+  } else if (mode == B2C_WS_DECODE) {
+    if (dtype == B2C_F32) { DecodeWs<float> w; w.carve(nullptr, *shape); return w.bytes; }
+    if (dtype == B2C_BF16) { DecodeWs<bf16> w; w.carve(nullptr, *shape); return w.bytes; }
+  } else if (mode == B2C_WS_ATTN) {
+    if (dtype == B2C_F32) { AttnWs<float> w; w.carve(nullptr, *shape); return w.bytes; }
+    if (dtype == B2C_BF16) { AttnWs<bf16> w; w.carve(nullptr, *shape); return w.bytes; }
+  }
+  set_err(B2C_EINVAL, "bad dtype %d / mode %d", dtype, mode);
+  return 0;
+}
+
+int b2c_decoder_forward(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
+                        void* logits, void* hidden_top, float* attn_w, void* workspace, size_t ws_bytes,
+                        int dtype, const B2CDropout* dropout, void* stream) {
+  B2C_TRY(check_shape(shape)); B2C_TRY(check_device());
+  B2C_CHECK_ARG(params && feats && captions && logits && hidden_top && attn_w && workspace, "NULL argument");
+  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0};
+  B2C_CHECK_ARG(dr.p >= 0.f && dr.p < 1.f, "dropout p=%f outside [0,1)", dr.p);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) return decoder_forward_impl<float>(*shape, *params, (const float*)feats, captions, (float*)logits, (float*)hidden_top, attn_w, workspace, ws_bytes, dr, st);
+  if (dtype == B2C_BF16) return decoder_forward_impl<bf16>(*shape, *params, (const bf16*)feats, captions, (bf16*)logits, (bf16*)hidden_top, attn_w, workspace, ws_bytes, dr, st);
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_decoder_backward(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
+                         const void* hidden_top, const float* attn_w, const void* dlogits, const void* dhidden_top,
+                         const B2CGrads* grads, float* dfeats, void* workspace, size_t ws_bytes,
+                         int dtype, const B2CDropout* dropout, void* stream) {
+  B2C_TRY(check_shape(shape)); B2C_TRY(check_device());
+  B2C_CHECK_ARG(params && feats && captions && hidden_top && attn_w && dlogits && grads && workspace, "NULL argument");
+  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) return decoder_backward_impl<float>(*shape, *params, (const float*)feats, captions, (const float*)hidden_top, attn_w, (const float*)dlogits, (const float*)dhidden_top, *grads, dfeats, workspace, ws_bytes, dr, st);
+  if (dtype == B2C_BF16) return decoder_backward_impl<bf16>(*shape, *params, (const bf16*)feats, captions, (const bf16*)hidden_top, attn_w, (const bf16*)dlogits, (const bf16*)dhidden_top, *grads, dfeats, workspace, ws_bytes, dr, st);
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_greedy_decode(const B2CShape* shape, const B2CParams* params, const void* feats, int64_t start_id, int64_t end_id,
+                      int64_t* tokens, int32_t* lengths, void* workspace, size_t ws_bytes, int dtype, void* stream) {
+  B2C_TRY(check_shape(shape)); B2C_TRY(check_device());
+  B2C_CHECK_ARG(params && feats && tokens && lengths && workspace, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) return greedy_decode_impl<float>(*shape, *params, (const float*)feats, start_id, end_id, tokens, lengths, workspace, ws_bytes, st);
+  if (dtype == B2C_BF16) return greedy_decode_impl<bf16>(*shape, *params, (const bf16*)feats, start_id, end_id, tokens, lengths, workspace, ws_bytes, st);
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_attention_step(const B2CShape* shape, const float* attn_w, const float* attn_b, const void* hidden, const void* feats,
+                       void* context, float* weights, void* workspace, size_t ws_bytes, int dtype, void* stream) {
+  B2C_TRY(check_shape(shape)); B2C_TRY(check_device());
+  B2C_CHECK_ARG(attn_w && attn_b && hidden && feats && context && weights && workspace, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) return attention_step_impl<float>(*shape, attn_w, attn_b, (const float*)hidden, (const float*)feats, (float*)context, weights, workspace, ws_bytes, st);
+  if (dtype == B2C_BF16) return attention_step_impl<bf16>(*shape, attn_w, attn_b, (const bf16*)hidden, (const bf16*)feats, (bf16*)context, weights, workspace, ws_bytes, st);
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_count_valid(const int64_t* targets, int64_t n, int32_t V, int32_t* n_valid_out, void* stream) {
+  B2C_TRY(check_device());
+  B2C_CHECK_ARG(targets && n_valid_out && n > 0, "bad argument");
+  count_valid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(targets, (long)n, V, n_valid_out);
+  B2C_LAUNCH_CHECK("count_valid_kernel");
+  return 0;
+}
+
+int b2c_kd_token_loss(const void* student_logits, const float* teacher_logits, const int64_t* targets,
+                      int64_t N, int32_t V, float temperature, float alpha, float w_ce, float ce_mult,
+                      const int32_t* n_valid, void* dlogits, float* row_kl, float* row_ce, int dtype, void* stream) {
+  B2C_TRY(check_device());
+  B2C_CHECK_ARG(student_logits && teacher_logits && targets && n_valid && dlogits && row_kl && row_ce, "NULL argument");
+  B2C_CHECK_ARG(N > 0 && N < 2147483647L && V > 1 && temperature > 0.f, "bad N=%ld V=%d temperature=%f", (long)N, V, temperature);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) return kd_token_loss_impl<float>((const float*)student_logits, teacher_logits, targets, (long)N, V, temperature, alpha, w_ce * ce_mult, n_valid, (float*)dlogits, row_kl, row_ce, st);
+  if (dtype == B2C_BF16) return kd_token_loss_impl<bf16>((const bf16*)student_logits, teacher_logits, targets, (long)N, V, temperature, alpha, w_ce * ce_mult, n_valid, (bf16*)dlogits, row_kl, row_ce, st);
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_aux_loss(const void* feats_s, const float* feats_t, int32_t B, int32_t Ss, int32_t St, int32_t E,
+                 const void* hid_s, const float* hid_t, int32_t T, int32_t Th, int32_t H,
+                 float beta, float gamma, float* dfeats_s, float* dfeats_t, void* dhid_s,
+                 float* feat_part, float* hid_part, int dtype, void* stream) {
+  B2C_TRY(check_device());
+  B2C_CHECK_ARG(B > 0, "B=%d", B);
+  if (feats_s) B2C_CHECK_ARG(feats_t && feat_part && Ss > 0 && St > 0 && E > 0, "feature KD needs feats_t, feat_part and positive Ss/St/E");
+  if (hid_s) B2C_CHECK_ARG(hid_t && hid_part && T > 0 && Th > 0 && Th <= T && H > 0, "hidden KD needs hid_t, hid_part and 0 < Th <= T");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) return aux_loss_impl<float>((const float*)feats_s, feats_t, B, Ss, St, E, (const float*)hid_s, hid_t, T, Th, H, beta, gamma, dfeats_s, dfeats_t, (float*)dhid_s, feat_part, hid_part, st);
+  if (dtype == B2C_BF16) return aux_loss_impl<bf16>((const bf16*)feats_s, feats_t, B, Ss, St, E, (const bf16*)hid_s, hid_t, T, Th, H, beta, gamma, dfeats_s, dfeats_t, (bf16*)dhid_s, feat_part, hid_part, st);
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_loss_finalize(const float* row_kl, const float* row_ce, int64_t N, const int32_t* n_valid, float ce_mult,
+                      const float* feat_part, int32_t B, int32_t E, const float* hid_part, int32_t Th, int32_t H,
+                      float temperature, float alpha, float beta, float gamma, float w_ce, float* out5, void* stream) {
+  B2C_TRY(check_device());
+  B2C_CHECK_ARG(row_kl && row_ce && n_valid && out5 && N > 0 && B > 0, "bad argument");
+  loss_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_kl, row_ce, (long)N, n_valid, feat_part, B, E, feat_part ? 1 : 0,
+                                                            hid_part, (long)Th * B, H, Th, hid_part ? 1 : 0,
+                                                            temperature, alpha, beta, gamma, w_ce, ce_mult, out5);
+  B2C_LAUNCH_CHECK("loss_finalize_kernel");
+  return 0;
+}
+
+int b2c_scale_inplace(void* p, int64_t n, int dtype, const float* scale, void* stream) {
+  B2C_TRY(check_device());
+  B2C_CHECK_ARG(p && scale && n >= 0, "bad argument");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) scale_inplace_kernel<float><<<ew_grid(n), 256, 0, st>>>((float*)p, (long)n, scale);
+  else if (dtype == B2C_BF16) scale_inplace_kernel<bf16><<<ew_grid(n), 256, 0, st>>>((bf16*)p, (long)n, scale);
+  else return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+  B2C_LAUNCH_CHECK("scale_inplace_kernel");
+  return 0;
+}
+
+int b2c_gemm(int32_t M, int32_t N, int32_t K, float alpha, const void* A, int64_t lda, int a_mn,
+             const void* B, int64_t ldb, int b_mn, float beta, void* C, int64_t ldc, const float* bias, int relu,
+             int dtype, int c_dtype, int impl, void* stream) {
+  B2C_TRY(check_device());
+  B2C_CHECK_ARG(M > 0 && N > 0 && K > 0 && A && B && C, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmArgs g{M, N, K, alpha, beta, A, (long)lda, a_mn, B, (long)ldb, b_mn, C, (long)ldc, bias, relu};
+  if (dtype == B2C_F32) {
+    B2C_CHECK_ARG(c_dtype == B2C_F32, "fp32 operands produce fp32 output");
+    return gemm_simt<float, float, float>(g, st);
+  }
+  if (dtype == B2C_BF16) {
+    if (impl == 1) return c_dtype == B2C_F32 ? gemm_simt<bf16, bf16, float>(g, st) : gemm_simt<bf16, bf16, bf16>(g, st);
+    return c_dtype == B2C_F32 ? Gemm<bf16, float>::run(g, st) : Gemm<bf16, bf16>::run(g, st);
+  }
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+}  // extern "C"

@@ -24,7 +24,8 @@ inline int set_err(int code, const char* fmt, ...) {
 #define B2C_CHECK_ARG(cond, ...) do { if (!(cond)) return b2c::set_err(B2C_EINVAL, __VA_ARGS__); } while (0)
 #define B2C_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
     return b2c::set_err(B2C_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
-#define B2C_LAUNCH_CHECK(name) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
+inline unsigned long long& launch_counter() { static unsigned long long n = 0; return n; }
+#define B2C_LAUNCH_CHECK(name) do { ++b2c::launch_counter(); cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
     return b2c::set_err(B2C_ECUDA, "launch of %s failed: %s (%s:%d)", name, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 #define B2C_TRY(expr) do { int r_ = (expr); if (r_ != 0) return r_; } while (0)
 
@@ -104,8 +105,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+// Bounded wait: a lost arrival (bad tensor map, wrong expect_tx) traps with a launch failure instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) { }
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    if (spins > (1u << 24)) { printf("b2c: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+  }
 }
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); size and both addresses 16-byte aligned.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {

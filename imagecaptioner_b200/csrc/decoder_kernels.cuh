@@ -1,0 +1,334 @@
+// Kernels (1) and the pointwise glue of the decoder hot path.  Math: SURVEY.md Appendix A.1/A.2,
+// reference src/student_model.py:173-203 (attention), :232-251 (step), :339-381 (greedy loop).
+#pragma once
+#include "common.cuh"
+
+namespace b2c {
+
+// ======================================================================================
+// Parameter packing: fp32 master weights -> compute-type operand buffers, one launch.
+// ======================================================================================
+struct PackSeg {
+  const float* src; void* dst;
+  const float* src2;        // optional: dst = src + src2 (bias_ih + bias_hh)
+  int rows, cols; long lds, ldd;
+  int as_float;             // 1: dst is fp32 regardless of T (bias vectors)
+};
+constexpr int PACK_MAX_SEGS = 20;
+struct PackTable { PackSeg seg[PACK_MAX_SEGS]; int n; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_params_kernel(const __grid_constant__ PackTable tab) {
+  const PackSeg& s = tab.seg[blockIdx.y];
+  const long total = (long)s.rows * s.cols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / s.cols; const int c = (int)(i - r * s.cols);
+    float v = s.src[r * s.lds + c];
+    if (s.src2) v += s.src2[r * s.lds + c];
+    if (s.as_float) reinterpret_cast<float*>(s.dst)[r * s.ldd + c] = v;
+    else reinterpret_cast<T*>(s.dst)[r * s.ldd + c] = from_f<T>(v);
+  }
+}
+
+// emb[r,:] = table[ids[r],:]   (ids out of range -> row 0, like a clamped lookup; the host validates nothing here)
+template <typename T>
+__global__ void __launch_bounds__(256) embedding_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids,
+                                                               long rows, int E, int V, T* __restrict__ out, long ldo) {
+  const int per = E / 4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * per; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / per; const int c = (int)(i - r * per) * 4;
+    long id = ids[r]; if (id < 0 || id >= V) id = 0;
+    const float4 v = *reinterpret_cast<const float4*>(table + id * E + c);
+    T* o = out + r * ldo + c;
+    o[0] = from_f<T>(v.x); o[1] = from_f<T>(v.y); o[2] = from_f<T>(v.z); o[3] = from_f<T>(v.w);
+  }
+}
+
+// dtable[ids[r],:] += drows[r,:]
+__global__ void __launch_bounds__(256) embedding_scatter_add_kernel(const float* __restrict__ drows, const int64_t* __restrict__ ids,
+                                                                    long rows, int E, int V, float* __restrict__ dtable) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * E; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / E; const int c = (int)(i - r * E);
+    long id = ids[r]; if (id < 0 || id >= V) id = 0;
+    atomicAdd(dtable + id * E + c, drows[i]);
+  }
+}
+
+// ======================================================================================
+// Kernel (1): one decode step of spatial attention for one sample per CTA.
+//   s_l = sum_e tanh(P[l,e] + u[e]);  w = softmax_l(s);  ctx[e] = sum_l w_l F[l,e]
+// P_b and F_b (S x E each, contiguous) are staged in shared memory by two 1-D TMA bulk copies.
+// ======================================================================================
+constexpr int ATT_THREADS = 256;
+
+template <typename T>
+__device__ __forceinline__ void att_stage(const T* P, const T* F, int b, int SE, T* Ps, T* Fs, uint64_t* bar) {
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)(SE * sizeof(T));
+    mbar_arrive_expect_tx(bar, (Ps ? bytes : 0u) + (Fs ? bytes : 0u));
+    if (Ps) bulk_g2s(Ps, P + (long)b * SE, bytes, bar);
+    if (Fs) bulk_g2s(Fs, F + (long)b * SE, bytes, bar);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_step_fwd_kernel(const T* __restrict__ P, const T* __restrict__ F, const T* __restrict__ u, long ldu,
+                     int S, int E, T* __restrict__ ctx, long ldctx, float* __restrict__ attw /* (B,S) or null */) {
+  extern __shared__ __align__(128) unsigned char att_smem[];
+  const int SE = S * E;
+  T* Ps = reinterpret_cast<T*>(att_smem);
+  T* Fs = Ps + SE;
+  float* us = reinterpret_cast<float*>(Fs + SE);
+  float* sc = us + E;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATT_THREADS / 32;
+  const int b = blockIdx.x;
+  att_stage<T>(P, F, b, SE, Ps, Fs, &bar);
+  for (int e = tid; e < E; e += ATT_THREADS) us[e] = to_f<T>(u[(long)b * ldu + e]);
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  for (int l = warp; l < S; l += nwarp) {
+    float a = 0.f;
+    for (int e = lane; e < E; e += 32) a += Math<T>::tanh_(to_f<T>(Ps[l * E + e]) + us[e]);
+    a = warp_sum(a);
+    if (lane == 0) sc[l] = a;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float m = -INFINITY;
+    for (int l = lane; l < S; l += 32) m = fmaxf(m, sc[l]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int l = lane; l < S; l += 32) { const float e = Math<T>::exp_(sc[l] - m); sc[l] = e; s += e; }
+    s = warp_sum(s);
+    const float inv = 1.0f / s;
+    for (int l = lane; l < S; l += 32) { const float wv = sc[l] * inv; sc[l] = wv; if (attw) attw[(long)b * S + l] = wv; }
+  }
+  __syncthreads();
+  for (int e = tid; e < E; e += ATT_THREADS) {
+    float a = 0.f;
+    for (int l = 0; l < S; ++l) a = fmaf(sc[l], to_f<T>(Fs[l * E + e]), a);
+    ctx[(long)b * ldctx + e] = from_f<T>(a);
+  }
+}
+
+// Backward of one attention step (inside the reverse time loop): ds (B,S) and du (B,E).
+//   dw_l = sum_e dctx_e F[l,e];  ds_l = w_l (dw_l - sum_j w_j dw_j);  du_e = sum_l ds_l (1 - tanh^2(P[l,e]+u_e))
+template <typename T>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_step_bwd_kernel(const T* __restrict__ P, const T* __restrict__ F, const T* __restrict__ u, long ldu,
+                     const float* __restrict__ attw, const T* __restrict__ dctx, long lddctx,
+                     int S, int E, float* __restrict__ ds_out, T* __restrict__ du, long lddu) {
+  extern __shared__ __align__(128) unsigned char att_smem[];
+  const int SE = S * E;
+  T* Ps = reinterpret_cast<T*>(att_smem);
+  T* Fs = Ps + SE;
+  float* us = reinterpret_cast<float*>(Fs + SE);
+  float* dcs = us + E;
+  float* dw = dcs + E;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATT_THREADS / 32;
+  const int b = blockIdx.x;
+  att_stage<T>(P, F, b, SE, Ps, Fs, &bar);
+  for (int e = tid; e < E; e += ATT_THREADS) { us[e] = to_f<T>(u[(long)b * ldu + e]); dcs[e] = to_f<T>(dctx[(long)b * lddctx + e]); }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  for (int l = warp; l < S; l += nwarp) {
+    float a = 0.f;
+    for (int e = lane; e < E; e += 32) a = fmaf(dcs[e], to_f<T>(Fs[l * E + e]), a);
+    a = warp_sum(a);
+    if (lane == 0) dw[l] = a;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float dot = 0.f;
+    for (int l = lane; l < S; l += 32) dot = fmaf(attw[(long)b * S + l], dw[l], dot);
+    dot = warp_sum(dot);
+    for (int l = lane; l < S; l += 32) { const float v = attw[(long)b * S + l] * (dw[l] - dot); dw[l] = v; ds_out[(long)b * S + l] = v; }
+  }
+  __syncthreads();
+  for (int e = tid; e < E; e += ATT_THREADS) {
+    float a = 0.f; const float ue = us[e];
+    for (int l = 0; l < S; ++l) { const float th = Math<T>::tanh_(to_f<T>(Ps[l * E + e]) + ue); a = fmaf(dw[l], 1.0f - th * th, a); }
+    du[(long)b * lddu + e] = from_f<T>(a);
+  }
+}
+
+// After the reverse loop, one pass per sample over all steps:
+//   dP[l,e]      = sum_t ds[t,l] (1 - tanh^2(P[l,e] + u[t,e]))
+//   dF_attn[l,e] = sum_t w[t,l] dctx[t,e]
+// u/dctx/w/ds for all T steps of this sample sit in shared memory (T*(2E+2S) floats).
+template <typename T>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_post_kernel(const T* __restrict__ P, const T* __restrict__ u /*(T,B,E)*/, const T* __restrict__ dctx /*(T,B,E)*/,
+                 const float* __restrict__ attw /*(T,B,S)*/, const float* __restrict__ ds /*(T,B,S)*/,
+                 int Tn, int B, int S, int E, T* __restrict__ dP, float* __restrict__ dF) {
+  extern __shared__ __align__(128) unsigned char att_smem[];
+  float* us = reinterpret_cast<float*>(att_smem);     // Tn*E
+  float* dcs = us + (long)Tn * E;                      // Tn*E
+  float* ws = dcs + (long)Tn * E;                      // Tn*S
+  float* dss = ws + (long)Tn * S;                      // Tn*S
+  const int tid = threadIdx.x, b = blockIdx.x;
+  for (int i = tid; i < Tn * E; i += ATT_THREADS) { const int t = i / E, e = i - t * E; us[i] = to_f<T>(u[((long)t * B + b) * E + e]); dcs[i] = to_f<T>(dctx[((long)t * B + b) * E + e]); }
+  for (int i = tid; i < Tn * S; i += ATT_THREADS) { const int t = i / S, l = i - t * S; ws[i] = attw[((long)t * B + b) * S + l]; dss[i] = ds[((long)t * B + b) * S + l]; }
+  __syncthreads();
+  const long base = (long)b * S * E;
+  for (int idx = tid; idx < S * E; idx += ATT_THREADS) {
+    const int l = idx / E, e = idx - l * E;
+    const float p = to_f<T>(P[base + idx]);
+    float aP = 0.f, aF = 0.f;
+    for (int t = 0; t < Tn; ++t) {
+      const float th = Math<T>::tanh_(p + us[t * E + e]);
+      aP = fmaf(dss[t * S + l], 1.0f - th * th, aP);
+      aF = fmaf(ws[t * S + l], dcs[t * E + e], aF);
+    }
+    dP[base + idx] = from_f<T>(aP);
+    dF[base + idx] = aF;
+  }
+}
+
+// ======================================================================================
+// LSTM cell pointwise (gate order i,f,g,o; pre already holds both biases)
+// ======================================================================================
+// h goes to up to three places: the recurrent slot (next step's [input;h] row block), the next layer's input
+// (inter-layer dropout applied in training) and the top-layer output buffer.
+template <typename T>
+__global__ void __launch_bounds__(256)
+lstm_pointwise_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ c_prev, float* __restrict__ c_out,
+                          T* __restrict__ gates_out, T* __restrict__ h_rec, long ld_rec, T* __restrict__ h_next, long ld_next,
+                          T* __restrict__ h_top, long ld_top, int B, int H,
+                          float drop_p, uint64_t seed, uint32_t site, long row_base) {
+  const long total = (long)B * H;
+  const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long b = idx / H; const int j = (int)(idx - b * H);
+    const float* pr = pre + b * 4 * H;
+    const float i = Math<T>::sigmoid_(pr[j]), f = Math<T>::sigmoid_(pr[H + j]);
+    const float g = Math<T>::tanh_(pr[2 * H + j]), o = Math<T>::sigmoid_(pr[3 * H + j]);
+    const float c = fmaf(f, c_prev[idx], i * g);
+    const float h = o * Math<T>::tanh_(c);
+    c_out[idx] = c;
+    if (gates_out) {
+      T* go = gates_out + b * 4 * H;
+      go[j] = from_f<T>(i); go[H + j] = from_f<T>(f); go[2 * H + j] = from_f<T>(g); go[3 * H + j] = from_f<T>(o);
+    }
+    if (h_rec) h_rec[b * ld_rec + j] = from_f<T>(h);
+    if (h_next) {
+      const float m = drop_p > 0.f ? dropout_scale(seed, site, (uint64_t)((row_base + b) * H + j), drop_p, inv_keep) : 1.0f;
+      h_next[b * ld_next + j] = from_f<T>(h * m);
+    }
+    if (h_top) h_top[b * ld_top + j] = from_f<T>(h);
+  }
+}
+
+// dh = [carry] + [dh_b * mask] + [dh_ext] + [dh_hid] + [dh_q]; then the cell adjoint; dc is updated in place.
+template <typename T>
+__global__ void __launch_bounds__(256)
+lstm_pointwise_bwd_kernel(const T* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_cur,
+                          float* __restrict__ dc, int dc_is_zero,
+                          const T* __restrict__ dh_carry, long ld_carry, const T* __restrict__ dh_above, long ld_above,
+                          const float* __restrict__ dh_ext, const T* __restrict__ dh_hid, const T* __restrict__ dh_q, long ld_q,
+                          T* __restrict__ dgates, int B, int H, float drop_p, uint64_t seed, uint32_t site, long row_base) {
+  const long total = (long)B * H;
+  const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long b = idx / H; const int j = (int)(idx - b * H);
+    float dh = 0.f;
+    if (dh_carry) dh += to_f<T>(dh_carry[b * ld_carry + j]);
+    if (dh_above) {
+      const float m = drop_p > 0.f ? dropout_scale(seed, site, (uint64_t)((row_base + b) * H + j), drop_p, inv_keep) : 1.0f;
+      dh += to_f<T>(dh_above[b * ld_above + j]) * m;
+    }
+    if (dh_ext) dh += dh_ext[idx];
+    if (dh_hid) dh += to_f<T>(dh_hid[idx]);
+    if (dh_q) dh += to_f<T>(dh_q[b * ld_q + j]);
+    const T* gt = gates + b * 4 * H;
+    const float i = to_f<T>(gt[j]), f = to_f<T>(gt[H + j]), g = to_f<T>(gt[2 * H + j]), o = to_f<T>(gt[3 * H + j]);
+    const float tc = Math<T>::tanh_(c_cur[idx]);
+    const float dcc = (dc_is_zero ? 0.f : dc[idx]) + dh * o * (1.0f - tc * tc);
+    T* dg = dgates + b * 4 * H;
+    dg[j] = from_f<T>(dcc * g * i * (1.0f - i));
+    dg[H + j] = from_f<T>(dcc * c_prev[idx] * f * (1.0f - f));
+    dg[2 * H + j] = from_f<T>(dcc * i * (1.0f - g * g));
+    dg[3 * H + j] = from_f<T>(dh * tc * o * (1.0f - o));
+    dc[idx] = dcc * f;
+  }
+}
+
+// ======================================================================================
+// small glue
+// ======================================================================================
+// output_projection dropout (training only): o1 *= keep-mask/(1-p)
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_inplace_kernel(T* __restrict__ x, long n, float p, uint64_t seed, uint32_t site) {
+  const float inv_keep = 1.0f / (1.0f - p);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    x[i] = from_f<T>(to_f<T>(x[i]) * dropout_scale(seed, site, (uint64_t)i, p, inv_keep));
+}
+// d(pre-ReLU, pre-dropout) = d(o1) * [o1 > 0] / (1-p)      (o1 is the saved post-ReLU, post-dropout activation)
+template <typename T>
+__global__ void __launch_bounds__(256) relu_bwd_inplace_kernel(T* __restrict__ d, const T* __restrict__ act, long n, float inv_keep) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    d[i] = from_f<T>(to_f<T>(act[i]) > 0.f ? to_f<T>(d[i]) * inv_keep : 0.f);
+}
+
+// column sums of a (rows, cols) matrix with pitch ld: grid (ceil(cols/32), RS); partial[(rs, col)]
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ A, long rows, int cols, long ld, float* __restrict__ partial) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  const long per = (rows + gridDim.y - 1) / gridDim.y;
+  const long r0 = (long)blockIdx.y * per, r1 = (r0 + per < rows) ? r0 + per : rows;
+  float a = 0.f;
+  if (col < cols) for (long r = r0 + ty; r < r1; r += 8) a += to_f<T>(A[r * ld + col]);
+  red[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && col < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][tx];
+    partial[(long)blockIdx.y * cols + col] = s;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int RS, int cols, float* __restrict__ out, float* __restrict__ out2) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= cols) return;
+  float s = 0.f;
+  for (int r = 0; r < RS; ++r) s += partial[(long)r * cols + col];
+  out[col] = s;
+  if (out2) out2[col] = s;
+}
+
+// Greedy feedback: tok[b] = argmax_v logits[b,v] (lowest index on ties, like torch.argmax); records the step's
+// tokens and the caption length (first <END>) without leaving the device.
+__global__ void __launch_bounds__(256)
+argmax_feedback_kernel(const float* __restrict__ logits, int V, long ld, int64_t end_id, int t,
+                       int64_t* __restrict__ cur_tok, int64_t* __restrict__ tokens_t, int32_t* __restrict__ lengths, int32_t* __restrict__ done) {
+  __shared__ float bv[8]; __shared__ int bi[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = logits + (long)b * ld;
+  float best = -INFINITY; int besti = 0x7fffffff;
+  for (int v = tid; v < V; v += 256) { const float x = row[v]; if (x > best || (x == best && v < besti)) { best = x; besti = v; } }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  if (lane == 0) { bv[warp] = best; bi[warp] = besti; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 1; i < 8; ++i) if (bv[i] > best || (bv[i] == best && bi[i] < besti)) { best = bv[i]; besti = bi[i]; }
+    if (besti == 0x7fffffff) besti = 0;      // all-NaN row
+    cur_tok[b] = besti; tokens_t[b] = besti;
+    if (t == 0) { done[b] = 0; lengths[b] = -1; }
+    if (besti == end_id && !done[b]) { done[b] = 1; lengths[b] = t; }
+  }
+}
+__global__ void fill_i64_kernel(int64_t* p, long n, int64_t v) { for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = v; }
+__global__ void finish_lengths_kernel(int32_t* lengths, int B, int T) { const int b = blockIdx.x * blockDim.x + threadIdx.x; if (b < B && lengths[b] < 0) lengths[b] = T; }
+
+}  // namespace b2c

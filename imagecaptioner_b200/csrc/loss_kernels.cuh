@@ -178,19 +178,18 @@ __global__ void count_valid_kernel(const int64_t* __restrict__ tgt, long n, int 
 }
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
 
-// Kernel (4).  blockIdx < B : feature KD for sample b (256 threads);  blockIdx >= B : hidden KD, one warp per
+// Kernel (4).  blockIdx < n_feat_blocks : feature KD for sample b (256 threads);  above : hidden KD, one warp per
 // (t,b) row.  Gradients already carry beta / gamma; loss partials go to workspace for the finalize kernel.
 template <typename TF, typename TH>
 __global__ void __launch_bounds__(256)
-aux_loss_kernel(const TF* __restrict__ fs, const float* __restrict__ ft, int B, int Ss, int St, int E,
+aux_loss_kernel(const TF* __restrict__ fs, const float* __restrict__ ft, int n_feat_blocks /*B or 0*/, int B, int Ss, int St, int E,
                 const TH* __restrict__ hs, const float* __restrict__ ht, int n_hid_rows /*Th*B*/, int n_all_rows /*T*B*/,
                 int H, int Th, float beta, float gamma,
                 float* __restrict__ dfs, float* __restrict__ dft, TH* __restrict__ dhs,
                 float* __restrict__ feat_part /*B*2*/, float* __restrict__ hid_part /*n_hid_rows*2*/) {
   extern __shared__ float sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-  if ((int)blockIdx.x < B) {
-    if (fs == nullptr) return;
+  if ((int)blockIdx.x < n_feat_blocks) {
     const int b = blockIdx.x;
     const TF* S = fs + (long)b * Ss * E;
     const float* Tp = ft + (long)b * St * E;
@@ -251,7 +250,7 @@ aux_loss_kernel(const TF* __restrict__ fs, const float* __restrict__ ft, int B, 
     }
   } else {
     if (hs == nullptr) return;
-    const long row = (long)(blockIdx.x - B) * nwarp + warp;
+    const long row = (long)(blockIdx.x - n_feat_blocks) * nwarp + warp;
     if (row >= n_all_rows) return;
     const TH* s = hs + row * H;
     TH* d = dhs ? dhs + row * H : nullptr;
@@ -284,7 +283,7 @@ __global__ void __launch_bounds__(1024)
 loss_finalize_kernel(const float* __restrict__ row_kl, const float* __restrict__ row_ce, long N, const int* __restrict__ n_valid_ptr,
                      const float* __restrict__ feat_part, int B, int E, int has_feat,
                      const float* __restrict__ hid_part, long n_hid_rows, int H, int Th, int has_hid,
-                     float temperature, float alpha, float beta, float gamma, float w_ce, float* __restrict__ out5) {
+                     float temperature, float alpha, float beta, float gamma, float w_ce, float ce_mult, float* __restrict__ out5) {
   __shared__ double red[32][5];
   double kl = 0, ce = 0, fg = 0, fa = 0, hm = 0, hc = 0;
   for (long i = threadIdx.x; i < N; i += blockDim.x) { kl += row_kl[i]; ce += row_ce[i]; }
@@ -299,7 +298,7 @@ loss_finalize_kernel(const float* __restrict__ row_kl, const float* __restrict__
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) for (int k = 0; k < 5; ++k) s[k] += red[w][k];
     const int nv = *n_valid_ptr;
     const double kd_l = (double)temperature * temperature * s[0] / (double)N;
-    const double ce_l = s[1] / (double)nv;                       // 0/0 -> NaN like the reference when every target is PAD
+    const double ce_l = s[1] * (double)ce_mult / (double)nv;                       // 0/0 -> NaN like the reference when every target is PAD
     const double ft_l = has_feat ? s[2] / ((double)B * E) : 0.0;
     const double hd_l = has_hid ? (0.7 * s[3] / ((double)B * H) + 0.3 * s[4] / (double)B) / (double)Th : 0.0;
     out5[0] = (float)((double)w_ce * ce_l + (double)alpha * kd_l + (double)beta * ft_l + (double)gamma * hd_l);

@@ -1,0 +1,83 @@
+"""Batch-sharded data parallelism for the KD step: one process per GPU, one flat gradient all-reduce.
+
+The reference has no distributed code; BASELINE.json's north_star adds data
+parallelism over the batch with NCCL only for the gradient all-reduce.  The step shards with no
+data-path collective (samples are independent through decoder, projector and every loss term), so
+the only exchanges are
+
+  * the gradient all-reduce (sum) over ONE flat fp32 buffer holding every trainable parameter's
+    gradient (7.33 M floats for the default student + projector), scaled by 1/world afterwards, and
+  * one int32 all-reduce of the non-PAD target count, because CrossEntropyLoss(ignore_index=0) divides
+    by the GLOBAL count (reference src/distillation_utils.py:22); KL 'batchmean', the MSE terms and the
+    cosine term have equal per-rank denominators, so their mean of per-rank means is already exact.
+
+Works with any torch.distributed backend (NCCL on the B200 box, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class FlatGradAllReducer:
+    """Owns one contiguous fp32 buffer; every parameter's ``.grad`` is a view into it, so autograd
+    accumulates straight into the buffer and the collective is a single call with no packing copies."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev = self.params[0].device
+        self.group = group
+        self.world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def zero_grad(self) -> None:
+        """Zero the buffer in place (keeps the .grad views; do NOT call optimizer.zero_grad(set_to_none=True))."""
+        self.flat.zero_()
+        off = 0
+        for p in self.params:                      # re-attach views if something replaced them
+            n = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.flat[off:off + n].data_ptr():
+                p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def allreduce(self, async_op: bool = False):
+        """Sum over ranks, then average.  With async_op the caller waits on the returned work and calls finish()."""
+        if self.world_size == 1:
+            return None
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+        if async_op:
+            return work
+        self.finish()
+        return None
+
+    def finish(self) -> None:
+        if self.world_size > 1:
+            self.flat.mul_(1.0 / self.world_size)
+
+
+def attach_loss_group(loss_module, group: Optional[dist.ProcessGroup] = None) -> None:
+    """Make DistillationLoss use the global non-PAD count (and the matching CE scale) under data parallelism."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        loss_module.process_group = group if group is not None else dist.group.WORLD
+        loss_module.world_size = dist.get_world_size(group)
+    else:
+        loss_module.process_group = None
+        loss_module.world_size = 1
+
+
+def shard_batch(n_global: int, rank: int, world_size: int) -> slice:
+    """Contiguous, even split of a global batch (the bench uses weak scaling: fixed per-rank batch)."""
+    if n_global % world_size != 0:
+        raise ValueError(f"global batch {n_global} is not divisible by world size {world_size}")
+    per = n_global // world_size
+    return slice(rank * per, (rank + 1) * per)

@@ -1,0 +1,153 @@
+/* b2c — C ABI of the B200-native KD hot path of VeeraKarthick609/ImageCaptioner.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; what this library replaces are the
+ * bodies of the reference's Python entry points on the hot path (citations are into /root/reference):
+ *
+ *   b2c_decoder_forward   <- LSTMDecoder.forward                    src/student_model.py:205-256
+ *                            (attention_mechanism :173-203, nn.LSTM step :244, output_projection :247)
+ *   b2c_decoder_backward  <- autograd of the above (loss.backward(), src/train_student_kd.py:288)
+ *   b2c_greedy_decode     <- CaptioningStudent.caption_image loop   src/student_model.py:339-381 (batched)
+ *   b2c_attention_step    <- LSTMDecoder.attention_mechanism          src/student_model.py:173-203 (stand-alone accessor)
+ *   b2c_count_valid       <- CrossEntropyLoss(ignore_index=0) normaliser  src/distillation_utils.py:22
+ *   b2c_kd_token_loss     <- token_level_distillation :30-54 + CE term :154 (+ their gradient)
+ *   b2c_aux_loss          <- encoder_feature_distillation :56-94 + decoder_hidden_state_distillation :96-136
+ *   b2c_loss_finalize     <- the alpha/beta/gamma weighting and loss_dict  :184-198
+ *   b2c_scale_inplace     <- the scalar grad_output of loss.backward() (GradScaler / accumulation, train_student_kd.py:285-288)
+ *   b2c_gemm              <- test hook for the tcgen05 / SIMT contraction tiles used inside the decoder
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host.
+ *   - The caller (PyTorch) owns every buffer; the library allocates nothing per call and keeps no pointer.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); calls are asynchronous.
+ *   - Return 0 on success, a negative B2C_E* code otherwise; message via b2c_last_error() (thread local).
+ *   - `dtype` selects the precision mode: B2C_F32 (parity mode: fp32 storage + FFMA contractions) or
+ *     B2C_BF16 (throughput mode: bf16 storage, tcgen05 contractions, fp32 accumulation and cell state).
+ *   - Time-major layouts like the reference: captions/targets (T,B) int64, logits (T,B,V).
+ *   - There is no CPU fallback.
+ */
+#ifndef B2C_H_
+#define B2C_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2C_ABI_VERSION 1
+#define B2C_MAX_LAYERS 4
+
+enum { B2C_OK = 0, B2C_EINVAL = -1, B2C_EARCH = -2, B2C_ECUDA = -3, B2C_ENOMEM = -4 };
+enum { B2C_F32 = 0, B2C_BF16 = 1 };
+enum { B2C_WS_TRAIN = 0, B2C_WS_DECODE = 1, B2C_WS_ATTN = 2 };
+
+/* B batch (per GPU), T decode steps, S image tokens (49), E embed, H hidden, L LSTM layers, V vocab. */
+typedef struct B2CShape { int32_t B, T, S, E, H, L, V; } B2CShape;
+
+/* fp32 master parameters of LSTMDecoder in the reference's own layouts (src/student_model.py:125-165);
+ * field <-> state_dict key:  embedding = decoder.embedding.weight (V,E); attn_w/attn_b = decoder.attention
+ * (E,H+E)/(E) [hidden columns first]; comb_w/comb_b = decoder.attention_combine (E,2E)/(E) [embedding
+ * columns first]; w_ih[k] (4H,in_k), w_hh[k] (4H,H), b_ih[k], b_hh[k] (4H) = decoder.lstm.*_l{k}, gate order
+ * i,f,g,o; out0_* = decoder.output_projection.0 (E,H); out3_* = decoder.output_projection.3 (V,E). */
+typedef struct B2CParams {
+  const float* embedding;
+  const float* attn_w;  const float* attn_b;
+  const float* comb_w;  const float* comb_b;
+  const float* w_ih[B2C_MAX_LAYERS]; const float* w_hh[B2C_MAX_LAYERS];
+  const float* b_ih[B2C_MAX_LAYERS]; const float* b_hh[B2C_MAX_LAYERS];
+  const float* out0_w;  const float* out0_b;
+  const float* out3_w;  const float* out3_b;
+} B2CParams;
+
+/* fp32 gradients, same layouts; every buffer is overwritten (not accumulated into). */
+typedef struct B2CGrads {
+  float* embedding;
+  float* attn_w;  float* attn_b;
+  float* comb_w;  float* comb_b;
+  float* w_ih[B2C_MAX_LAYERS]; float* w_hh[B2C_MAX_LAYERS];
+  float* b_ih[B2C_MAX_LAYERS]; float* b_hh[B2C_MAX_LAYERS];
+  float* out0_w;  float* out0_b;
+  float* out3_w;  float* out3_b;
+} B2CGrads;
+
+/* Dropout of the reference's training mode (decoder p in output_projection and between LSTM layers,
+ * src/student_model.py:142-156).  p == 0 disables it (eval mode / parity runs).  The keep mask is a
+ * counter-based hash of (seed, site, element index): backward regenerates it, nothing is stored. */
+typedef struct B2CDropout { float p; uint64_t seed; } B2CDropout;
+
+int b2c_abi_version(void);
+const char* b2c_last_error(void);
+/* Number of kernels this library has launched so far in this process (bench.py reports the per-step delta). */
+uint64_t b2c_launch_count(void);
+
+/* Bytes of caller-provided workspace for mode B2C_WS_TRAIN (forward saves + backward scratch) or
+ * B2C_WS_DECODE (greedy decode; shape->T = max_len).  0 on invalid shape. */
+size_t b2c_workspace_bytes(const B2CShape* shape, int dtype, int mode);
+
+/* LSTMDecoder.forward with hidden=None.  feats (B,S,E) [dtype]; captions (T,B) int64;
+ * out: logits (T,B,V) [dtype], hidden_top (T,B,H) [dtype] (top-layer h_t), attn_w (T,B,S) fp32.
+ * The workspace keeps what backward needs and must be passed unchanged to b2c_decoder_backward. */
+int b2c_decoder_forward(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
+                        void* logits, void* hidden_top, float* attn_w, void* workspace, size_t ws_bytes,
+                        int dtype, const B2CDropout* dropout, void* stream);
+
+/* Backward of b2c_decoder_forward.  dlogits (T,B,V) [dtype]; dhidden_top (T,B,H) [dtype] or NULL;
+ * hidden_top / attn_w are the forward outputs.  out: grads (fp32, all fields), dfeats (B,S,E) fp32. */
+int b2c_decoder_backward(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
+                         const void* hidden_top, const float* attn_w, const void* dlogits, const void* dhidden_top,
+                         const B2CGrads* grads, float* dfeats, void* workspace, size_t ws_bytes,
+                         int dtype, const B2CDropout* dropout, void* stream);
+
+/* Batched greedy decode: every sample starts at start_id and steps shape->T (= max_len) times with its own
+ * argmax fed back on the device (no host sync per token).  out: tokens (T,B) int64; lengths (B) int32 =
+ * number of tokens emitted before the first end_id (T if none) == len(caption_image(...)). */
+int b2c_greedy_decode(const B2CShape* shape, const B2CParams* params, const void* feats, int64_t start_id, int64_t end_id,
+                      int64_t* tokens, int32_t* lengths, void* workspace, size_t ws_bytes, int dtype, void* stream);
+
+/* One stand-alone attention step: hidden (B,H), feats (B,S,E) [dtype] -> context (B,E) [dtype], weights (B,S) fp32.
+ * Only shape->{B,S,E,H} are read; workspace size from b2c_workspace_bytes(shape, dtype, B2C_WS_ATTN). */
+int b2c_attention_step(const B2CShape* shape, const float* attn_w, const float* attn_b, const void* hidden, const void* feats,
+                       void* context, float* weights, void* workspace, size_t ws_bytes, int dtype, void* stream);
+
+/* n_valid_out[0] = #{ i < n : 0 < targets[i] < V }   (int32 on the device). */
+int b2c_count_valid(const int64_t* targets, int64_t n, int32_t V, int32_t* n_valid_out, void* stream);
+
+/* Streaming token pass over N = T*B rows of V logits: one read of student logits [dtype] and teacher logits
+ * (fp32), one write of dlogits [dtype]:
+ *   row_kl[r] = KL(softmax(z_r/Temp) || softmax(y_r/Temp)),  row_ce[r] = logsumexp(y_r) - y_r[tgt] (0 on PAD rows)
+ *   dlogits   = alpha*Temp/N * (pS - pT) + w_ce*ce_mult/n_valid * [tgt != 0] * (softmax(y) - onehot(tgt))
+ * n_valid points at the (global, under data parallelism) non-PAD count on the device; ce_mult = world size. */
+int b2c_kd_token_loss(const void* student_logits, const float* teacher_logits, const int64_t* targets,
+                      int64_t N, int32_t V, float temperature, float alpha, float w_ce, float ce_mult,
+                      const int32_t* n_valid, void* dlogits, float* row_kl, float* row_ce, int dtype, void* stream);
+
+/* Fused feature-KD + hidden-KD reduction and gradients.
+ *   feats_s (B,Ss,E) [dtype] or NULL, feats_t (B,St,E) fp32 (the projected teacher features);
+ *   hid_s (T,B,H) [dtype] or NULL, hid_t (Th,B,H) fp32, Th <= T steps are compared (list truncation).
+ *   out: dfeats_s, dfeats_t (fp32, scaled by beta; may be NULL), dhid_s (T,B,H) [dtype] scaled by gamma (may be NULL),
+ *   feat_part (B*2) and hid_part (Th*B*2) fp32 partials consumed by b2c_loss_finalize. */
+int b2c_aux_loss(const void* feats_s, const float* feats_t, int32_t B, int32_t Ss, int32_t St, int32_t E,
+                 const void* hid_s, const float* hid_t, int32_t T, int32_t Th, int32_t H,
+                 float beta, float gamma, float* dfeats_s, float* dfeats_t, void* dhid_s,
+                 float* feat_part, float* hid_part, int dtype, void* stream);
+
+/* out5 = { total, ce, token_kd, feature_kd, hidden_kd } (device, fp32); fixed-order fp64 reduction. */
+int b2c_loss_finalize(const float* row_kl, const float* row_ce, int64_t N, const int32_t* n_valid, float ce_mult,
+                      const float* feat_part, int32_t B, int32_t E, const float* hid_part, int32_t Th, int32_t H,
+                      float temperature, float alpha, float beta, float gamma, float w_ce, float* out5, void* stream);
+
+/* p[i] *= *scale for i < n  (scale is a device fp32 scalar: autograd's grad_output). */
+int b2c_scale_inplace(void* p, int64_t n, int dtype, const float* scale, void* stream);
+
+/* C[m,n] = act(alpha * sum_k A(m,k) B(n,k) + bias[n]) + beta*C[m,n];  a_mn/b_mn = 1 when the operand is stored
+ * MN-major (A[k*lda+m]) instead of K-major (A[m*lda+k]).  dtype = operand type; c_dtype = output type.
+ * impl: 0 = the mode's default (tcgen05 for bf16 when TMA can describe the operands, FFMA otherwise), 1 = force FFMA tiles. */
+int b2c_gemm(int32_t M, int32_t N, int32_t K, float alpha, const void* A, int64_t lda, int a_mn,
+             const void* B, int64_t ldb, int b_mn, float beta, void* C, int64_t ldc, const float* bias, int relu,
+             int dtype, int c_dtype, int impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2C_H_ */

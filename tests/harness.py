@@ -1,0 +1,78 @@
+"""Shared by tests/, __graft_entry__.smoke() and bench.py: build the public modules from an oracle parameter
+dict and replay the reference's KD step structure (src/train_student_kd.py:262-288) on a synthetic batch."""
+from __future__ import annotations
+
+import os
+
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def build_student(params, proj_params, V, E, H, L, refinement, Et, device, dropout=0.0):
+    """CaptioningStudent (features fed directly) + FeatureProjector loaded from oracle/reference state_dicts."""
+    from imagecaptioner_b200.student_model import CaptioningStudent, PrecomputedFeatures
+    from imagecaptioner_b200.distillation_utils import FeatureProjector
+    model = CaptioningStudent(V, E, H, L, dropout=dropout, use_attention_refinement=refinement, encoder=PrecomputedFeatures(E))
+    missing, unexpected = model.load_state_dict({k: v.float() for k, v in params.items()}, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.startswith("encoder.") for k in missing), missing
+    projector = FeatureProjector(Et, E, 197, 49)
+    if proj_params:
+        projector.load_state_dict({k: v.float() for k, v in proj_params.items()})
+    return model.to(device).eval(), projector.to(device).eval()
+
+
+def run_kd_step(model, projector, batch, device, dtype=torch.float32, alpha=0.7, beta=0.2, gamma=0.1, temperature=4.0):
+    """forward + DistillationLoss + backward; returns what oracle.kd_step returns (on the CPU, fp32)."""
+    from imagecaptioner_b200.distillation_utils import DistillationLoss
+    model.zero_grad(set_to_none=True)
+    projector.zero_grad(set_to_none=True)
+    model.decoder.compute_dtype = dtype
+    feats = batch["encoder_features"].to(device).clone().requires_grad_(True)
+    cap = batch["captions_input"].to(device)
+    tgt = batch["targets"].to(device)
+    outputs, enc, hids, atts = model(feats, cap)
+    th = batch.get("teacher_hiddens")
+    t_out = {"logits": batch["teacher_logits"].to(device),
+             "encoder_features": projector(batch["teacher_features"].to(device)),
+             "hidden_states": None if th is None else [th[t].to(device) for t in range(th.shape[0])]}
+    s_out = {"logits": outputs, "encoder_features": enc, "hidden_states": hids}
+    loss_mod = DistillationLoss(alpha, beta, gamma, temperature, vocab_size=outputs.shape[-1])
+    total, loss_dict = loss_mod(s_out, t_out, tgt)
+    total.backward()
+    f32 = lambda t: t.detach().float().cpu()
+    return {
+        "loss": loss_dict,
+        "grads": {k: f32(v.grad) for k, v in model.named_parameters() if v.grad is not None},
+        "proj_grads": {k: f32(v.grad) for k, v in projector.named_parameters() if v.grad is not None},
+        "d_encoder_features": f32(feats.grad),
+        "logits": f32(outputs), "hidden_states": f32(torch.stack(list(hids))),
+        "attention_weights": f32(torch.stack(list(atts))),
+        "teacher_projected": f32(t_out["encoder_features"]),
+    }
+
+
+def relerr(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def compare_step(got, ref, tol, verbose=True, loss_tol=None):
+    """max-norm relative error of every output / gradient / loss component; asserts < tol; returns the worst."""
+    rows = []
+    for k in ("logits", "hidden_states", "attention_weights", "teacher_projected", "d_encoder_features"):
+        rows.append((k, relerr(got[k], ref[k])))
+    for k, v in ref["grads"].items():
+        rows.append(("grad:" + k, relerr(got["grads"][k], v)))
+    for k, v in ref["proj_grads"].items():
+        rows.append(("pgrad:" + k, relerr(got["proj_grads"][k], v)))
+    for k, v in ref["loss"].items():
+        rows.append(("loss:" + k, abs(got["loss"][k] - v) / (abs(v) + 1e-30) if v != 0 else abs(got["loss"][k])))
+    worst = max(r[1] for r in rows)
+    bad = [r for r in rows if not r[1] < tol]
+    if verbose or bad:
+        for name, e in rows:
+            print(f"   {name:55s} {e:.3e}{'   <-- FAIL' if not e < tol else ''}")
+    assert not bad, f"{len(bad)} quantities exceed rel tol {tol}: {bad[:4]}"
+    return worst

@@ -1,0 +1,175 @@
+"""GPU: the whole KD step and greedy decode through the public modules against the golden vectors produced by the
+REAL reference (tests/golden, generator oracle/pin_against_reference.py) and against the oracle at larger sizes."""
+import os
+
+import pytest
+import torch
+
+from oracle import kd_oracle as O
+from tests.harness import GOLDEN, build_student, compare_step, relerr, run_kd_step
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FP32_TOL = 1e-4      # BASELINE.json north_star: loss and gradients within 1e-4 relative in fp32
+BF16_TOL = 2e-2      # ... and 2e-2 in bf16
+KD_CASES = ["kd_small_default", "kd_small_large_variant", "kd_small_ce_heavy_nohid"]
+
+
+def _golden_step(name, dtype):
+    g = torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+    m = g["meta"]
+    Et = g["batch"]["teacher_features"].shape[-1]
+    model, projector = build_student(g["params"], g["proj_params"], m["V"], m["E"], m["H"], m["L"], m["refinement"], Et, DEV)
+    got = run_kd_step(model, projector, g["batch"], DEV, dtype, m["alpha"], m["beta"], m["gamma"], m["temperature"])
+    return got, g["reference"]
+
+
+@pytest.mark.parametrize("name", KD_CASES)
+def test_kd_step_fp32_matches_reference(name):
+    got, ref = _golden_step(name, torch.float32)
+    compare_step(got, ref, FP32_TOL)
+
+
+@pytest.mark.parametrize("name", KD_CASES)
+def test_kd_step_bf16_matches_reference(name):
+    got, ref = _golden_step(name, torch.bfloat16)
+    # tiny-width fixtures (E=32): a few gradients are sums of O(10) bf16-rounded terms, so allow 3x the headline tolerance here;
+    # the 2e-2 bar itself is asserted on the config-1 shapes below
+    compare_step(got, ref, 3 * BF16_TOL)
+
+
+def _config1():
+    g = torch.load(os.path.join(GOLDEN, "config1_summary.pt"), weights_only=False)
+    m = g["meta"]
+    params = O.init_student_params(m["V"], m["E"], m["H"], m["L"], True, seed=m["param_seed"])
+    pparams = O.init_projector_params(384, m["E"], seed=m["proj_seed"])
+    batch = O.synthetic_batch(m["B"], m["T"], m["V"], m["E"], m["H"], seed=m["batch_seed"])
+    return g, m, params, pparams, batch
+
+
+def test_config1_fp32_against_reference_summary_and_oracle():
+    """BASELINE config 1 (B16 T20 V5000 E256 H512 L2): loss + gradient norms pinned by the reference, full tensors by the oracle."""
+    g, m, params, pparams, batch = _config1()
+    model, projector = build_student(params, pparams, m["V"], m["E"], m["H"], m["L"], True, 384, DEV)
+    got = run_kd_step(model, projector, batch, DEV, torch.float32)
+    for k, v in g["loss"].items():
+        assert abs(got["loss"][k] - v) <= FP32_TOL * max(abs(v), 1e-6), (k, got["loss"][k], v)
+    for k, v in g["grad_norms"].items():
+        assert abs(float(got["grads"][k].norm()) - v) <= 5e-4 * max(v, 1e-9), k
+    assert relerr(got["logits"][::5, ::4, ::499], g["logits_sample"]) < FP32_TOL
+    ref = O.kd_step(params, pparams, batch)
+    compare_step(got, ref, 2e-4)       # oracle itself is fp32-CPU (7e-5 from the reference at this size)
+
+
+def test_config1_bf16_within_north_star_tolerance():
+    g, m, params, pparams, batch = _config1()
+    model, projector = build_student(params, pparams, m["V"], m["E"], m["H"], m["L"], True, 384, DEV)
+    got = run_kd_step(model, projector, batch, DEV, torch.bfloat16)
+    ref = O.kd_step(params, pparams, batch)
+    compare_step(got, ref, BF16_TOL)
+
+
+def test_greedy_decode_token_ids_identical_fp32():
+    g = torch.load(os.path.join(GOLDEN, "greedy_small.pt"), weights_only=False)
+    m = g["meta"]
+    model, _ = build_student(g["params"], {}, m["V"], m["E"], m["H"], m["L"], True, m["E"], DEV)
+    toks, lengths = model.decoder.greedy(g["refined"].to(DEV), m["max_len"])
+    assert torch.equal(toks.cpu(), g["reference"]["tokens"])
+    assert torch.equal(lengths.cpu().long(), g["reference"]["lengths"])
+
+    class Vocab:
+        itos = {0: "<PAD>", 1: "<START>", 2: "<END>", 3: "<UNK>", **{i: f"w{i}" for i in range(4, m["V"])}}
+        stoi = {v: k for k, v in itos.items()}
+    # caption_image (refinement included) reproduces the reference's own captions word for word
+    for b in range(m["B"]):
+        assert model.caption_image(g["features"][b].to(DEV), Vocab, max_length=m["max_len"]) == g["reference"]["captions"][b]
+    assert not model.training                                   # caption_image leaves the model in eval() like the reference
+
+
+def test_greedy_decode_with_end_tokens_against_oracle():
+    """Bias the <END> logit so captions end at different steps; lengths and the tokens before <END> must match."""
+    V, E, H, L, B, max_len = 60, 32, 64, 2, 16, 10
+    params = O.init_student_params(V, E, H, L, False, seed=9, logit_scale=10.0)
+    params["decoder.output_projection.3.bias"][2] += 1.2
+    feats = torch.randn(B, 49, E, generator=torch.Generator().manual_seed(2))
+    toks, lengths, margins = O.greedy_decode(params, feats, max_len)
+    assert float(margins.min()) > 1e-3 and 0 < int((lengths < max_len).sum()) <= B
+    model, _ = build_student(params, {}, V, E, H, L, False, E, DEV)
+    t2, l2 = model.decoder.greedy(feats.to(DEV), max_len)
+    assert torch.equal(l2.cpu().long(), lengths) and torch.equal(t2.cpu(), toks)
+
+
+def test_training_mode_dropout_is_consistent():
+    """Dropout on: forward is reproducible for a fixed seed, the keep rate is ~1-p and backward uses the same mask
+    (finite-difference check of one directional derivative in fp32)."""
+    from imagecaptioner_b200 import _ops
+    V, E, H, L, B, T = 80, 32, 64, 2, 6, 5
+    params = O.init_student_params(V, E, H, L, False, seed=4)
+    model, _ = build_student(params, {}, V, E, H, L, False, E, DEV, dropout=0.3)
+    dec = model.decoder
+    plist = dec._param_list()
+    feats = torch.randn(B, 49, E, device=DEV)
+    cap = torch.randint(1, V, (T, B), device=DEV)
+
+    def fwd(f, seed=123):
+        return _ops.DecoderFunction.apply(f, cap, torch.float32, 0.3, seed, L, *plist)
+    y1, h1, _ = fwd(feats); y2, _, _ = fwd(feats); y3, _, _ = fwd(feats, seed=124)
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3)
+    f = feats.clone().requires_grad_(True)
+    y, _, _ = fwd(f)
+    w = torch.randn_like(y)
+    (y * w).sum().backward()
+    d = torch.randn_like(feats)
+    eps = 1e-2
+    num = (((fwd(feats + eps * d)[0] - fwd(feats - eps * d)[0]) * w).sum() / (2 * eps)).item()
+    ana = (f.grad * d).sum().item()
+    assert abs(num - ana) < 2e-2 * max(abs(ana), 1e-3), (num, ana)
+
+
+def test_data_parallel_normaliser_matches_global_batch():
+    """Two half-batches with the GLOBAL non-PAD count and ce_mult = 2, averaged like the gradient all-reduce does,
+    reproduce the full-batch gradient (SURVEY.md §8e exactness caveat), here emulated on one GPU through the C ABI."""
+    from imagecaptioner_b200 import _ops
+    lib = _ops.load_library()
+    g = torch.Generator().manual_seed(5)
+    T, B, V = 6, 8, 96
+    y = torch.randn(T, B, V, generator=g).to(DEV); z = (torch.randn(T, B, V, generator=g) * 2).to(DEV)
+    tgt = torch.randint(1, V, (T, B), generator=g); tgt[3:, :3] = 0; tgt = tgt.to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(ys, zs, ts, nval, mult):
+        N = ys.shape[0] * ys.shape[1]
+        ys, zs, ts = ys.contiguous(), zs.contiguous(), ts.contiguous()
+        dy = torch.empty_like(ys); rows = torch.empty(2, N, device=DEV)
+        assert lib.b2c_kd_token_loss(ys.data_ptr(), zs.data_ptr(), ts.data_ptr(), N, V, 4.0, 0.5, 0.5, mult, nval.data_ptr(),
+                                     dy.data_ptr(), rows[0].data_ptr(), rows[1].data_ptr(), 0, st) == 0
+        return dy
+    nval = torch.tensor([int((tgt != 0).sum())], dtype=torch.int32, device=DEV)
+    full = run(y, z, tgt, nval, 1.0)
+    halves = torch.cat([run(y[:, :4], z[:, :4], tgt[:, :4], nval, 2.0), run(y[:, 4:], z[:, 4:], tgt[:, 4:], nval, 2.0)], dim=1) / 2
+    assert relerr(halves.cpu(), full.cpu()) < 1e-5
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 sizes (B512 T20 V5000, bf16): size-independent properties instead of an oracle run."""
+    V, E, H, L, B, T = 5000, 256, 512, 2, 512, 20
+    params = O.init_student_params(V, E, H, L, True, seed=0)
+    pparams = O.init_projector_params(384, E, seed=1)
+    model, projector = build_student(params, pparams, V, E, H, L, True, 384, DEV)
+    batch = O.synthetic_batch(B, T, V, E, H, seed=1234)
+    got = run_kd_step(model, projector, batch, DEV, torch.bfloat16)
+    att = got["attention_weights"]
+    assert torch.allclose(att.sum(-1), torch.ones(T, B), atol=1e-4) and (att >= 0).all()
+    for k, v in got["grads"].items():
+        assert torch.isfinite(v).all(), k
+    assert torch.isfinite(got["d_encoder_features"]).all() and all(v == v and v >= 0 for v in got["loss"].values())
+    # the same step in fp32 parity mode agrees with bf16 within the bf16 tolerance on the loss
+    got32 = run_kd_step(model, projector, batch, DEV, torch.float32)
+    for k in got["loss"]:
+        assert abs(got["loss"][k] - got32["loss"][k]) <= BF16_TOL * max(abs(got32["loss"][k]), 1e-6), k
+    # dlogits rows sum to zero (softmax gradients) -> output bias gradient sums to ~0
+    assert abs(float(got32["grads"]["decoder.output_projection.3.bias"].sum())) < 1e-4
+    # PAD rows contribute only the KD part: CE weight is ~0 at the defaults, so grads must be independent of targets
+    batch2 = dict(batch); batch2["targets"] = batch["targets"].clone().clamp_min(1)
+    got_b = run_kd_step(model, projector, batch2, DEV, torch.float32)
+    assert relerr(got_b["grads"]["decoder.lstm.weight_hh_l0"], got32["grads"]["decoder.lstm.weight_hh_l0"]) < 1e-5
