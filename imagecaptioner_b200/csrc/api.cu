@@ -84,14 +84,14 @@ int pack_params(const B2CShape& s, const B2CParams& p, const Weights<T>& w, cuda
 // ------------------------------------------------------------------ workspaces
 template <typename T> struct TrainWs {
   Weights<T> w;
-  T *P, *emb, *u, *ctx, *o1; T* xh[MAXL]; T* gates[MAXL]; float* c[MAXL]; float* pre;
+  float *P, *u; T *emb, *ctx, *o1; T* xh[MAXL]; T* gates[MAXL]; float* c[MAXL]; float* pre;
   T* dgates[MAXL]; T* dxh0; T* dxh[MAXL]; float* dc[MAXL]; T* do1; float* dHext; T* dctx; float* ds; T* du; T* dq; T* dP; float* demb; float* partial;
   size_t bytes;
   void carve(void* base, const B2CShape& s) {
     Carver c{reinterpret_cast<unsigned char*>(base), 0};
     const size_t B = s.B, Tn = s.T, S = s.S, E = s.E, H = s.H, TB = Tn * B;
     w.carve(c, s);
-    P = c.take<T>(B * S * E); emb = c.take<T>(TB * E); u = c.take<T>(TB * E); ctx = c.take<T>(TB * E); o1 = c.take<T>(TB * E);
+    P = c.take<float>(B * S * E); emb = c.take<T>(TB * E); u = c.take<float>(TB * E); ctx = c.take<T>(TB * E); o1 = c.take<T>(TB * E);
     for (int k = 0; k < s.L; ++k) {
       xh[k] = c.take<T>((Tn + 1) * B * (in_dim(s, k) + H));
       gates[k] = c.take<T>(TB * 4 * H);
@@ -114,13 +114,13 @@ template <typename T> struct TrainWs {
 
 template <typename T> struct DecodeWs {
   Weights<T> w;
-  T *P, *emb, *u, *ctx, *o1; T* xh[MAXL]; float* c[MAXL]; float* pre; float* logits; int64_t* cur; int32_t* done;
+  float *P, *u; T *emb, *ctx, *o1; T* xh[MAXL]; float* c[MAXL]; float* pre; float* logits; int64_t* cur; int32_t* done;
   size_t bytes;
   void carve(void* base, const B2CShape& s) {
     Carver c{reinterpret_cast<unsigned char*>(base), 0};
     const size_t B = s.B, S = s.S, E = s.E, H = s.H;
     w.carve(c, s);
-    P = c.take<T>(B * S * E); emb = c.take<T>(B * E); u = c.take<T>(B * E); ctx = c.take<T>(B * E); o1 = c.take<T>(B * E);
+    P = c.take<float>(B * S * E); emb = c.take<T>(B * E); u = c.take<float>(B * E); ctx = c.take<T>(B * E); o1 = c.take<T>(B * E);
     for (int k = 0; k < s.L; ++k) { xh[k] = c.take<T>(B * (in_dim(s, k) + H)); this->c[k] = c.take<float>(B * H); }
     pre = c.take<float>(B * 4 * H); logits = c.take<float>(B * (size_t)s.V); cur = c.take<int64_t>(B); done = c.take<int32_t>(B);
     bytes = align_up(c.off, 256);
@@ -154,8 +154,8 @@ template <typename K> int set_smem(K kern, size_t bytes) {
 }
 
 template <typename T>
-int attn_fwd(cudaStream_t st, const B2CShape& s, const T* P, const T* F, const T* u, T* ctx, float* attw) {
-  const size_t smem = (size_t)2 * s.S * s.E * sizeof(T) + (size_t)(s.E + s.S) * 4;
+int attn_fwd(cudaStream_t st, const B2CShape& s, const float* P, const T* F, const float* u, T* ctx, float* attw) {
+  const size_t smem = (size_t)s.S * s.E * (sizeof(T) + 4) + (size_t)(s.E + s.S) * 4;
   B2C_TRY(set_smem(attn_step_fwd_kernel<T>, smem));
   attn_step_fwd_kernel<T><<<s.B, ATT_THREADS, smem, st>>>(P, F, u, s.E, s.S, s.E, ctx, s.E, attw);
   B2C_LAUNCH_CHECK("attn_step_fwd_kernel");
@@ -185,7 +185,7 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
   const long TB = (long)Tn * B;
   B2C_TRY(pack_params<T>(s, p, W.w, st));
   // time-invariant half of the attention projection: P = F W_f^T + b_a
-  B2C_TRY((gemm<T, T>(st, B * S, E, E, feats, E, 0, W.w.Wf, E, 0, W.P, E, 0.f, p.attn_b)));
+  B2C_TRY((gemm<T, float>(st, B * S, E, E, feats, E, 0, W.w.Wf, E, 0, W.P, E, 0.f, p.attn_b)));
   embedding_gather_kernel<T><<<ew_grid(TB * E / 4), 256, 0, st>>>(p.embedding, cap, TB, E, V, W.emb, E);
   B2C_LAUNCH_CHECK("embedding_gather_kernel");
   for (int k = 0; k < L; ++k) {
@@ -197,9 +197,9 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
   const int inL = in_dim(s, L - 1), ldL = inL + H;
   for (int t = 0; t < Tn; ++t) {
     const T* q = W.xh[L - 1] + (long)t * B * ldL + inL;
-    T* u_t = W.u + (long)t * B * E;
+    float* u_t = W.u + (long)t * B * E;
     T* ctx_t = W.ctx + (long)t * B * E;
-    B2C_TRY((gemm<T, T>(st, B, E, H, q, ldL, 0, W.w.Wh, H, 0, u_t, E)));
+    B2C_TRY((gemm<T, float>(st, B, E, H, q, ldL, 0, W.w.Wh, H, 0, u_t, E)));
     B2C_TRY(attn_fwd<T>(st, s, W.P, feats, u_t, ctx_t, attw + (long)t * B * S));
     B2C_TRY((gemm<T, T>(st, B, E, E, ctx_t, E, 0, W.w.Wcc, E, 0, W.xh[0] + (long)t * B * (E + H), E + H, 1.f)));
     for (int k = 0; k < L; ++k) {
@@ -242,7 +242,7 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
   B2C_TRY((gemm<T, float>(st, E, H, (int)TB, W.do1, E, 1, hid_top, H, 1, g.out0_w, H)));
   B2C_TRY(colsum<T>(st, W.do1, TB, E, E, W.partial, g.out0_b));
   // ---- reverse time loop
-  const size_t att_smem = (size_t)2 * S * E * sizeof(T) + (size_t)(2 * E + S) * 4;
+  const size_t att_smem = (size_t)S * E * (sizeof(T) + 4) + (size_t)(2 * E + S) * 4;
   B2C_TRY(set_smem(attn_step_bwd_kernel<T>, att_smem));
   for (int t = Tn - 1; t >= 0; --t) {
     const bool last = (t == Tn - 1);
@@ -306,7 +306,7 @@ int greedy_decode_impl(const B2CShape& s, const B2CParams& p, const T* feats, in
   const int B = s.B, Tn = s.T, S = s.S, E = s.E, H = s.H, L = s.L, V = s.V;
   const B2CDropout nodrop{0.f, 0};
   B2C_TRY(pack_params<T>(s, p, W.w, st));
-  B2C_TRY((gemm<T, T>(st, B * S, E, E, feats, E, 0, W.w.Wf, E, 0, W.P, E, 0.f, p.attn_b)));
+  B2C_TRY((gemm<T, float>(st, B * S, E, E, feats, E, 0, W.w.Wf, E, 0, W.P, E, 0.f, p.attn_b)));
   for (int k = 0; k < L; ++k) {
     B2C_CUDA(cudaMemsetAsync(W.xh[k], 0, (size_t)B * (in_dim(s, k) + H) * sizeof(T), st));
     B2C_CUDA(cudaMemsetAsync(W.c[k], 0, (size_t)B * H * sizeof(float), st));
@@ -318,7 +318,7 @@ int greedy_decode_impl(const B2CShape& s, const B2CParams& p, const T* feats, in
     embedding_gather_kernel<T><<<ew_grid((long)B * E / 4), 256, 0, st>>>(p.embedding, W.cur, B, E, V, W.emb, E);
     B2C_LAUNCH_CHECK("embedding_gather_kernel");
     B2C_TRY((gemm<T, T>(st, B, E, E, W.emb, E, 0, W.w.Wce, E, 0, W.xh[0], E + H, 0.f, p.comb_b)));
-    B2C_TRY((gemm<T, T>(st, B, E, H, W.xh[L - 1] + inL, ldL, 0, W.w.Wh, H, 0, W.u, E)));
+    B2C_TRY((gemm<T, float>(st, B, E, H, W.xh[L - 1] + inL, ldL, 0, W.w.Wh, H, 0, W.u, E)));
     B2C_TRY(attn_fwd<T>(st, s, W.P, feats, W.u, W.ctx, nullptr));
     B2C_TRY((gemm<T, T>(st, B, E, E, W.ctx, E, 0, W.w.Wcc, E, 0, W.xh[0], E + H, 1.f)));
     for (int k = 0; k < L; ++k) {
@@ -337,11 +337,11 @@ int greedy_decode_impl(const B2CShape& s, const B2CParams& p, const T* feats, in
 }
 
 template <typename T> struct AttnWs {
-  T *Wh, *Wf, *P, *u; size_t bytes;
+  T *Wh, *Wf; float *P, *u; size_t bytes;
   void carve(void* base, const B2CShape& s) {
     Carver c{reinterpret_cast<unsigned char*>(base), 0};
     Wh = c.take<T>((size_t)s.E * s.H); Wf = c.take<T>((size_t)s.E * s.E);
-    P = c.take<T>((size_t)s.B * s.S * s.E); u = c.take<T>((size_t)s.B * s.E);
+    P = c.take<float>((size_t)s.B * s.S * s.E); u = c.take<float>((size_t)s.B * s.E);
     bytes = align_up(c.off, 256);
   }
 };
@@ -357,8 +357,8 @@ int attention_step_impl(const B2CShape& s, const float* attn_w, const float* att
   tab.seg[1] = PackSeg{attn_w + H, W.Wf, nullptr, E, E, (long)H + E, (long)E, 0};
   pack_params_kernel<T><<<dim3(32, 2), 256, 0, st>>>(tab);
   B2C_LAUNCH_CHECK("pack_params_kernel");
-  B2C_TRY((gemm<T, T>(st, B * S, E, E, feats, E, 0, W.Wf, E, 0, W.P, E, 0.f, attn_b)));
-  B2C_TRY((gemm<T, T>(st, B, E, H, hidden, H, 0, W.Wh, H, 0, W.u, E)));
+  B2C_TRY((gemm<T, float>(st, B * S, E, E, feats, E, 0, W.Wf, E, 0, W.P, E, 0.f, attn_b)));
+  B2C_TRY((gemm<T, float>(st, B, E, H, hidden, H, 0, W.Wh, H, 0, W.u, E)));
   return attn_fwd<T>(st, s, W.P, feats, W.u, context, weights);
 }
 

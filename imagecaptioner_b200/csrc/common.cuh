@@ -45,9 +45,11 @@ template <> struct Math<float> {
   static __device__ __forceinline__ float exp_(float x) { return expf(x); }
   static __device__ __forceinline__ float log_(float x) { return logf(x); }
 };
+// bf16 mode: MUFU ex2/rcp based forms (abs error ~1e-7).  tanh.approx (rel 2^-11) is NOT used: the attention score is a sum
+// of E tanh values, and its error goes straight into the softmax weights and from there into ReLU-mask flips downstream.
 template <> struct Math<bf16> {
-  static __device__ __forceinline__ float tanh_(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-  static __device__ __forceinline__ float sigmoid_(float x) { return 0.5f * tanh_(0.5f * x) + 0.5f; }
+  static __device__ __forceinline__ float tanh_(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+  static __device__ __forceinline__ float sigmoid_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
   static __device__ __forceinline__ float exp_(float x) { return __expf(x); }
   static __device__ __forceinline__ float log_(float x) { return __logf(x); }
 };

@@ -61,38 +61,39 @@ __global__ void __launch_bounds__(256) embedding_scatter_add_kernel(const float*
 // ======================================================================================
 constexpr int ATT_THREADS = 256;
 
+// P (the hoisted projection, kept in fp32 in both modes: the score sums E tanh terms) and F (features, compute type)
 template <typename T>
-__device__ __forceinline__ void att_stage(const T* P, const T* F, int b, int SE, T* Ps, T* Fs, uint64_t* bar) {
+__device__ __forceinline__ void att_stage(const float* P, const T* F, int b, int SE, float* Ps, T* Fs, uint64_t* bar) {
   if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const uint32_t bytes = (uint32_t)(SE * sizeof(T));
-    mbar_arrive_expect_tx(bar, (Ps ? bytes : 0u) + (Fs ? bytes : 0u));
-    if (Ps) bulk_g2s(Ps, P + (long)b * SE, bytes, bar);
-    if (Fs) bulk_g2s(Fs, F + (long)b * SE, bytes, bar);
+    const uint32_t pb = (uint32_t)(SE * sizeof(float)), fb = (uint32_t)(SE * sizeof(T));
+    mbar_arrive_expect_tx(bar, pb + fb);
+    bulk_g2s(Ps, P + (long)b * SE, pb, bar);
+    bulk_g2s(Fs, F + (long)b * SE, fb, bar);
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS)
-attn_step_fwd_kernel(const T* __restrict__ P, const T* __restrict__ F, const T* __restrict__ u, long ldu,
+attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const float* __restrict__ u, long ldu,
                      int S, int E, T* __restrict__ ctx, long ldctx, float* __restrict__ attw /* (B,S) or null */) {
   extern __shared__ __align__(128) unsigned char att_smem[];
   const int SE = S * E;
-  T* Ps = reinterpret_cast<T*>(att_smem);
-  T* Fs = Ps + SE;
+  float* Ps = reinterpret_cast<float*>(att_smem);
+  T* Fs = reinterpret_cast<T*>(Ps + SE);
   float* us = reinterpret_cast<float*>(Fs + SE);
   float* sc = us + E;
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATT_THREADS / 32;
   const int b = blockIdx.x;
   att_stage<T>(P, F, b, SE, Ps, Fs, &bar);
-  for (int e = tid; e < E; e += ATT_THREADS) us[e] = to_f<T>(u[(long)b * ldu + e]);
+  for (int e = tid; e < E; e += ATT_THREADS) us[e] = u[(long)b * ldu + e];
   __syncthreads();
   mbar_wait(&bar, 0);
   for (int l = warp; l < S; l += nwarp) {
     float a = 0.f;
-    for (int e = lane; e < E; e += 32) a += Math<T>::tanh_(to_f<T>(Ps[l * E + e]) + us[e]);
+    for (int e = lane; e < E; e += 32) a += Math<T>::tanh_(Ps[l * E + e] + us[e]);
     a = warp_sum(a);
     if (lane == 0) sc[l] = a;
   }
@@ -119,13 +120,13 @@ attn_step_fwd_kernel(const T* __restrict__ P, const T* __restrict__ F, const T* 
 //   dw_l = sum_e dctx_e F[l,e];  ds_l = w_l (dw_l - sum_j w_j dw_j);  du_e = sum_l ds_l (1 - tanh^2(P[l,e]+u_e))
 template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS)
-attn_step_bwd_kernel(const T* __restrict__ P, const T* __restrict__ F, const T* __restrict__ u, long ldu,
+attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const float* __restrict__ u, long ldu,
                      const float* __restrict__ attw, const T* __restrict__ dctx, long lddctx,
                      int S, int E, float* __restrict__ ds_out, T* __restrict__ du, long lddu) {
   extern __shared__ __align__(128) unsigned char att_smem[];
   const int SE = S * E;
-  T* Ps = reinterpret_cast<T*>(att_smem);
-  T* Fs = Ps + SE;
+  float* Ps = reinterpret_cast<float*>(att_smem);
+  T* Fs = reinterpret_cast<T*>(Ps + SE);
   float* us = reinterpret_cast<float*>(Fs + SE);
   float* dcs = us + E;
   float* dw = dcs + E;
@@ -133,7 +134,7 @@ attn_step_bwd_kernel(const T* __restrict__ P, const T* __restrict__ F, const T* 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATT_THREADS / 32;
   const int b = blockIdx.x;
   att_stage<T>(P, F, b, SE, Ps, Fs, &bar);
-  for (int e = tid; e < E; e += ATT_THREADS) { us[e] = to_f<T>(u[(long)b * ldu + e]); dcs[e] = to_f<T>(dctx[(long)b * lddctx + e]); }
+  for (int e = tid; e < E; e += ATT_THREADS) { us[e] = u[(long)b * ldu + e]; dcs[e] = to_f<T>(dctx[(long)b * lddctx + e]); }
   __syncthreads();
   mbar_wait(&bar, 0);
   for (int l = warp; l < S; l += nwarp) {
@@ -152,7 +153,7 @@ attn_step_bwd_kernel(const T* __restrict__ P, const T* __restrict__ F, const T* 
   __syncthreads();
   for (int e = tid; e < E; e += ATT_THREADS) {
     float a = 0.f; const float ue = us[e];
-    for (int l = 0; l < S; ++l) { const float th = Math<T>::tanh_(to_f<T>(Ps[l * E + e]) + ue); a = fmaf(dw[l], 1.0f - th * th, a); }
+    for (int l = 0; l < S; ++l) { const float th = Math<T>::tanh_(Ps[l * E + e] + ue); a = fmaf(dw[l], 1.0f - th * th, a); }
     du[(long)b * lddu + e] = from_f<T>(a);
   }
 }
@@ -163,7 +164,7 @@ attn_step_bwd_kernel(const T* __restrict__ P, const T* __restrict__ F, const T* 
 // u/dctx/w/ds for all T steps of this sample sit in shared memory (T*(2E+2S) floats).
 template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS)
-attn_post_kernel(const T* __restrict__ P, const T* __restrict__ u /*(T,B,E)*/, const T* __restrict__ dctx /*(T,B,E)*/,
+attn_post_kernel(const float* __restrict__ P, const float* __restrict__ u /*(T,B,E)*/, const T* __restrict__ dctx /*(T,B,E)*/,
                  const float* __restrict__ attw /*(T,B,S)*/, const float* __restrict__ ds /*(T,B,S)*/,
                  int Tn, int B, int S, int E, T* __restrict__ dP, float* __restrict__ dF) {
   extern __shared__ __align__(128) unsigned char att_smem[];
@@ -172,13 +173,13 @@ attn_post_kernel(const T* __restrict__ P, const T* __restrict__ u /*(T,B,E)*/, c
   float* ws = dcs + (long)Tn * E;                      // Tn*S
   float* dss = ws + (long)Tn * S;                      // Tn*S
   const int tid = threadIdx.x, b = blockIdx.x;
-  for (int i = tid; i < Tn * E; i += ATT_THREADS) { const int t = i / E, e = i - t * E; us[i] = to_f<T>(u[((long)t * B + b) * E + e]); dcs[i] = to_f<T>(dctx[((long)t * B + b) * E + e]); }
+  for (int i = tid; i < Tn * E; i += ATT_THREADS) { const int t = i / E, e = i - t * E; us[i] = u[((long)t * B + b) * E + e]; dcs[i] = to_f<T>(dctx[((long)t * B + b) * E + e]); }
   for (int i = tid; i < Tn * S; i += ATT_THREADS) { const int t = i / S, l = i - t * S; ws[i] = attw[((long)t * B + b) * S + l]; dss[i] = ds[((long)t * B + b) * S + l]; }
   __syncthreads();
   const long base = (long)b * S * E;
   for (int idx = tid; idx < S * E; idx += ATT_THREADS) {
     const int l = idx / E, e = idx - l * E;
-    const float p = to_f<T>(P[base + idx]);
+    const float p = P[base + idx];
     float aP = 0.f, aF = 0.f;
     for (int t = 0; t < Tn; ++t) {
       const float th = Math<T>::tanh_(p + us[t * E + e]);

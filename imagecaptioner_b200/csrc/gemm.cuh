@@ -149,18 +149,40 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+constexpr int TC_EPI_PITCH = 144;                       // bytes per staged row: 128 B of payload + 16 B pad (bank-conflict free)
+constexpr int TC_EPI_BYTES = 4 * 32 * TC_EPI_PITCH;    // one 32-row staging tile per epilogue warp
+
 template <int BN> struct TcCfg {
   static constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   static constexpr uint32_t STAGE_BYTES = TC_A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-  static constexpr size_t SMEM_BYTES = (size_t)TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr size_t SMEM_BYTES = (size_t)TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + TC_EPI_BYTES;
 };
 
+__device__ __forceinline__ uint4 epi_combine_bf16(uint4 acc, uint4 old, float beta) {
+  uint4 o;
+  o.x = pack_bf16(bf16_lo(acc.x) + beta * bf16_lo(old.x), bf16_hi(acc.x) + beta * bf16_hi(old.x));
+  o.y = pack_bf16(bf16_lo(acc.y) + beta * bf16_lo(old.y), bf16_hi(acc.y) + beta * bf16_hi(old.y));
+  o.z = pack_bf16(bf16_lo(acc.z) + beta * bf16_lo(old.z), bf16_hi(acc.z) + beta * bf16_hi(old.z));
+  o.w = pack_bf16(bf16_lo(acc.w) + beta * bf16_lo(old.w), bf16_hi(acc.w) + beta * bf16_hi(old.w));
+  return o;
+}
+__device__ __forceinline__ uint4 epi_combine_f32(uint4 acc, uint4 old, float beta) {
+  uint4 o;
+  o.x = __float_as_uint(__uint_as_float(acc.x) + beta * __uint_as_float(old.x));
+  o.y = __float_as_uint(__uint_as_float(acc.y) + beta * __uint_as_float(old.y));
+  o.z = __float_as_uint(__uint_as_float(acc.z) + beta * __uint_as_float(old.z));
+  o.w = __float_as_uint(__uint_as_float(acc.w) + beta * __uint_as_float(old.w));
+  return o;
+}
+
+// grid = (N tiles, M tiles, K splits).  With K splits > 1 (fp32 output only) every split adds its partial tile into C with
+// red.global.add.f32; the host has zeroed C (beta == 0) or C already holds the value to accumulate onto (beta == 1).
 template <int BN, bool A_MN, bool B_MN, typename TC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, float alpha, float beta, TC* __restrict__ C, long ldc,
-               const float* __restrict__ bias, int relu) {
+               const float* __restrict__ bias, int relu, int kb_per_split) {
   using Cfg = TcCfg<BN>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
@@ -168,10 +190,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + TC_STAGES;
   uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  unsigned char* epi_stage = base + (size_t)TC_STAGES * Cfg::STAGE_BYTES + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-  const int num_kb = (K + TC_BK - 1) / TC_BK;
+  const int num_kb_total = (K + TC_BK - 1) / TC_BK;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(num_kb_total, kb_begin + kb_per_split);
+  const int num_kb = kb_end - kb_begin;                 // >= 1 by construction of the grid
+  const bool split = gridDim.z > 1;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1) {
@@ -192,13 +219,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % TC_STAGES; const uint32_t ph = (kb / TC_STAGES) & 1;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % TC_STAGES; const uint32_t ph = (i / TC_STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         unsigned char* sa = base + (size_t)s * Cfg::STAGE_BYTES;
         unsigned char* sb = sa + TC_A_BYTES;
         mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        const int k0 = kb * TC_BK;
+        const int k0 = (kb_begin + i) * TC_BK;
         if (!A_MN) {
           tma_load_2d(sa, &tmA, k0, m0, &full_bar[s]);                      // box {64 k, 128 m}
         } else {
@@ -218,8 +245,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                  ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % TC_STAGES; const uint32_t ph = (kb / TC_STAGES) & 1;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % TC_STAGES; const uint32_t ph = (i / TC_STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(base + (size_t)s * Cfg::STAGE_BYTES);
@@ -228,56 +255,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int k = 0; k < TC_BK / 16; ++k) {
           const uint64_t adesc = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
           const uint64_t bdesc = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-          tc_mma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_mma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
         }
         tc_commit(&empty_bar[s]);              // frees the smem slot once these MMAs have read it
       }
       tc_commit(tmem_full_bar);                // accumulator complete
     }
   } else {
-    // ------------------------------------------------ epilogue: warps 2..5 -> TMEM lane quarters (warp % 4)
+    // ------------------------------------------------ epilogue: warps 2..5 -> TMEM lane quarters (warp % 4).
+    // TMEM -> registers (one accumulator row per lane) -> alpha/bias/ReLU -> 128-byte row chunks staged in shared memory
+    // -> written out with each quarter-warp covering one contiguous 128-byte row segment (full sectors, 16-byte accesses).
     const int q = warp & 3;
+    unsigned char* my = epi_stage + (size_t)(warp - 2) * 32 * TC_EPI_PITCH;
+    constexpr int PER = 16 / (int)sizeof(TC);           // elements per 16-byte unit: 8 (bf16) or 4 (fp32)
+    constexpr int CH = 128 / (int)sizeof(TC);           // columns per staged chunk: 64 (bf16) or 32 (fp32)
+    const bool vec_ok = (((uintptr_t)C) % 16 == 0) && ((ldc * (long)sizeof(TC)) % 16 == 0);
+    const bool add_bias = (bias != nullptr) && (!split || blockIdx.z == 0);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int row = m0 + q * 32 + lane;
-    const bool vec_ok = (((uintptr_t)C) % 16 == 0) && ((ldc * sizeof(TC)) % 16 == 0) && (beta == 0.f);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      const int col0 = n0 + c0;
-      if (row < M && col0 < N) {
-        const bool full = (col0 + 32 <= N);
+    for (int c0 = 0; c0 < BN; c0 += CH) {
+      if (n0 + c0 >= N) break;
+#pragma unroll
+      for (int h = 0; h < CH / 32; ++h) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + h * 32), v);
+        const int colb = n0 + c0 + h * 32;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = alpha * v[j];
-          if (bias && (full || col0 + j < N)) x += bias[col0 + j];
+          if (add_bias && colb + j < N) x += bias[colb + j];
           if (relu) x = fmaxf(x, 0.f);
           v[j] = x;
         }
-        TC* crow = C + (long)row * ldc + col0;
-        if (full && vec_ok) {
-          if (sizeof(TC) == 2) {
+        unsigned char* dst = my + lane * TC_EPI_PITCH + h * 32 * sizeof(TC);
+        if (sizeof(TC) == 2) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 o = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
-              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(crow) + j) = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(crow) + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
+          for (int j = 0; j < 32; j += 8)
+            *reinterpret_cast<uint4*>(dst + j * 2) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
         } else {
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j < N) {
-              float x = v[j];
-              if (beta != 0.f) x += beta * to_f<TC>(crow[j]);
-              crow[j] = from_f<TC>(x);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(dst + j * 4) = make_uint4(__float_as_uint(v[j]), __float_as_uint(v[j + 1]), __float_as_uint(v[j + 2]), __float_as_uint(v[j + 3]));
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), part = lane & 7;
+        const int grow = m0 + q * 32 + r, gcol = n0 + c0 + part * PER;
+        if (grow < M && gcol < N) {
+          const uint4 acc = *reinterpret_cast<const uint4*>(my + r * TC_EPI_PITCH + part * 16);
+          TC* cp = C + (long)grow * ldc + gcol;
+          if (split) {
+            const float* a = reinterpret_cast<const float*>(&acc);
+#pragma unroll
+            for (int e = 0; e < PER; ++e) if (gcol + e < N) atomicAdd(reinterpret_cast<float*>(cp) + e, a[e]);
+          } else if (vec_ok && gcol + PER <= N) {
+            uint4 o = acc;
+            if (beta != 0.f) {
+              const uint4 old = *reinterpret_cast<const uint4*>(cp);
+              o = (sizeof(TC) == 2) ? epi_combine_bf16(acc, old, beta) : epi_combine_f32(acc, old, beta);
+            }
+            *reinterpret_cast<uint4*>(cp) = o;
+          } else {
+            const TC* a = reinterpret_cast<const TC*>(&acc);
+#pragma unroll
+            for (int e = 0; e < PER; ++e) {
+              if (gcol + e < N) {
+                float x = to_f<TC>(a[e]);
+                if (beta != 0.f) x += beta * to_f<TC>(cp[e]);
+                cp[e] = from_f<TC>(x);
+              }
             }
           }
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -333,6 +387,23 @@ inline bool tc_eligible(const GemmArgs& g) {
   return ((uintptr_t)g.A % 16 == 0) && ((uintptr_t)g.B % 16 == 0) && (g.lda % 8 == 0) && (g.ldb % 8 == 0);
 }
 
+// K splits for skinny outputs with a long reduction (weight gradients: M*N small, K = T*B): fill the SMs.
+template <int BN, typename TC>
+inline int pick_k_splits(const GemmArgs& g, int* kb_per_split) {
+  const int num_kb = cdiv(g.K, TC_BK);
+  int splits = 1;
+  if (sizeof(TC) == 4 && !g.relu && (g.beta == 0.f || g.beta == 1.f)) {
+    const long tiles = (long)cdiv(g.N, BN) * cdiv(g.M, TC_BM);
+    if (tiles <= 74 && num_kb >= 16) {
+      splits = (int)(148 / tiles);
+      if (splits > num_kb / 8) splits = num_kb / 8;          // at least 8 k-blocks (512 of K) per split
+      if (splits < 1) splits = 1;
+    }
+  }
+  *kb_per_split = cdiv(num_kb, splits);
+  return cdiv(num_kb, *kb_per_split);                      // no empty split
+}
+
 template <int BN, bool A_MN, bool B_MN, typename TC>
 int launch_tc(const GemmArgs& g, cudaStream_t st) {
   CUtensorMap ta, tb;
@@ -344,8 +415,12 @@ int launch_tc(const GemmArgs& g, cudaStream_t st) {
     B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid(cdiv(g.N, BN), cdiv(g.M, TC_BM));
-  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ta, tb, g.M, g.N, g.K, g.alpha, g.beta, (TC*)g.C, g.ldc, g.bias, g.relu);
+  int kb_per_split = 0;
+  const int splits = pick_k_splits<BN, TC>(g, &kb_per_split);
+  if (splits > 1 && g.beta == 0.f)
+    B2C_CUDA(cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(TC), 0, (size_t)g.N * sizeof(TC), (size_t)g.M, st));
+  dim3 grid(cdiv(g.N, BN), cdiv(g.M, TC_BM), splits);
+  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ta, tb, g.M, g.N, g.K, g.alpha, g.beta, (TC*)g.C, g.ldc, g.bias, g.relu, kb_per_split);
   B2C_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }

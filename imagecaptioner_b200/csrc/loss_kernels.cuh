@@ -306,11 +306,24 @@ loss_finalize_kernel(const float* __restrict__ row_kl, const float* __restrict__
   }
 }
 
-// y *= *scale (device scalar): applies autograd's incoming grad_output to a precomputed gradient.
+// y *= *scale (device scalar): applies autograd's incoming grad_output to a precomputed gradient; 16-byte accesses.
 template <typename T>
-__global__ void scale_inplace_kernel(T* __restrict__ p, long n, const float* __restrict__ scale) {
+__global__ void __launch_bounds__(256) scale_inplace_kernel(T* __restrict__ p, long n, const float* __restrict__ scale) {
   const float s = *scale;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = from_f<T>(to_f<T>(p[i]) * s);
+  constexpr int PER = 16 / (int)sizeof(T);
+  const long nvec = (((uintptr_t)p) % 16 == 0) ? n / PER : 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    uint4 v = reinterpret_cast<uint4*>(p)[i];
+    if (sizeof(T) == 2) {
+      v.x = pack_bf16(bf16_lo(v.x) * s, bf16_hi(v.x) * s); v.y = pack_bf16(bf16_lo(v.y) * s, bf16_hi(v.y) * s);
+      v.z = pack_bf16(bf16_lo(v.z) * s, bf16_hi(v.z) * s); v.w = pack_bf16(bf16_lo(v.w) * s, bf16_hi(v.w) * s);
+    } else {
+      v.x = __float_as_uint(__uint_as_float(v.x) * s); v.y = __float_as_uint(__uint_as_float(v.y) * s);
+      v.z = __float_as_uint(__uint_as_float(v.z) * s); v.w = __float_as_uint(__uint_as_float(v.w) * s);
+    }
+    reinterpret_cast<uint4*>(p)[i] = v;
+  }
+  for (long i = nvec * PER + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = from_f<T>(to_f<T>(p[i]) * s);
 }
 
 }  // namespace b2c

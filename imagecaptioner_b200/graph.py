@@ -1,0 +1,90 @@
+"""Whole-step CUDA graph for the KD training step.
+
+One KD step launches several hundred small kernels (T serial decode steps, forward and backward); issued
+eagerly the step is bound by host launch latency, not by the GPU.  ``GraphedKDStep`` captures the complete step —
+student forward (refinement + decoder), FeatureProjector, DistillationLoss, backward, gradient all-reduce,
+global-norm clip and AdamW — into ONE ``torch.cuda.CUDAGraph`` over static input buffers and replays it with a
+single launch per step ("CUDA Graph over the whole sequence at minimum").
+
+The step structure is the reference's training loop body (src/train_student_kd.py:262-303) with the encoders
+outside the path: the caller provides encoder features, captions, targets and the teacher's outputs.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from .ddp import FlatGradAllReducer
+
+
+class GraphedKDStep:
+    INPUT_KEYS = ("encoder_features", "captions_input", "targets", "teacher_logits", "teacher_features", "teacher_hiddens")
+
+    def __init__(self, model, projector, loss_module, optimizer, reducer: FlatGradAllReducer, example: Dict[str, torch.Tensor],
+                 max_grad_norm: float = 1.0, autocast_dtype: Optional[torch.dtype] = torch.bfloat16, use_graph: bool = True,
+                 warmup_steps: int = 3):
+        self.model, self.projector, self.loss_module = model, projector, loss_module
+        self.optimizer, self.reducer = optimizer, reducer
+        self.max_grad_norm = max_grad_norm
+        self.autocast_dtype = autocast_dtype
+        self.static = {k: example[k].clone() for k in self.INPUT_KEYS if example.get(k) is not None}
+        self.static["encoder_features"].requires_grad_(True)
+        self.out5 = None
+        self.graph = None
+        if use_graph:
+            self._capture(warmup_steps)
+
+    # ---- the step body (eager or under capture)
+    def _body(self):
+        inp = self.static
+        feats = inp["encoder_features"]
+        if feats.grad is not None:
+            feats.grad = None
+        ctx = torch.autocast("cuda", dtype=self.autocast_dtype) if self.autocast_dtype is not None else torch.autocast("cuda", enabled=False)
+        with ctx:                                                      # the reference's loop runs under autocast (train_student_kd.py:271)
+            outputs, enc, hids, _ = self.model(feats, inp["captions_input"])
+            tproj = self.projector(inp["teacher_features"])
+        loss, out5 = self.loss_module.forward_device(
+            {"logits": outputs, "encoder_features": enc, "hidden_states": hids},
+            {"logits": inp["teacher_logits"], "encoder_features": tproj, "hidden_states": inp.get("teacher_hiddens")},
+            inp["targets"])
+        self.reducer.zero_grad()
+        loss.backward()
+        self.reducer.allreduce()
+        if self.max_grad_norm is not None:                             # clip_grad_norm_ on the flat buffer, no host sync
+            gn = self.reducer.flat.norm()
+            self.reducer.flat.mul_(torch.clamp(self.max_grad_norm / (gn + 1e-6), max=1.0))
+        self.optimizer.step()
+        return out5
+
+    def _capture(self, warmup_steps):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup_steps):
+                self.out5 = self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out5 = self._body()
+
+    def load(self, batch: Dict[str, torch.Tensor], non_blocking: bool = True) -> int:
+        """Copy one step's inputs (host or device tensors) into the static buffers; returns the bytes copied."""
+        n = 0
+        with torch.no_grad():
+            for k, dst in self.static.items():
+                src = batch[k]
+                dst.copy_(src, non_blocking=non_blocking)
+                n += src.numel() * src.element_size()
+        return n
+
+    def step(self) -> torch.Tensor:
+        """Run one KD step on the current contents of the static buffers -> device tensor
+        [total, ce, token_kd, feature_kd, hidden_kd] (no host sync)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.out5 = self._body()
+        return self.out5
