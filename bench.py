@@ -34,6 +34,14 @@ CFG = dict(B=512, T=20, V=5000, E=256, H=512, L=2, S=49, St=197, Et=384)
 METRIC = "kd_train_samples_per_sec"
 
 
+def log(msg):
+    if os.environ.get("BENCH_VERBOSE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter() - T0:7.2f}s] {msg}", file=sys.stderr, flush=True)
+
+
+T0 = time.perf_counter()
+
+
 def read_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -178,8 +186,10 @@ def run_ours(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N>1"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    log(f"start world={world} local={local}")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        log("process group up")
     lib = _ops.load_library()
     cfg = CFG
     B, T, V, E, H, L = cfg["B"], cfg["T"], cfg["V"], cfg["E"], cfg["H"], cfg["L"]
@@ -205,6 +215,7 @@ def run_ours(args):
     n_before = lib.b2c_launch_count()
     kd = GraphedKDStep(model, projector, loss_mod, opt, reducer, resident, max_grad_norm=1.0, autocast_dtype=torch.bfloat16,
                        use_graph=not args.no_graph, warmup_steps=3)
+    log("step object ready (warm-up + capture done)")
     launches_per_step = None if args.no_graph else (lib.b2c_launch_count() - n_before) // 4      # 3 warm-up bodies + 1 captured body
 
     def barrier_sync():
@@ -238,12 +249,12 @@ def run_ours(args):
     ms_step = float(tmax.item()) / args.steps
     value = B * world / (ms_step * 1e-3)
     final_loss = out5.tolist()
+    log(f"value leg done: {ms_step:.3f} ms/step")
 
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_run": True, "ms_per_step": ms_step, "value": value, "gpu_launches_per_step": launches_per_step}), flush=True)
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
     # ---- e2e: every step's inputs come from pinned host memory (uploaded on a copy stream into a staging set while the
     # previous step computes, then moved device-to-device into the graph's static buffers); the loss goes back to the host
@@ -281,6 +292,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
     e2e_val = B * world / (float(e_ms.item()) / args.steps * 1e-3)
+    log("e2e leg done")
 
     # ---- roofline of the named kernels, timed live with CUDA events on the launching stream
     peaks = read_peaks()
@@ -296,8 +308,18 @@ def run_ours(args):
     if rank == 0:
         line["cpu_baseline"] = cpu_baseline() if world == 1 and not args.no_cpu_baseline else None
         print(json.dumps(line), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """Multi-rank teardown: barrier, flush, hard exit.  destroy_process_group() after CUDA-graph work has been seen to
+    block for minutes on this stack (round 1, 2 GPUs: the JSON line was printed, then the job hung until the box timeout)."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def kernel_rooflines(lib, _ops, dev, cfg, peaks):

@@ -248,6 +248,17 @@ def attention_step(hidden: torch.Tensor, feats: torch.Tensor, attn_w: torch.Tens
     return ctx, wts
 
 
+def count_valid(targets: torch.Tensor, V: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """#{0 < target < V} as an int32 device scalar (the CrossEntropyLoss(ignore_index=0) normaliser)."""
+    lib = load_library()
+    _require_cuda(targets, "targets")
+    tg = targets.detach().to(torch.int64).contiguous()
+    if out is None:
+        out = torch.empty(1, dtype=torch.int32, device=targets.device)
+    _check(lib.b2c_count_valid(tg.data_ptr(), tg.numel(), int(V), out.data_ptr(), _stream()), "b2c_count_valid")
+    return out
+
+
 class KDLossFunction(torch.autograd.Function):
     """DistillationLoss.forward (reference src/distillation_utils.py:138-200): the token pass, the fused
     feature/hidden reduction and the weighting, with all gradients produced during the forward."""
@@ -256,7 +267,7 @@ class KDLossFunction(torch.autograd.Function):
     def forward(ctx, logits, teacher_logits, targets, feats_s, feats_t, hid_s, hid_t, cfg):
         lib = load_library()
         _require_cuda(logits, "student logits")
-        alpha, beta, gamma, temperature, w_ce, ce_mult, group = cfg
+        alpha, beta, gamma, temperature, w_ce, ce_mult, group, nval_global = cfg
         T, B, V = logits.shape
         N = T * B
         dev = logits.device
@@ -266,10 +277,12 @@ class KDLossFunction(torch.autograd.Function):
         z = teacher_logits.detach().to(device=dev, dtype=torch.float32).contiguous()
         tg = targets.detach().to(device=dev, dtype=torch.int64).contiguous()
         st = _stream()
-        nval = torch.empty(1, dtype=torch.int32, device=dev)
-        _check(lib.b2c_count_valid(tg.data_ptr(), N, V, nval.data_ptr(), st), "b2c_count_valid")
-        if group is not None:                      # data parallel: the CE normaliser is the GLOBAL non-PAD count
-            torch.distributed.all_reduce(nval, group=group)
+        if nval_global is not None:                # the caller already holds the (global) non-PAD count on the device
+            nval = nval_global
+        else:
+            nval = count_valid(tg, V)
+            if group is not None:                  # data parallel: the CE normaliser is the GLOBAL non-PAD count
+                torch.distributed.all_reduce(nval, group=group)
         dlogits = torch.empty_like(y)
         rows = torch.empty(2, N, dtype=torch.float32, device=dev)
         _check(lib.b2c_kd_token_loss(y.data_ptr(), z.data_ptr(), tg.data_ptr(), N, V, float(temperature), float(alpha), float(w_ce),

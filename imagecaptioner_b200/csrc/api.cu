@@ -1,5 +1,6 @@
 // b2c C ABI: host-side orchestration of the decoder / loss kernels.  See include/b2c.h for the contract and
 // oracle/manual_backward.py for the (CPU, test-only) blueprint of exactly this dataflow.
+#include <stdlib.h>
 #include "gemm.cuh"
 #include "loss_kernels.cuh"
 #include "decoder_kernels.cuh"
@@ -155,9 +156,12 @@ template <typename K> int set_smem(K kern, size_t bytes) {
 
 template <typename T>
 int attn_fwd(cudaStream_t st, const B2CShape& s, const float* P, const T* F, const float* u, T* ctx, float* attw) {
-  const size_t smem = (size_t)s.S * s.E * (sizeof(T) + 4) + (size_t)(s.E + s.S) * 4;
-  B2C_TRY(set_smem(attn_step_fwd_kernel<T>, smem));
-  attn_step_fwd_kernel<T><<<s.B, ATT_THREADS, smem, st>>>(P, F, u, s.E, s.S, s.E, ctx, s.E, attw);
+  const size_t smem = (size_t)s.S * s.E * sizeof(T) + (size_t)(s.E + s.S) * 4;
+  const int nq = cdiv(s.E / 4, 32);
+#define B2C_ATT(NQ) do { B2C_TRY(set_smem(attn_step_fwd_kernel<T, NQ>, smem)); \
+    attn_step_fwd_kernel<T, NQ><<<s.B, ATT_THREADS, smem, st>>>(P, F, u, s.E, s.S, s.E, ctx, s.E, attw); } while (0)
+  if (nq == 1) B2C_ATT(1); else if (nq == 2) B2C_ATT(2); else if (nq == 3) B2C_ATT(3); else B2C_ATT(0);
+#undef B2C_ATT
   B2C_LAUNCH_CHECK("attn_step_fwd_kernel");
   return 0;
 }
@@ -172,6 +176,57 @@ int lstm_layer_fwd(cudaStream_t st, const B2CShape& s, const Weights<T>& w, int 
   lstm_pointwise_fwd_kernel<T><<<ew_grid((long)s.B * s.H), 256, 0, st>>>(pre, c_prev, c_out, gates_out, h_rec, ld, h_next, 2 * s.H, h_top, s.H,
                                                                        s.B, s.H, dr.p, dr.seed, (uint32_t)k, row_base);
   B2C_LAUNCH_CHECK("lstm_pointwise_fwd_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------ sub-batch streams
+// The T-step recurrence is a serial chain of small kernels (a 128..512-row GEMM, a per-sample attention kernel, a pointwise
+// kernel), each bound by launch / prologue / L2 latency rather than by the machine's throughput.  Samples are independent,
+// so the batch is cut into NS contiguous sub-batches whose chains run on NS forked streams and overlap on the GPU; all
+// buffers keep their (T, B, .) layout (a sub-batch is a row range), so the time-batched GEMMs before and after the loop
+// still see whole tensors.  Fork / join use events, which CUDA graph capture records as parallel branches.
+constexpr int MAX_SUB = 4;
+struct SubStreams { cudaStream_t s[MAX_SUB]; cudaEvent_t fork; cudaEvent_t join[MAX_SUB]; };
+int get_substreams(SubStreams** out) {
+  static SubStreams ss; static bool ready = false;
+  if (!ready) {
+    for (int i = 0; i < MAX_SUB; ++i) {
+      B2C_CUDA(cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking));
+      B2C_CUDA(cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming));
+    }
+    B2C_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+    ready = true;
+  }
+  *out = &ss;
+  return 0;
+}
+// Measured on B200 (round 1, tools/microbench_streams.py): the branches do overlap 4-way, but a 128-row gate GEMM takes as
+// long as the 512-row one (7.8 vs 8.6 us) — the chain is bound by per-kernel latency x chain length, which a narrower
+// kernel does not shorten — so the whole step got 5 % slower (4x the launches).  Off unless B2C_SUB_BATCHES=2|4 is set.
+inline int pick_sub_batches(int B) {
+  static int want = -1;
+  if (want < 0) { const char* e = getenv("B2C_SUB_BATCHES"); want = e ? atoi(e) : 1; if (want != 2 && want != 4) want = 1; }
+  if (want > 1 && B >= 32 * want && B % want == 0) return want;
+  return 1;
+}
+struct SubPlan { int ns; cudaStream_t st[MAX_SUB]; int b0[MAX_SUB]; int bn[MAX_SUB]; SubStreams* ss; cudaStream_t main; };
+int fork_subs(SubPlan& sp, int B, cudaStream_t st) {
+  sp.ns = pick_sub_batches(B); sp.main = st; sp.ss = nullptr;
+  if (sp.ns == 1) { sp.st[0] = st; sp.b0[0] = 0; sp.bn[0] = B; return 0; }
+  B2C_TRY(get_substreams(&sp.ss));
+  B2C_CUDA(cudaEventRecord(sp.ss->fork, st));
+  for (int i = 0; i < sp.ns; ++i) {
+    sp.st[i] = sp.ss->s[i]; sp.bn[i] = B / sp.ns; sp.b0[i] = i * sp.bn[i];
+    B2C_CUDA(cudaStreamWaitEvent(sp.st[i], sp.ss->fork, 0));
+  }
+  return 0;
+}
+int join_subs(SubPlan& sp) {
+  if (sp.ns == 1) return 0;
+  for (int i = 0; i < sp.ns; ++i) {
+    B2C_CUDA(cudaEventRecord(sp.ss->join[i], sp.st[i]));
+    B2C_CUDA(cudaStreamWaitEvent(sp.main, sp.ss->join[i], 0));
+  }
   return 0;
 }
 
@@ -195,21 +250,30 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
   // embedding half of attention_combine for all steps, straight into layer 0's input slots
   B2C_TRY((gemm<T, T>(st, (int)TB, E, E, W.emb, E, 0, W.w.Wce, E, 0, W.xh[0], E + H, 0.f, p.comb_b)));
   const int inL = in_dim(s, L - 1), ldL = inL + H;
+  SubPlan sp;
+  B2C_TRY(fork_subs(sp, B, st));
   for (int t = 0; t < Tn; ++t) {
-    const T* q = W.xh[L - 1] + (long)t * B * ldL + inL;
-    float* u_t = W.u + (long)t * B * E;
-    T* ctx_t = W.ctx + (long)t * B * E;
-    B2C_TRY((gemm<T, float>(st, B, E, H, q, ldL, 0, W.w.Wh, H, 0, u_t, E)));
-    B2C_TRY(attn_fwd<T>(st, s, W.P, feats, u_t, ctx_t, attw + (long)t * B * S));
-    B2C_TRY((gemm<T, T>(st, B, E, E, ctx_t, E, 0, W.w.Wcc, E, 0, W.xh[0] + (long)t * B * (E + H), E + H, 1.f)));
-    for (int k = 0; k < L; ++k) {
-      const int in = in_dim(s, k), ld = in + H;
-      B2C_TRY(lstm_layer_fwd<T>(st, s, W.w, k, W.xh[k] + (long)t * B * ld, W.pre, W.c[k] + (long)t * B * H, W.c[k] + (long)(t + 1) * B * H,
-                                W.gates[k] + (long)t * B * 4 * H, W.xh[k] + (long)(t + 1) * B * ld + in,
-                                k + 1 < L ? W.xh[k + 1] + (long)t * B * 2 * H : nullptr, k == L - 1 ? hid_top + (long)t * B * H : nullptr,
-                                dr, (long)t * B));
+    for (int i = 0; i < sp.ns; ++i) {                          // interleaved issue: sub-batch chains advance together
+      cudaStream_t ss = sp.st[i];
+      const long b0 = sp.b0[i];
+      B2CShape sh = s; sh.B = sp.bn[i];
+      const long row = (long)t * B + b0;                       // first row of this sub-batch at step t in a (T,B,.) buffer
+      const T* q = W.xh[L - 1] + row * ldL + inL;
+      float* u_t = W.u + row * E;
+      T* ctx_t = W.ctx + row * E;
+      B2C_TRY((gemm<T, float>(ss, sh.B, E, H, q, ldL, 0, W.w.Wh, H, 0, u_t, E)));
+      B2C_TRY(attn_fwd<T>(ss, sh, W.P + b0 * S * E, feats + b0 * S * E, u_t, ctx_t, attw + row * S));
+      B2C_TRY((gemm<T, T>(ss, sh.B, E, E, ctx_t, E, 0, W.w.Wcc, E, 0, W.xh[0] + row * (E + H), E + H, 1.f)));
+      for (int k = 0; k < L; ++k) {
+        const int in = in_dim(s, k), ld = in + H;
+        B2C_TRY(lstm_layer_fwd<T>(ss, sh, W.w, k, W.xh[k] + row * ld, W.pre + b0 * 4 * H, W.c[k] + row * H, W.c[k] + (row + B) * H,
+                                  W.gates[k] + row * 4 * H, W.xh[k] + (row + B) * ld + in,
+                                  k + 1 < L ? W.xh[k + 1] + row * 2 * H : nullptr, k == L - 1 ? hid_top + row * H : nullptr,
+                                  dr, row));
+      }
     }
   }
+  B2C_TRY(join_subs(sp));
   // output head, time-batched: y = W2 Drop(ReLU(W1 h + b1)) + b2
   B2C_TRY((gemm<T, T>(st, (int)TB, E, H, hid_top, H, 0, W.w.W1, H, 0, W.o1, E, 0.f, p.out0_b, 1)));
   if (dr.p > 0.f) {
@@ -242,33 +306,42 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
   B2C_TRY((gemm<T, float>(st, E, H, (int)TB, W.do1, E, 1, hid_top, H, 1, g.out0_w, H)));
   B2C_TRY(colsum<T>(st, W.do1, TB, E, E, W.partial, g.out0_b));
   // ---- reverse time loop
-  const size_t att_smem = (size_t)S * E * (sizeof(T) + 4) + (size_t)(2 * E + S) * 4;
+  const size_t att_smem = (size_t)S * E * sizeof(T) + (size_t)(E + S) * 4;
   B2C_TRY(set_smem(attn_step_bwd_kernel<T>, att_smem));
+  for (int k = 0; k < L; ++k) B2C_CHECK_ARG(g.w_ih[k] && g.w_hh[k] && g.b_ih[k] && g.b_hh[k], "NULL LSTM gradient pointer (layer %d)", k);
+  SubPlan sp;
+  B2C_TRY(fork_subs(sp, B, st));
   for (int t = Tn - 1; t >= 0; --t) {
     const bool last = (t == Tn - 1);
-    for (int k = L - 1; k >= 0; --k) {
-      B2C_CHECK_ARG(g.w_ih[k] && g.w_hh[k] && g.b_ih[k] && g.b_hh[k], "NULL LSTM gradient pointer (layer %d)", k);
-      const int in = in_dim(s, k), ld = in + H;
-      const T* carry = last ? nullptr : (k == 0 ? W.dxh0 + (long)(t + 1) * B * (E + H) + E : W.dxh[k] + H);
-      const T* above = (k < L - 1) ? W.dxh[k + 1] : nullptr;
-      const bool top = (k == L - 1);
-      lstm_pointwise_bwd_kernel<T><<<ew_grid((long)B * H), 256, 0, st>>>(
-          W.gates[k] + (long)t * B * 4 * H, W.c[k] + (long)t * B * H, W.c[k] + (long)(t + 1) * B * H, W.dc[k], last ? 1 : 0,
-          carry, ld, above, 2 * H, top ? W.dHext + (long)t * B * H : nullptr, (top && dhid) ? dhid + (long)t * B * H : nullptr,
-          (top && !last) ? W.dq : nullptr, H, W.dgates[k] + (long)t * B * 4 * H, B, H, dr.p, dr.seed, (uint32_t)k, (long)t * B);
-      B2C_LAUNCH_CHECK("lstm_pointwise_bwd_kernel");
-      T* out = (k == 0) ? W.dxh0 + (long)t * B * (E + H) : W.dxh[k];
-      B2C_TRY((gemm<T, T>(st, B, ld, 4 * H, W.dgates[k] + (long)t * B * 4 * H, 4 * H, 0, W.w.Wcat[k], ld, 1, out, ld)));
+    for (int i = 0; i < sp.ns; ++i) {
+      cudaStream_t ss = sp.st[i];
+      const long b0 = sp.b0[i];
+      const int Bh = sp.bn[i];
+      const long row = (long)t * B + b0;
+      for (int k = L - 1; k >= 0; --k) {
+        const int in = in_dim(s, k), ld = in + H;
+        const T* carry = last ? nullptr : (k == 0 ? W.dxh0 + (row + B) * (E + H) + E : W.dxh[k] + b0 * 2 * H + H);
+        const T* above = (k < L - 1) ? W.dxh[k + 1] + b0 * 2 * H : nullptr;
+        const bool top = (k == L - 1);
+        lstm_pointwise_bwd_kernel<T><<<ew_grid((long)Bh * H), 256, 0, ss>>>(
+            W.gates[k] + row * 4 * H, W.c[k] + row * H, W.c[k] + (row + B) * H, W.dc[k] + b0 * H, last ? 1 : 0,
+            carry, ld, above, 2 * H, top ? W.dHext + row * H : nullptr, (top && dhid) ? dhid + row * H : nullptr,
+            (top && !last) ? W.dq + b0 * H : nullptr, H, W.dgates[k] + row * 4 * H, Bh, H, dr.p, dr.seed, (uint32_t)k, row);
+        B2C_LAUNCH_CHECK("lstm_pointwise_bwd_kernel");
+        T* out = (k == 0) ? W.dxh0 + row * (E + H) : W.dxh[k] + b0 * 2 * H;
+        B2C_TRY((gemm<T, T>(ss, Bh, ld, 4 * H, W.dgates[k] + row * 4 * H, 4 * H, 0, W.w.Wcat[k], ld, 1, out, ld)));
+      }
+      const T* dx = W.dxh0 + row * (E + H);
+      T* dctx_t = W.dctx + row * E;
+      T* du_t = W.du + row * E;
+      B2C_TRY((gemm<T, T>(ss, Bh, E, E, dx, E + H, 0, W.w.Wcc, E, 1, dctx_t, E)));
+      attn_step_bwd_kernel<T><<<Bh, ATT_THREADS, att_smem, ss>>>(W.P + b0 * S * E, feats + b0 * S * E, W.u + row * E, E, attw + row * S, dctx_t, E,
+                                                               S, E, W.ds + row * S, du_t, E);
+      B2C_LAUNCH_CHECK("attn_step_bwd_kernel");
+      if (t > 0) B2C_TRY((gemm<T, T>(ss, Bh, H, E, du_t, E, 0, W.w.Wh, H, 1, W.dq + b0 * H, H)));
     }
-    const T* dx = W.dxh0 + (long)t * B * (E + H);
-    T* dctx_t = W.dctx + (long)t * B * E;
-    T* du_t = W.du + (long)t * B * E;
-    B2C_TRY((gemm<T, T>(st, B, E, E, dx, E + H, 0, W.w.Wcc, E, 1, dctx_t, E)));
-    attn_step_bwd_kernel<T><<<B, ATT_THREADS, att_smem, st>>>(W.P, feats, W.u + (long)t * B * E, E, attw + (long)t * B * S, dctx_t, E,
-                                                             S, E, W.ds + (long)t * B * S, du_t, E);
-    B2C_LAUNCH_CHECK("attn_step_bwd_kernel");
-    if (t > 0) B2C_TRY((gemm<T, T>(st, B, H, E, du_t, E, 0, W.w.Wh, H, 1, W.dq, H)));
   }
+  B2C_TRY(join_subs(sp));
   // ---- post-loop, time-batched weight gradients
   for (int k = 0; k < L; ++k) {
     const int in = in_dim(s, k), ld = in + H;
@@ -369,6 +442,29 @@ int kd_token_loss_impl(const TS* y, const float* z, const int64_t* tgt, long N, 
   const bool t4 = (temperature == 4.0f);
   const size_t smem = align_up((size_t)V * 4, 16) + align_up((size_t)V * sizeof(TS), 16);
   const float inv_temp = 1.0f / temperature, kd_coef = alpha * temperature / (float)N;
+  // default: persistent CTAs, TMA double-buffered row prefetch, register-resident math (V % 8 == 0, V <= 16384)
+  if (vec && V <= 8 * KDR_THREADS * 8) {
+    const int need = cdiv(V / 8, KDR_THREADS);
+    const size_t psmem = 2 * ((size_t)V * 4 + (size_t)V * sizeof(TS));
+    int per_sm = (int)((200 * 1024) / (psmem + 1024)); if (per_sm < 1) per_sm = 1;
+    const int reg_cap = need <= 3 ? 3 : (need <= 5 ? 2 : 1);      // matches the kernel's __launch_bounds__ min-blocks
+    if (per_sm > reg_cap) per_sm = reg_cap;
+    long grid = (long)sm_count() * per_sm; if (grid > N) grid = N;
+#define B2C_KDP(NCH, T4)                                                                                                   \
+  do {                                                                                                                     \
+    B2C_TRY(set_smem(kd_token_loss_pipe_kernel<TS, NCH, T4>, psmem));                                                      \
+    kd_token_loss_pipe_kernel<TS, NCH, T4><<<(unsigned)grid, KDR_THREADS, psmem, st>>>(y, z, tgt, N, V, inv_temp, temperature, kd_coef, w_ce_eff, n_valid, dy, row_kl, row_ce); \
+  } while (0)
+#define B2C_KDP2(NCH) do { if (t4) B2C_KDP(NCH, true); else B2C_KDP(NCH, false); } while (0)
+    switch (need) {
+      case 1: B2C_KDP2(1); break; case 2: B2C_KDP2(2); break; case 3: B2C_KDP2(3); break; case 4: B2C_KDP2(4); break;
+      case 5: B2C_KDP2(5); break; case 6: B2C_KDP2(6); break; case 7: B2C_KDP2(7); break; default: B2C_KDP2(8); break;
+    }
+#undef B2C_KDP2
+#undef B2C_KDP
+    B2C_LAUNCH_CHECK("kd_token_loss_pipe_kernel");
+    return 0;
+  }
 #define B2C_KD_LAUNCH(G, T4)                                                                                             \
   do {                                                                                                                   \
     B2C_TRY(set_smem(kd_token_loss_kernel<TS, G, T4>, smem));                                                            \

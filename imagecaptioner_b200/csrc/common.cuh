@@ -54,6 +54,9 @@ template <> struct Math<bf16> {
   static __device__ __forceinline__ float log_(float x) { return __logf(x); }
 };
 
+// 2^x, one MUFU (flush-to-zero: no denormal range fix-up code around it)
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -60,42 +60,83 @@ __global__ void __launch_bounds__(256) embedding_scatter_add_kernel(const float*
 // P_b and F_b (S x E each, contiguous) are staged in shared memory by two 1-D TMA bulk copies.
 // ======================================================================================
 constexpr int ATT_THREADS = 256;
+constexpr int ATT_MAXTOK = 7;     // tokens per warp held in registers (S <= 56 with 8 warps)
 
-// P (the hoisted projection, kept in fp32 in both modes: the score sums E tanh terms) and F (features, compute type)
+// F_b (the S x E feature tokens of one sample, compute type) is staged in shared memory by one 1-D TMA bulk copy on an
+// mbarrier.  P_b (the hoisted projection, fp32 in both modes because the score sums E tanh terms) is used exactly once per
+// step, so it is streamed from L2 with coalesced 128-bit loads that overlap the TMA instead of taking shared memory:
+// 26 KB per CTA at E=256 bf16, so all B CTAs of a step are co-resident and their loads overlap each other's math.
 template <typename T>
-__device__ __forceinline__ void att_stage(const float* P, const T* F, int b, int SE, float* Ps, T* Fs, uint64_t* bar) {
+__device__ __forceinline__ void att_stage_F(const T* F, int b, int SE, T* Fs, uint64_t* bar) {
   if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const uint32_t pb = (uint32_t)(SE * sizeof(float)), fb = (uint32_t)(SE * sizeof(T));
-    mbar_arrive_expect_tx(bar, pb + fb);
-    bulk_g2s(Ps, P + (long)b * SE, pb, bar);
+    const uint32_t fb = (uint32_t)(SE * sizeof(T));
+    mbar_arrive_expect_tx(bar, fb);
     bulk_g2s(Fs, F + (long)b * SE, fb, bar);
   }
 }
 
-template <typename T>
+template <typename T, int NQ>       // NQ = float4 per lane per token held in registers (ceil(E/128)); 0 = generic loop
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const float* __restrict__ u, long ldu,
                      int S, int E, T* __restrict__ ctx, long ldctx, float* __restrict__ attw /* (B,S) or null */) {
   extern __shared__ __align__(128) unsigned char att_smem[];
   const int SE = S * E;
-  float* Ps = reinterpret_cast<float*>(att_smem);
-  T* Fs = reinterpret_cast<T*>(Ps + SE);
+  T* Fs = reinterpret_cast<T*>(att_smem);
   float* us = reinterpret_cast<float*>(Fs + SE);
   float* sc = us + E;
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATT_THREADS / 32;
   const int b = blockIdx.x;
-  att_stage<T>(P, F, b, SE, Ps, Fs, &bar);
+  att_stage_F<T>(F, b, SE, Fs, &bar);
   for (int e = tid; e < E; e += ATT_THREADS) us[e] = u[(long)b * ldu + e];
   __syncthreads();
-  mbar_wait(&bar, 0);
-  for (int l = warp; l < S; l += nwarp) {
-    float a = 0.f;
-    for (int e = lane; e < E; e += 32) a += Math<T>::tanh_(Ps[l * E + e] + us[e]);
-    a = warp_sum(a);
-    if (lane == 0) sc[l] = a;
+  // scores: warp per token, lanes over E in float4 units.  P is streamed: every warp first issues ALL its loads (its
+  // <= ATT_MAXTOK tokens x ATT_MAXQ float4 per lane) so they are in flight together, then does the tanh sums from registers.
+  const float4* Pb = reinterpret_cast<const float4*>(P + (long)b * SE);
+  const int E4 = E >> 2;
+  if (NQ > 0 && S <= ATT_MAXTOK * nwarp) {
+    constexpr int NQR = NQ > 0 ? NQ : 1;
+    float4 pv[ATT_MAXTOK][NQR];
+#pragma unroll
+    for (int k = 0; k < ATT_MAXTOK; ++k) {
+      const int l = warp + k * nwarp;
+#pragma unroll
+      for (int j = 0; j < NQR; ++j) {
+        const int q = lane + j * 32;
+        if (l < S && q < E4) pv[k][j] = __ldg(Pb + l * E4 + q);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < ATT_MAXTOK; ++k) {
+      const int l = warp + k * nwarp;
+      if (l < S) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < NQR; ++j) {
+          const int q = lane + j * 32;
+          if (q < E4) {
+            const float4 p = pv[k][j];
+            const float4 uu = *reinterpret_cast<const float4*>(us + q * 4);
+            a += Math<T>::tanh_(p.x + uu.x) + Math<T>::tanh_(p.y + uu.y) + Math<T>::tanh_(p.z + uu.z) + Math<T>::tanh_(p.w + uu.w);
+          }
+        }
+        a = warp_sum(a);
+        if (lane == 0) sc[l] = a;
+      }
+    }
+  } else {
+    for (int l = warp; l < S; l += nwarp) {
+      float a = 0.f;
+      for (int q = lane; q < E4; q += 32) {
+        const float4 p = __ldg(Pb + l * E4 + q);
+        const float4 uu = *reinterpret_cast<const float4*>(us + q * 4);
+        a += Math<T>::tanh_(p.x + uu.x) + Math<T>::tanh_(p.y + uu.y) + Math<T>::tanh_(p.z + uu.z) + Math<T>::tanh_(p.w + uu.w);
+      }
+      a = warp_sum(a);
+      if (lane == 0) sc[l] = a;
+    }
   }
   __syncthreads();
   if (warp == 0) {
@@ -109,6 +150,7 @@ attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
     for (int l = lane; l < S; l += 32) { const float wv = sc[l] * inv; sc[l] = wv; if (attw) attw[(long)b * S + l] = wv; }
   }
   __syncthreads();
+  mbar_wait(&bar, 0);                          // the feature tokens have landed (their copy overlapped the score phase)
   for (int e = tid; e < E; e += ATT_THREADS) {
     float a = 0.f;
     for (int l = 0; l < S; ++l) a = fmaf(sc[l], to_f<T>(Fs[l * E + e]), a);
@@ -125,16 +167,14 @@ attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
                      int S, int E, float* __restrict__ ds_out, T* __restrict__ du, long lddu) {
   extern __shared__ __align__(128) unsigned char att_smem[];
   const int SE = S * E;
-  float* Ps = reinterpret_cast<float*>(att_smem);
-  T* Fs = reinterpret_cast<T*>(Ps + SE);
-  float* us = reinterpret_cast<float*>(Fs + SE);
-  float* dcs = us + E;
+  T* Fs = reinterpret_cast<T*>(att_smem);
+  float* dcs = reinterpret_cast<float*>(Fs + SE);
   float* dw = dcs + E;
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATT_THREADS / 32;
   const int b = blockIdx.x;
-  att_stage<T>(P, F, b, SE, Ps, Fs, &bar);
-  for (int e = tid; e < E; e += ATT_THREADS) { us[e] = u[(long)b * ldu + e]; dcs[e] = to_f<T>(dctx[(long)b * lddctx + e]); }
+  att_stage_F<T>(F, b, SE, Fs, &bar);
+  for (int e = tid; e < E; e += ATT_THREADS) dcs[e] = to_f<T>(dctx[(long)b * lddctx + e]);
   __syncthreads();
   mbar_wait(&bar, 0);
   for (int l = warp; l < S; l += nwarp) {
@@ -151,9 +191,10 @@ attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
     for (int l = lane; l < S; l += 32) { const float v = attw[(long)b * S + l] * (dw[l] - dot); dw[l] = v; ds_out[(long)b * S + l] = v; }
   }
   __syncthreads();
+  const float* Pb = P + (long)b * SE;
   for (int e = tid; e < E; e += ATT_THREADS) {
-    float a = 0.f; const float ue = us[e];
-    for (int l = 0; l < S; ++l) { const float th = Math<T>::tanh_(Ps[l * E + e] + ue); a = fmaf(dw[l], 1.0f - th * th, a); }
+    float a = 0.f; const float ue = u[(long)b * ldu + e];
+    for (int l = 0; l < S; ++l) { const float th = Math<T>::tanh_(__ldg(Pb + l * E + e) + ue); a = fmaf(dw[l], 1.0f - th * th, a); }
     du[(long)b * lddu + e] = from_f<T>(a);
   }
 }

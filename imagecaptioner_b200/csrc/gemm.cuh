@@ -155,7 +155,7 @@ constexpr int TC_EPI_BYTES = 4 * 32 * TC_EPI_PITCH;    // one 32-row staging til
 template <int BN> struct TcCfg {
   static constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   static constexpr uint32_t STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (128 / 256 / 512 columns)
   static constexpr size_t SMEM_BYTES = (size_t)TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + TC_EPI_BYTES;
 };
 
@@ -176,35 +176,34 @@ __device__ __forceinline__ uint4 epi_combine_f32(uint4 acc, uint4 old, float bet
   return o;
 }
 
-// grid = (N tiles, M tiles, K splits).  With K splits > 1 (fp32 output only) every split adds its partial tile into C with
+// Persistent: grid = min(work items, SMs); work item = (M tile, N tile, K split).  With K splits > 1 (fp32 output only) every split adds its partial tile into C with
 // red.global.add.f32; the host has zeroed C (beta == 0) or C already holds the value to accumulate onto (beta == 1).
 template <int BN, bool A_MN, bool B_MN, typename TC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, float alpha, float beta, TC* __restrict__ C, long ldc,
-               const float* __restrict__ bias, int relu, int kb_per_split) {
+               const float* __restrict__ bias, int relu, int kb_per_split, int tiles_m, int tiles_n, int splits) {
   using Cfg = TcCfg<BN>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + (size_t)TC_STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + TC_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tfull_bar = empty_bar + TC_STAGES;          // [2] accumulator stage complete (MMA -> epilogue)
+  uint64_t* tempty_bar = tfull_bar + 2;                 // [2] accumulator stage drained  (epilogue -> MMA), 4 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   unsigned char* epi_stage = base + (size_t)TC_STAGES * Cfg::STAGE_BYTES + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   const int num_kb_total = (K + TC_BK - 1) / TC_BK;
-  const int kb_begin = blockIdx.z * kb_per_split;
-  const int kb_end = min(num_kb_total, kb_begin + kb_per_split);
-  const int num_kb = kb_end - kb_begin;                 // >= 1 by construction of the grid
-  const bool split = gridDim.z > 1;
+  const int tiles_mn = tiles_m * tiles_n;
+  const int total = tiles_mn * splits;                  // work items (M tile, N tile, K split), dealt round-robin to the CTAs
+  const bool split = splits > 1;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-      mbar_init(tmem_full_bar, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -219,47 +218,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % TC_STAGES; const uint32_t ph = (i / TC_STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        unsigned char* sa = base + (size_t)s * Cfg::STAGE_BYTES;
-        unsigned char* sb = sa + TC_A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        const int k0 = (kb_begin + i) * TC_BK;
-        if (!A_MN) {
-          tma_load_2d(sa, &tmA, k0, m0, &full_bar[s]);                      // box {64 k, 128 m}
-        } else {
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int sp = w / tiles_mn, rem = w - sp * tiles_mn;
+        const int m0 = (rem / tiles_n) * TC_BM, n0 = (rem % tiles_n) * BN;
+        const int kb_begin = sp * kb_per_split, kb_end = min(num_kb_total, kb_begin + kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % TC_STAGES; const uint32_t ph = (it / TC_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          unsigned char* sa = base + (size_t)s * Cfg::STAGE_BYTES;
+          unsigned char* sb = sa + TC_A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          const int k0 = kb * TC_BK;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, k0, m0, &full_bar[s]);                      // box {64 k, 128 m}
+          } else {
 #pragma unroll
-          for (int j = 0; j < TC_BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, m0 + j * 64, k0, &full_bar[s]);   // box {64 m, 64 k}
-        }
-        if (!B_MN) {
-          tma_load_2d(sb, &tmB, k0, n0, &full_bar[s]);                      // box {64 k, BN n}
-        } else {
+            for (int j = 0; j < TC_BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, m0 + j * 64, k0, &full_bar[s]);   // box {64 m, 64 k}
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, k0, n0, &full_bar[s]);                      // box {64 k, BN n}
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, n0 + j * 64, k0, &full_bar[s]);      // box {64 n, 64 k}
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, n0 + j * 64, k0, &full_bar[s]);      // box {64 n, 64 k}
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (one thread)
+    // ------------------------------------------------ MMA issuer (one thread), two TMEM accumulator stages
     if (lane == 0) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                  ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % TC_STAGES; const uint32_t ph = (i / TC_STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, t = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++t) {
+        const int sp = w / tiles_mn;
+        const int kb_begin = sp * kb_per_split, kb_end = min(num_kb_total, kb_begin + kb_per_split);
+        const int as = t & 1; const uint32_t aph = (t >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1);                                  // the epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t sa = smem_u32(base + (size_t)s * Cfg::STAGE_BYTES);
-        const uint32_t sb = sa + TC_A_BYTES;
+        const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % TC_STAGES; const uint32_t ph = (it / TC_STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(base + (size_t)s * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + TC_A_BYTES;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t adesc = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
-          const uint64_t bdesc = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-          tc_mma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+            tc_mma_bf16(tacc, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);            // frees the smem slot once these MMAs have read it
         }
-        tc_commit(&empty_bar[s]);              // frees the smem slot once these MMAs have read it
+        tc_commit(&tfull_bar[as]);             // accumulator stage complete
       }
-      tc_commit(tmem_full_bar);                // accumulator complete
     }
   } else {
     // ------------------------------------------------ epilogue: warps 2..5 -> TMEM lane quarters (warp % 4).
@@ -270,16 +284,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int PER = 16 / (int)sizeof(TC);           // elements per 16-byte unit: 8 (bf16) or 4 (fp32)
     constexpr int CH = 128 / (int)sizeof(TC);           // columns per staged chunk: 64 (bf16) or 32 (fp32)
     const bool vec_ok = (((uintptr_t)C) % 16 == 0) && ((ldc * (long)sizeof(TC)) % 16 == 0);
-    const bool add_bias = (bias != nullptr) && (!split || blockIdx.z == 0);
-    mbar_wait(tmem_full_bar, 0);
+    int t = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++t) {
+    const int sp = w / tiles_mn, rem = w - sp * tiles_mn;
+    const int m0 = (rem / tiles_n) * TC_BM, n0 = (rem % tiles_n) * BN;
+    const int as = t & 1; const uint32_t aph = (t >> 1) & 1;
+    const bool add_bias = (bias != nullptr) && (sp == 0);
+    mbar_wait(&tfull_bar[as], aph);
     tc_fence_after();
+    const uint32_t tacc = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += CH) {
       if (n0 + c0 >= N) break;
 #pragma unroll
       for (int h = 0; h < CH / 32; ++h) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + h * 32), v);
+        tmem_ld32(tacc + (uint32_t)(c0 + h * 32), v);
         const int colb = n0 + c0 + h * 32;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -310,7 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (split) {
             const float* a = reinterpret_cast<const float*>(&acc);
 #pragma unroll
-            for (int e = 0; e < PER; ++e) if (gcol + e < N) atomicAdd(reinterpret_cast<float*>(cp) + e, a[e]);
+            for (int e = 0; e < 4; ++e) if (gcol + e < N) atomicAdd(reinterpret_cast<float*>(cp) + e, a[e]);
           } else if (vec_ok && gcol + PER <= N) {
             uint4 o = acc;
             if (beta != 0.f) {
@@ -332,6 +352,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       __syncwarp();
+    }
+    tc_fence_before();                         // order this warp's tcgen05.ld before releasing the accumulator stage
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
   }
   tc_fence_before();
@@ -404,6 +428,12 @@ inline int pick_k_splits(const GemmArgs& g, int* kb_per_split) {
   return cdiv(num_kb, *kb_per_split);                      // no empty split
 }
 
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148; }
+  return n;
+}
+
 template <int BN, bool A_MN, bool B_MN, typename TC>
 int launch_tc(const GemmArgs& g, cudaStream_t st) {
   CUtensorMap ta, tb;
@@ -419,8 +449,11 @@ int launch_tc(const GemmArgs& g, cudaStream_t st) {
   const int splits = pick_k_splits<BN, TC>(g, &kb_per_split);
   if (splits > 1 && g.beta == 0.f)
     B2C_CUDA(cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(TC), 0, (size_t)g.N * sizeof(TC), (size_t)g.M, st));
-  dim3 grid(cdiv(g.N, BN), cdiv(g.M, TC_BM), splits);
-  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ta, tb, g.M, g.N, g.K, g.alpha, g.beta, (TC*)g.C, g.ldc, g.bias, g.relu, kb_per_split);
+  const int tiles_m = cdiv(g.M, TC_BM), tiles_n = cdiv(g.N, BN);
+  const long total = (long)tiles_m * tiles_n * splits;
+  const int grid = (int)(total < sm_count() ? total : sm_count());
+  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ta, tb, g.M, g.N, g.K, g.alpha, g.beta, (TC*)g.C, g.ldc, g.bias, g.relu,
+                                                        kb_per_split, tiles_m, tiles_n, splits);
   B2C_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -436,7 +469,9 @@ int launch_tc_major(const GemmArgs& g, cudaStream_t st) {
 // bf16 operands on tensor cores; TC = bf16 or float output.
 template <typename TC>
 int gemm_bf16_tc(const GemmArgs& g, cudaStream_t st) {
-  const long tiles128 = (long)cdiv(g.M, TC_BM) * cdiv(g.N, 128);
+  const long tm = cdiv(g.M, TC_BM);
+  const long tiles128 = tm * cdiv(g.N, 128), tiles256 = tm * cdiv(g.N, 256);
+  if (g.N >= 1024 && tiles256 >= 2L * sm_count()) return launch_tc_major<256, TC>(g, st);   // wide outputs: fewest operand re-reads
   if (g.N <= 64 || tiles128 < 120) return launch_tc_major<64, TC>(g, st);
   return launch_tc_major<128, TC>(g, st);
 }

@@ -167,6 +167,163 @@ kd_token_loss_kernel(const TS* __restrict__ y, const float* __restrict__ z, cons
   }
 }
 
+// Kernel (3), default form (V % 8 == 0, V <= 16384; NCH == ceil(V/8/256) so only the last chunk can be partial): persistent CTAs (grid = SMs x resident CTAs), each looping over logits
+// rows.  The NEXT row's student and teacher logits are prefetched into a double-buffered shared-memory slot by two 1-D TMA
+// bulk copies on an mbarrier while the CURRENT row is processed entirely in registers: one 128-bit shared-memory read per
+// 8 logits, then row maxima, partition sums and the gradient on registers (2 ex2 per logit pair), 128-bit streaming
+// stores.  HBM traffic is exactly {read y, read z, write dy}; the TMA prefetch keeps ~3 rows per SM in flight.
+constexpr int KDR_THREADS = 256;
+
+template <typename TS> struct RowS;     // 8 elements from shared memory / to global memory
+template <> struct RowS<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    v[0] = bf16_lo(a.x); v[1] = bf16_hi(a.x); v[2] = bf16_lo(a.y); v[3] = bf16_hi(a.y);
+    v[4] = bf16_lo(a.z); v[5] = bf16_hi(a.z); v[6] = bf16_lo(a.w); v[7] = bf16_hi(a.w);
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
+    st_na_v4(p, make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])));
+  }
+};
+template <> struct RowS<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    st_na_v4(p, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+    st_na_v4(p + 4, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+  }
+};
+
+template <typename TS, int NCH, bool TEMP4>
+__global__ void __launch_bounds__(KDR_THREADS, (NCH <= 3 ? 3 : (NCH <= 5 ? 2 : 1)))
+kd_token_loss_pipe_kernel(const TS* __restrict__ y, const float* __restrict__ z, const int64_t* __restrict__ tgt,
+                          long N, int V, float inv_temp, float temperature, float kd_coef, float w_ce, const int* __restrict__ n_valid_ptr,
+                          TS* __restrict__ dy, float* __restrict__ row_kl, float* __restrict__ row_ce) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[2];
+  __shared__ float scratch[KDR_THREADS / 32 * 4];
+  const size_t zbytes = (size_t)V * 4, ybytes = (size_t)V * sizeof(TS), slot = zbytes + ybytes;    // both multiples of 16
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int groups = V >> 3;
+  const int n_valid = *n_valid_ptr;
+
+  auto issue = [&](long row, int sidx) {       // thread 0 only
+    unsigned char* dst = smem_raw + (size_t)sidx * slot;
+    mbar_arrive_expect_tx(&full_bar[sidx], (uint32_t)slot);
+    bulk_g2s(dst, z + row * (long)V, (uint32_t)zbytes, &full_bar[sidx]);
+    bulk_g2s(dst + zbytes, y + row * (long)V, (uint32_t)ybytes, &full_bar[sidx]);
+  };
+  if (tid == 0) { mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1); fence_barrier_init(); }
+  __syncthreads();
+  const long r0 = blockIdx.x, stride = gridDim.x;
+  if (tid == 0) {
+    if (r0 < N) issue(r0, 0);
+    if (r0 + stride < N) issue(r0 + stride, 1);
+  }
+
+  int it = 0;
+  for (long r = r0; r < N; r += stride, ++it) {
+    const int sidx = it & 1; const uint32_t ph = (it >> 1) & 1;
+    const float* zs = reinterpret_cast<const float*>(smem_raw + (size_t)sidx * slot);
+    const TS* ys = reinterpret_cast<const TS*>(smem_raw + (size_t)sidx * slot + zbytes);
+    mbar_wait(&full_bar[sidx], ph);
+    float yv[NCH][8], zv[NCH][8];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int g = tid + i * KDR_THREADS;
+      if (i < NCH - 1 || g < groups) { RowS<TS>::load(ys + g * 8, yv[i]); RowS<float>::load(zs + g * 8, zv[i]); }
+    }
+    const long t64 = tgt[r];
+    const bool valid = (t64 > 0) && (t64 < V);
+    const int t_idx = valid ? (int)t64 : -1;
+    const float y_tgt = valid ? to_f<TS>(ys[t_idx]) : 0.f, z_tgt = valid ? zs[t_idx] : 0.f;
+    __syncthreads();                           // every thread has taken its groups out of the slot ...
+    if (tid == 0 && r + 2 * stride < N) issue(r + 2 * stride, sidx);      // ... so the row after next can land in it
+
+    // phase 1: row maxima
+    float my = -INFINITY, mz = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      if (i < NCH - 1 || tid + i * KDR_THREADS < groups) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { my = fmaxf(my, yv[i][j]); mz = fmaxf(mz, zv[i][j]); }
+      }
+    }
+    my = warp_max(my); mz = warp_max(mz);
+    if (lane == 0) { scratch[warp * 2] = my; scratch[warp * 2 + 1] = mz; }
+    __syncthreads();
+    my = scratch[0]; mz = scratch[1];
+#pragma unroll
+    for (int i = 1; i < KDR_THREADS / 32; ++i) { my = fmaxf(my, scratch[i * 2]); mz = fmaxf(mz, scratch[i * 2 + 1]); }
+    __syncthreads();
+
+    // phase 2: exponentials (kept in the same registers) and the four partition sums.  Everything is in log2 units:
+    // yd2 = (y - my)/Temp * log2(e) is ONE FFMA, e^x is ONE ex2.approx.ftz; the ln(2) factor of sA is applied once per row.
+    const float cy = inv_temp * 1.4426950408889634f;
+    const float my_c = -my * cy, mz_c = -mz * cy;
+    float sT = 0.f, sZ = 0.f, sA = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      if (i < NCH - 1 || tid + i * KDR_THREADS < groups) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float yd2 = fmaf(yv[i][j], cy, my_c), zd2 = fmaf(zv[i][j], cy, mz_c);
+          const float ey = ex2_ftz(yd2), ez = ex2_ftz(zd2);
+          sT += ey; sZ += ez; sA = fmaf(ez, zd2 - yd2, sA);
+          if (TEMP4) { const float e2 = ey * ey; s1 = fmaf(e2, e2, s1); }
+          else s1 += ex2_ftz((yv[i][j] - my) * 1.4426950408889634f);
+          yv[i][j] = ey; zv[i][j] = ez;
+        }
+      }
+    }
+    sT = warp_sum(sT); sZ = warp_sum(sZ); sA = warp_sum(sA); s1 = warp_sum(s1);
+    if (lane == 0) { scratch[warp * 4] = sT; scratch[warp * 4 + 1] = sZ; scratch[warp * 4 + 2] = sA; scratch[warp * 4 + 3] = s1; }
+    __syncthreads();
+    sT = sZ = sA = s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < KDR_THREADS / 32; ++i) { sT += scratch[i * 4]; sZ += scratch[i * 4 + 1]; sA += scratch[i * 4 + 2]; s1 += scratch[i * 4 + 3]; }
+    sA *= 0.6931471805599453f;
+
+    const float inv_sT = 1.0f / sT, inv_sZ = 1.0f / sZ, inv_s1 = 1.0f / s1;
+    const float ce_coef = (valid && n_valid > 0) ? w_ce / (float)n_valid : 0.0f;
+    if (tid == 0) {
+      row_kl[r] = sA * inv_sZ - __logf(sZ) + __logf(sT);
+      row_ce[r] = valid ? (__logf(s1) + my - y_tgt) : 0.0f;
+    }
+
+    // phase 3: gradient, straight from registers to 128-bit streaming stores.  The one-hot term of the target logit is
+    // applied by the thread that owns that logit with one scalar store after its vector store (same thread, same address).
+    TS* dyg = dy + r * (long)V;
+    const float a_s = kd_coef * inv_sT, a_t = -kd_coef * inv_sZ, a_c = ce_coef * inv_s1;
+    const int t_grp = t_idx >> 3;               // -1 on PAD rows: matches no group
+    float g_t = 0.f;
+    if (valid) {
+      const float ey_t = ex2_ftz(fmaf(y_tgt, cy, my_c)), ez_t = ex2_ftz(fmaf(z_tgt, cy, mz_c));
+      float e1_t;
+      if (TEMP4) { const float e2 = ey_t * ey_t; e1_t = e2 * e2; } else { e1_t = ex2_ftz((y_tgt - my) * 1.4426950408889634f); }
+      g_t = fmaf(a_s, ey_t, fmaf(a_t, ez_t, a_c * e1_t)) - ce_coef;
+    }
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int g = tid + i * KDR_THREADS;
+      if (i < NCH - 1 || g < groups) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float ey = yv[i][j];
+          float e1;
+          if (TEMP4) { const float e2 = ey * ey; e1 = e2 * e2; } else { e1 = __powf(ey, temperature); }
+          o[j] = fmaf(a_s, ey, fmaf(a_t, zv[i][j], a_c * e1));
+        }
+        RowS<TS>::store(dyg + g * 8, o);
+        if (g == t_grp) dyg[t_idx] = from_f<TS>(g_t);
+      }
+    }
+  }
+}
+
 __global__ void count_valid_kernel(const int64_t* __restrict__ tgt, long n, int V, int* __restrict__ out) {
   __shared__ int part[32];
   int c = 0;

@@ -15,6 +15,7 @@ from typing import Dict, Optional
 
 import torch
 
+from . import _ops
 from .ddp import FlatGradAllReducer
 
 
@@ -31,12 +32,23 @@ class GraphedKDStep:
         self.static = {k: example[k].clone() for k in self.INPUT_KEYS if example.get(k) is not None}
         self.static["encoder_features"].requires_grad_(True)
         self.out5 = None
-        self.graph = None
+        self.graph = None          # forward + loss + backward (+ clip + AdamW when there is a single rank)
+        self.graph_opt = None      # clip + AdamW, a second graph when a gradient all-reduce sits in between
+        self.world = reducer.world_size
+        # Data parallel: NCCL stays OUTSIDE the graphs.  The non-PAD count is all-reduced before graph 1 (targets are an
+        # input, so it does not depend on the step) and the flat gradient buffer between graph 1 and graph 2.
+        self.nval = torch.zeros(1, dtype=torch.int32, device=self.static["targets"].device) if self.world > 1 else None
         if use_graph:
             self._capture(warmup_steps)
 
     # ---- the step body (eager or under capture)
-    def _body(self):
+    def _pre(self):
+        if self.world > 1:
+            _ops.count_valid(self.static["targets"], self.loss_module.vocab_size or 2 ** 31 - 1, out=self.nval)
+            torch.distributed.all_reduce(self.nval, group=self.loss_module.process_group)
+            self.loss_module.n_valid_global = self.nval
+
+    def _fwd_bwd(self):
         inp = self.static
         feats = inp["encoder_features"]
         if feats.grad is not None:
@@ -51,11 +63,19 @@ class GraphedKDStep:
             inp["targets"])
         self.reducer.zero_grad()
         loss.backward()
-        self.reducer.allreduce()
+        return out5
+
+    def _clip_and_update(self):
         if self.max_grad_norm is not None:                             # clip_grad_norm_ on the flat buffer, no host sync
             gn = self.reducer.flat.norm()
             self.reducer.flat.mul_(torch.clamp(self.max_grad_norm / (gn + 1e-6), max=1.0))
         self.optimizer.step()
+
+    def _body(self):
+        self._pre()
+        out5 = self._fwd_bwd()
+        self.reducer.allreduce()
+        self._clip_and_update()
         return out5
 
     def _capture(self, warmup_steps):
@@ -66,9 +86,20 @@ class GraphedKDStep:
                 self.out5 = self._body()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self._pre()
+        torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out5 = self._body()
+        if self.world == 1:
+            with torch.cuda.graph(self.graph):
+                self.out5 = self._fwd_bwd()
+                self._clip_and_update()
+        else:
+            with torch.cuda.graph(self.graph):
+                self.out5 = self._fwd_bwd()
+            self.reducer.allreduce()
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
+                self._clip_and_update()
 
     def load(self, batch: Dict[str, torch.Tensor], non_blocking: bool = True) -> int:
         """Copy one step's inputs (host or device tensors) into the static buffers; returns the bytes copied."""
@@ -83,8 +114,13 @@ class GraphedKDStep:
     def step(self) -> torch.Tensor:
         """Run one KD step on the current contents of the static buffers -> device tensor
         [total, ce, token_kd, feature_kd, hidden_kd] (no host sync)."""
-        if self.graph is not None:
+        if self.graph is None:
+            self.out5 = self._body()
+        elif self.world == 1:
             self.graph.replay()
         else:
-            self.out5 = self._body()
+            self._pre()
+            self.graph.replay()
+            self.reducer.allreduce()
+            self.graph_opt.replay()
         return self.out5

@@ -50,7 +50,8 @@ def test_gemm_bf16_tcgen05(a_mn, b_mn, out_dtype):
     """tcgen05/TMEM/TMA tile against fp64 matmul of the same bf16 operands: full tiles, ragged M/N/K, padded pitches."""
     ops = _ops()
     g = torch.Generator().manual_seed(2)
-    shapes = [(128, 128, 64), (512, 2048, 768), (200, 72, 40), (1000, 264, 520), (256, 512, 10240), (96, 5000, 256)]
+    shapes = [(128, 128, 64), (512, 2048, 768), (200, 72, 40), (1000, 264, 520), (256, 512, 10240), (96, 5000, 256),
+              (2048, 2048, 128), (4096, 2560, 192)]      # persistent: >1 tile per CTA (BN=128) and the BN=256 wide-output tile
     for (M_, N_, K_) in shapes:
         pad_a, pad_b = 8, 16                                  # pitches larger than the logical extent
         A = torch.randn((K_, M_ + pad_a) if a_mn else (M_, K_ + pad_a), generator=g).to(DEV).bfloat16()
@@ -68,7 +69,7 @@ def test_gemm_bf16_tcgen05(a_mn, b_mn, out_dtype):
     B = torch.randn((K_, N_) if b_mn else (N_, K_), generator=g).to(DEV).bfloat16()
     C0 = torch.randn(M_, N_, generator=g).to(DEV).to(out_dtype)
     C1 = ops.gemm(A, B, M_, N_, K_, a_mn, b_mn, beta=1.0, C=C0.clone())
-    tol = 3e-5 if out_dtype == torch.float32 else 6e-3
+    tol = 3e-5 if out_dtype == torch.float32 else 1e-2     # bf16 beta path: accumulator and sum are each rounded to bf16
     assert relerr(C1.cpu(), _ref_gemm(A, B, a_mn, b_mn, M_, N_, K_) + C0.cpu().double()) < tol
     C2 = ops.gemm(A, B, M_, N_, K_, a_mn, b_mn, out_dtype, relu=True)
     assert relerr(C2.cpu(), _ref_gemm(A, B, a_mn, b_mn, M_, N_, K_).clamp_min(0)) < tol

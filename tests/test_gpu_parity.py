@@ -125,11 +125,15 @@ def test_training_mode_dropout_is_consistent():
     y, _, _ = fwd(f)
     w = torch.randn_like(y)
     (y * w).sum().backward()
-    d = torch.randn_like(feats)
-    eps = 1e-2
-    num = (((fwd(feats + eps * d)[0] - fwd(feats - eps * d)[0]) * w).sum() / (2 * eps)).item()
-    ana = (f.grad * d).sum().item()
-    assert abs(num - ana) < 2e-2 * max(abs(ana), 1e-3), (num, ana)
+    # a backward that regenerated a DIFFERENT mask would be off by O(p) = 30 %; ReLU kinks and fp32 round-off limit the
+    # finite difference itself to a few per cent, so average three directions and allow 6 %
+    eps, errs = 5e-3, []
+    for i in range(3):
+        d = torch.randn(feats.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(100 + i))
+        num = (((fwd(feats + eps * d)[0].double() - fwd(feats - eps * d)[0].double()) * w.double()).sum() / (2 * eps)).item()
+        ana = (f.grad.double() * d.double()).sum().item()
+        errs.append(abs(num - ana) / max(abs(ana), 1e-3))
+    assert sum(errs) / len(errs) < 6e-2, errs
 
 
 def test_data_parallel_normaliser_matches_global_batch():
@@ -209,3 +213,17 @@ def test_graphed_step_equals_eager_step():
     (l0, w0), (l1, w1) = results
     assert relerr(l1[0], l0[0]) < 1e-5                       # first step: identical weights, identical loss parts
     assert float(l0[2, 0]) < float(l0[0, 0])                 # and the loss goes down over the three steps
+
+
+@pytest.mark.parametrize("B", [128, 256])
+def test_larger_batch_matches_oracle(B):
+    """Several M tiles per GEMM and several waves of attention CTAs (and, with B2C_SUB_BATCHES set, the forked sub-batch
+    streams): same results as the oracle on the whole batch."""
+    V, E, H, L, T = 120, 32, 64, 2, 4
+    params = O.init_student_params(V, E, H, L, True, seed=5)
+    pparams = O.init_projector_params(24, E, seed=6)
+    batch = O.synthetic_batch(B, T, V, E, H, Et=24, seed=8)
+    model, projector = build_student(params, pparams, V, E, H, L, True, 24, DEV)
+    got = run_kd_step(model, projector, batch, DEV, torch.float32)
+    ref = O.kd_step(params, pparams, batch)
+    compare_step(got, ref, FP32_TOL, verbose=False)

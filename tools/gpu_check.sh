@@ -1,0 +1,7 @@
+#!/bin/bash
+# tests + bench on one GPU; every group under its own timeout
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name"; timeout "$@" > gpurun_out/$name.log 2>&1; echo "exit $? ($name)"; tail -n 6 gpurun_out/$name.log | cut -c1-1800; }
+run t_kernels 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x
+run t_parity 900 python -m pytest tests/test_gpu_parity.py -m gpu -q
+run bench 400 python bench.py --steps 20 --warmup 5 ${BENCH_ARGS:---no-cpu-baseline}
