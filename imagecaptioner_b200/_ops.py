@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libb2c.so")
 
 B2C_MAX_LAYERS = 4
 B2C_F32, B2C_BF16 = 0, 1
-B2C_WS_TRAIN, B2C_WS_DECODE, B2C_WS_ATTN = 0, 1, 2
+B2C_WS_TRAIN, B2C_WS_DECODE, B2C_WS_ATTN, B2C_WS_REFINE, B2C_WS_PROJ = 0, 1, 2, 3, 4
 ABI_VERSION = 1
 
 c_f32p = ctypes.c_void_p
@@ -42,6 +42,26 @@ class B2CGrads(ctypes.Structure):
     _fields_ = _PARAM_FIELDS
 
 
+_REFINE_FIELDS = [(n, c_f32p) for n in ("in_w", "in_b", "out_w", "out_b", "ffn0_w", "ffn0_b", "ffn3_w", "ffn3_b", "n1_w", "n1_b", "n2_w", "n2_b")]
+_PROJ_FIELDS = [(n, c_f32p) for n in ("w", "b", "ln_w", "ln_b")]
+
+
+class B2CRefineParams(ctypes.Structure):
+    _fields_ = _REFINE_FIELDS
+
+
+class B2CRefineGrads(ctypes.Structure):
+    _fields_ = _REFINE_FIELDS
+
+
+class B2CProjParams(ctypes.Structure):
+    _fields_ = _PROJ_FIELDS
+
+
+class B2CProjGrads(ctypes.Structure):
+    _fields_ = _PROJ_FIELDS
+
+
 class B2CDropout(ctypes.Structure):
     _fields_ = [("p", ctypes.c_float), ("seed", ctypes.c_uint64)]
 
@@ -58,6 +78,10 @@ SYMBOLS = {
     "b2c_decoder_backward": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _GRD, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_greedy_decode": (ctypes.c_int, [_SHP, _PRM, _vp, _i64, _i64, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_attention_step": (ctypes.c_int, [_SHP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
+    "b2c_refinement_forward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CRefineParams), _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
+    "b2c_refinement_backward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CRefineParams), _vp, ctypes.POINTER(B2CRefineGrads), _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
+    "b2c_projector_forward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CProjParams), _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
+    "b2c_projector_backward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CProjParams), _vp, ctypes.POINTER(B2CProjGrads), _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_count_valid": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "b2c_kd_token_loss": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _f, _f, _f, _f, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
     "b2c_aux_loss": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _f, _f, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
@@ -337,6 +361,93 @@ class KDLossFunction(torch.autograd.Function):
             return None if t is None else (t if t.dtype == dt else t.to(dt))
 
         return cast(sv["dlogits"], dt_l), None, None, cast(sv["dfs"], dt_fs), cast(sv["dft"], dt_ft), cast(sv["dhs"], dt_hs), None, None
+
+
+REFINE_PARAM_ORDER = ["attention.in_proj_weight", "attention.in_proj_bias", "attention.out_proj.weight", "attention.out_proj.bias",
+                      "ffn.0.weight", "ffn.0.bias", "ffn.3.weight", "ffn.3.bias", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias"]
+PROJ_PARAM_ORDER = ["feature_projection.0.weight", "feature_projection.0.bias", "feature_projection.3.weight", "feature_projection.3.bias"]
+
+
+def _fill_flat(st, tensors):
+    for (name, _), t in zip(st._fields_, tensors):
+        setattr(st, name, t.data_ptr())
+    return st
+
+
+class RefinementFunction(torch.autograd.Function):
+    """AttentionRefinement.forward (reference src/student_model.py:72-118): QKV / out-proj / FFN contractions on the tcgen05
+    GEMM, the 49x49 4-head attention core, residual LayerNorms and every gradient in native kernels."""
+
+    @staticmethod
+    def forward(ctx, x, compute_dtype, dropout_p, seed, heads, *params):
+        lib = load_library()
+        _require_cuda(x, "features")
+        B, S, E = x.shape
+        shape = B2CShape(B, 1, S, E, heads, 1, 2)
+        code = dtype_code(compute_dtype)
+        xf = x.detach().to(torch.float32).contiguous()
+        master = _master(params)
+        ws = torch.empty(workspace_bytes(shape, code, B2C_WS_REFINE), dtype=torch.uint8, device=x.device)
+        out = torch.empty(B, S, E, dtype=compute_dtype, device=x.device)
+        prm = _fill_flat(B2CRefineParams(), master)
+        drop = B2CDropout(float(dropout_p), int(seed))
+        _check(lib.b2c_refinement_forward(ctypes.byref(shape), ctypes.byref(prm), xf.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          code, ctypes.byref(drop), _stream()), "b2c_refinement_forward")
+        ctx.b2c = (shape, code, drop, ws, master, x.dtype, [p.dtype for p in params], compute_dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = load_library()
+        shape, code, drop, ws, master, x_dtype, pdtypes, cdt = ctx.b2c
+        dout = dout.to(cdt).contiguous()
+        grads = [torch.empty_like(m) for m in master]
+        dx = torch.empty(shape.B, shape.S, shape.E, dtype=torch.float32, device=dout.device)
+        prm = _fill_flat(B2CRefineParams(), master)
+        grd = _fill_flat(B2CRefineGrads(), grads)
+        _check(lib.b2c_refinement_backward(ctypes.byref(shape), ctypes.byref(prm), dout.data_ptr(), ctypes.byref(grd), dx.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), code, ctypes.byref(drop), _stream()), "b2c_refinement_backward")
+        grads = [g if g.dtype == dt else g.to(dt) for g, dt in zip(grads, pdtypes)]
+        return (dx if x_dtype == torch.float32 else dx.to(x_dtype), None, None, None, None, *grads)
+
+
+class ProjectorFunction(torch.autograd.Function):
+    """FeatureProjector.forward (reference src/distillation_utils.py:233-252): Linear+ReLU(+dropout) on the tcgen05 GEMM, LayerNorm,
+    token pooling, and the parameter gradients, in native kernels.  `params` is empty for the identity channel projection."""
+
+    @staticmethod
+    def forward(ctx, x, compute_dtype, dropout_p, seed, out_tokens, student_dim, *params):
+        lib = load_library()
+        _require_cuda(x, "teacher features")
+        B, St, Et = x.shape
+        shape = B2CShape(B, out_tokens, St, Et, student_dim, 1, 2)
+        code = dtype_code(compute_dtype)
+        xf = x.detach().to(torch.float32).contiguous()
+        master = _master(params)
+        prm = _fill_flat(B2CProjParams(), master) if master else B2CProjParams()
+        nbytes = workspace_bytes(shape, code, B2C_WS_PROJ) if master else 256
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        out = torch.empty(B, out_tokens, student_dim, dtype=torch.float32, device=x.device)
+        drop = B2CDropout(float(dropout_p), int(seed))
+        _check(lib.b2c_projector_forward(ctypes.byref(shape), ctypes.byref(prm), xf.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         code, ctypes.byref(drop), _stream()), "b2c_projector_forward")
+        ctx.b2c = (shape, code, drop, ws, master, [p.dtype for p in params])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = load_library()
+        shape, code, drop, ws, master, pdtypes = ctx.b2c
+        if not master:
+            return (None,) * 6
+        dout = dout.to(torch.float32).contiguous()
+        grads = [torch.empty_like(m) for m in master]
+        prm = _fill_flat(B2CProjParams(), master)
+        grd = _fill_flat(B2CProjGrads(), grads)
+        _check(lib.b2c_projector_backward(ctypes.byref(shape), ctypes.byref(prm), dout.data_ptr(), ctypes.byref(grd), ws.data_ptr(), ws.numel(),
+                                          code, ctypes.byref(drop), _stream()), "b2c_projector_backward")
+        grads = [g if g.dtype == dt else g.to(dt) for g, dt in zip(grads, pdtypes)]
+        return (None, None, None, None, None, None, *grads)
 
 
 def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,

@@ -4,6 +4,7 @@
 #include "gemm.cuh"
 #include "loss_kernels.cuh"
 #include "decoder_kernels.cuh"
+#include "refine_kernels.cuh"
 
 using namespace b2c;
 
@@ -435,6 +436,228 @@ int attention_step_impl(const B2CShape& s, const float* attn_w, const float* att
   return attn_fwd<T>(st, s, W.P, feats, W.u, context, weights);
 }
 
+// ------------------------------------------------------------------ AttentionRefinement / FeatureProjector
+constexpr int LN_GRID = 148 * 2;
+template <typename T> struct RefineWs {
+  T *Win, *Wo, *W1, *W2;                                         // packed operand weights
+  T *x, *qkv, *probs, *attn, *proj, *x1, *f1, *f2;               // forward saves
+  float *mean1, *rstd1, *mean2, *rstd2;
+  T *dz2, *df1, *dz1, *dattn, *dqkv; float *dz1f, *lnpart, *partial;
+  size_t bytes;
+  void carve(void* base, const B2CShape& s) {
+    Carver c{reinterpret_cast<unsigned char*>(base), 0};
+    const size_t R = (size_t)s.B * s.S, E = s.E, heads = s.H;
+    Win = c.take<T>(3 * E * E); Wo = c.take<T>(E * E); W1 = c.take<T>(2 * E * E); W2 = c.take<T>(2 * E * E);
+    x = c.take<T>(R * E); qkv = c.take<T>(R * 3 * E); probs = c.take<T>((size_t)s.B * heads * s.S * s.S); attn = c.take<T>(R * E);
+    proj = c.take<T>(R * E); x1 = c.take<T>(R * E); f1 = c.take<T>(R * 2 * E); f2 = c.take<T>(R * E);
+    mean1 = c.take<float>(R); rstd1 = c.take<float>(R); mean2 = c.take<float>(R); rstd2 = c.take<float>(R);
+    dz2 = c.take<T>(R * E); df1 = c.take<T>(R * 2 * E); dz1 = c.take<T>(R * E); dattn = c.take<T>(R * E); dqkv = c.take<T>(R * 3 * E);
+    dz1f = c.take<float>(R * E); lnpart = c.take<float>((size_t)LN_GRID * 3 * E); partial = c.take<float>((size_t)COLSUM_RS * 3 * E);
+    bytes = align_up(c.off, 256);
+  }
+};
+
+int check_refine_shape(const B2CShape* s) {
+  B2C_CHECK_ARG(s != nullptr, "shape is NULL");
+  B2C_CHECK_ARG(s->B > 0 && s->S > 0 && s->E > 0 && s->H > 0, "bad refinement shape B=%d S=%d E=%d heads=%d", s->B, s->S, s->E, s->H);
+  B2C_CHECK_ARG(s->E % 8 == 0 && s->E <= 256 * LN_MAXC && s->E % s->H == 0, "E=%d must be a multiple of 8 and of heads=%d, and <= %d", s->E, s->H, 256 * LN_MAXC);
+  const size_t hd = s->E / s->H;
+  B2C_CHECK_ARG(hd % 4 == 0, "head_dim=%zu must be a multiple of 4", hd);
+  B2C_CHECK_ARG((4 * (size_t)s->S * mha_pitch((int)hd) + 3 * (size_t)s->S * mha_pitch(s->S)) * 4 <= 200 * 1024, "S=%d x head_dim=%zu does not fit the attention core's shared memory", s->S, hd);
+  return 0;
+}
+
+template <typename TX, typename TY>
+int ln_fwd(cudaStream_t st, const TX* x, const TX* res, const float* g, const float* b, TY* y, float* mean, float* rstd, long R, int E) {
+  long grid = (R + 7) / 8; if (grid > 148 * 8) grid = 148 * 8;
+  ln_fwd_kernel<TX, TY><<<(unsigned)grid, LN_THREADS, 0, st>>>(x, res, g, b, y, mean, rstd, R, E, 1e-5f);
+  B2C_LAUNCH_CHECK("ln_fwd_kernel");
+  return 0;
+}
+// LayerNorm backward; dy is a tensor (dpool == nullptr) or pooled window gradients (projector).  dbias_prev (optional) receives
+// the column sums of dz = the bias gradient of the Linear whose output entered the LayerNorm.
+template <typename TX, typename TDY, typename TDZ>
+int ln_bwd(cudaStream_t st, const TDY* dy, const float* dpool, int L, int O, const TX* x, const TX* res, const float* mean, const float* rstd,
+           const float* gamma, TDZ* dz, float* dz32, float* part, float* dgamma, float* dbeta, float* dbias_prev, long R, int E) {
+  long grid = (R + 7) / 8; if (grid > LN_GRID) grid = LN_GRID;
+  const size_t smem = (size_t)(LN_THREADS / 32) * 3 * E * 4;
+  if (dpool) {
+    B2C_TRY(set_smem(ln_bwd_kernel<TX, TDY, TDZ, true>, smem));
+    ln_bwd_kernel<TX, TDY, TDZ, true><<<(unsigned)grid, LN_THREADS, smem, st>>>(dy, dpool, L, O, x, res, mean, rstd, gamma, dz, dz32, part, R, E);
+  } else {
+    B2C_TRY(set_smem(ln_bwd_kernel<TX, TDY, TDZ, false>, smem));
+    ln_bwd_kernel<TX, TDY, TDZ, false><<<(unsigned)grid, LN_THREADS, smem, st>>>(dy, dpool, L, O, x, res, mean, rstd, gamma, dz, dz32, part, R, E);
+  }
+  B2C_LAUNCH_CHECK("ln_bwd_kernel");
+  ln_param_grad_kernel<<<cdiv(3 * E, 256), 256, 0, st>>>(part, (int)grid, E, dgamma, dbeta, dbias_prev);
+  B2C_LAUNCH_CHECK("ln_param_grad_kernel");
+  return 0;
+}
+
+// column sums of a contiguous (rows, cols) matrix, cols % 8 == 0, optionally fused with the in-place ReLU backward
+template <typename T>
+int colsum_vec(cudaStream_t st, T* A, const T* act, long rows, int cols, float inv_keep, float* partial, float* out) {
+  int rs = (int)((rows + 511) / 512); if (rs > COLSUM_RS) rs = COLSUM_RS; if (rs < 1) rs = 1;
+  dim3 grid(cdiv(cols, 256), rs);
+  if (act) colsum_vec_kernel<T, true><<<grid, 256, 0, st>>>(A, act, rows, cols, inv_keep, partial);
+  else colsum_vec_kernel<T, false><<<grid, 256, 0, st>>>(A, act, rows, cols, inv_keep, partial);
+  B2C_LAUNCH_CHECK("colsum_vec_kernel");
+  colsum_final_kernel<<<cdiv(cols, 256), 256, 0, st>>>(partial, rs, cols, out, nullptr);
+  B2C_LAUNCH_CHECK("colsum_final_kernel");
+  return 0;
+}
+
+template <typename T>
+int refine_pack(const B2CShape& s, const B2CRefineParams& p, const RefineWs<T>& W, cudaStream_t st) {
+  B2C_CHECK_ARG(p.in_w && p.in_b && p.out_w && p.out_b && p.ffn0_w && p.ffn0_b && p.ffn3_w && p.ffn3_b && p.n1_w && p.n1_b && p.n2_w && p.n2_b, "NULL refinement parameter");
+  const int E = s.E;
+  PackTable tab; tab.n = 4;
+  tab.seg[0] = PackSeg{p.in_w, W.Win, nullptr, 3 * E, E, (long)E, (long)E, 0};
+  tab.seg[1] = PackSeg{p.out_w, W.Wo, nullptr, E, E, (long)E, (long)E, 0};
+  tab.seg[2] = PackSeg{p.ffn0_w, W.W1, nullptr, 2 * E, E, (long)E, (long)E, 0};
+  tab.seg[3] = PackSeg{p.ffn3_w, W.W2, nullptr, E, 2 * E, (long)2 * E, (long)2 * E, 0};
+  pack_params_kernel<T><<<dim3(48, 4), 256, 0, st>>>(tab);
+  B2C_LAUNCH_CHECK("pack_params_kernel");
+  return 0;
+}
+
+template <typename T>
+int refinement_forward_impl(const B2CShape& s, const B2CRefineParams& p, const float* x, T* out, void* ws, size_t ws_bytes,
+                            const B2CDropout& dr, cudaStream_t st) {
+  RefineWs<T> W; W.carve(ws, s);
+  B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
+  const int B = s.B, S = s.S, E = s.E, heads = s.H, hd = E / heads;
+  const long R = (long)B * S;
+  B2C_TRY(refine_pack<T>(s, p, W, st));
+  cast_f32_kernel<T><<<ew_grid(R * E / 4), 256, 0, st>>>(x, W.x, R * E);
+  B2C_LAUNCH_CHECK("cast_f32_kernel");
+  B2C_TRY((gemm<T, T>(st, (int)R, 3 * E, E, W.x, E, 0, W.Win, E, 0, W.qkv, 3 * E, 0.f, p.in_b)));
+  {
+    const size_t smem = ((size_t)3 * S * mha_pitch(hd) + (size_t)S * mha_pitch(S)) * 4;
+    B2C_TRY(set_smem(mha_fwd_kernel<T>, smem));
+    mha_fwd_kernel<T><<<dim3(B, heads), MHA_THREADS, smem, st>>>(W.qkv, W.attn, W.probs, S, E, heads, 1.0f / sqrtf((float)hd), dr.p, dr.seed);
+    B2C_LAUNCH_CHECK("mha_fwd_kernel");
+  }
+  B2C_TRY((gemm<T, T>(st, (int)R, E, E, W.attn, E, 0, W.Wo, E, 0, W.proj, E, 0.f, p.out_b)));
+  B2C_TRY((ln_fwd<T, T>(st, W.x, W.proj, p.n1_w, p.n1_b, W.x1, W.mean1, W.rstd1, R, E)));
+  B2C_TRY((gemm<T, T>(st, (int)R, 2 * E, E, W.x1, E, 0, W.W1, E, 0, W.f1, 2 * E, 0.f, p.ffn0_b, 1)));
+  if (dr.p > 0.f) {
+    dropout_inplace_kernel<T><<<ew_grid(R * 2 * E), 256, 0, st>>>(W.f1, R * 2 * E, dr.p, dr.seed, 201u);
+    B2C_LAUNCH_CHECK("dropout_inplace_kernel");
+  }
+  B2C_TRY((gemm<T, T>(st, (int)R, E, 2 * E, W.f1, 2 * E, 0, W.W2, 2 * E, 0, W.f2, E, 0.f, p.ffn3_b)));
+  B2C_TRY((ln_fwd<T, T>(st, W.x1, W.f2, p.n2_w, p.n2_b, out, W.mean2, W.rstd2, R, E)));
+  return 0;
+}
+
+template <typename T>
+int refinement_backward_impl(const B2CShape& s, const B2CRefineParams& p, const T* dout, const B2CRefineGrads& g, float* dx,
+                             void* ws, size_t ws_bytes, const B2CDropout& dr, cudaStream_t st) {
+  RefineWs<T> W; W.carve(ws, s);
+  B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
+  B2C_CHECK_ARG(g.in_w && g.in_b && g.out_w && g.out_b && g.ffn0_w && g.ffn0_b && g.ffn3_w && g.ffn3_b && g.n1_w && g.n1_b && g.n2_w && g.n2_b && dx, "NULL refinement gradient");
+  const int B = s.B, S = s.S, E = s.E, heads = s.H, hd = E / heads;
+  const long R = (long)B * S;
+  const float inv_keep = dr.p > 0.f ? 1.0f / (1.0f - dr.p) : 1.0f;
+  // out = LN2(x1 + f2);  f2 = f1 W2^T + b2  (its bias gradient = column sums of dz2, produced by the same kernel)
+  B2C_TRY((ln_bwd<T, T, T>(st, dout, nullptr, 0, 0, W.x1, W.f2, W.mean2, W.rstd2, p.n2_w, W.dz2, nullptr, W.lnpart, g.n2_w, g.n2_b, g.ffn3_b, R, E)));
+  B2C_TRY((gemm<T, float>(st, E, 2 * E, (int)R, W.dz2, E, 1, W.f1, 2 * E, 1, g.ffn3_w, 2 * E)));
+  B2C_TRY((gemm<T, T>(st, (int)R, 2 * E, E, W.dz2, E, 0, W.W2, 2 * E, 1, W.df1, 2 * E)));
+  // f1 = Drop(ReLU(x1 W1^T + b1)): mask in place + bias gradient in one pass
+  B2C_TRY(colsum_vec<T>(st, W.df1, W.f1, R, 2 * E, inv_keep, W.partial, g.ffn0_b));
+  B2C_TRY((gemm<T, float>(st, 2 * E, E, (int)R, W.df1, 2 * E, 1, W.x1, E, 1, g.ffn0_w, E)));
+  B2C_TRY((gemm<T, T>(st, (int)R, E, 2 * E, W.df1, 2 * E, 0, W.W1, E, 1, W.dz2, E, 1.f)));          // dz2 <- d(x1) = dz2 + df1 W1
+  // x1 = LN1(x + proj);  proj = attn Wo^T + bo
+  B2C_TRY((ln_bwd<T, T, T>(st, W.dz2, nullptr, 0, 0, W.x, W.proj, W.mean1, W.rstd1, p.n1_w, W.dz1, W.dz1f, W.lnpart, g.n1_w, g.n1_b, g.out_b, R, E)));
+  B2C_TRY((gemm<T, float>(st, E, E, (int)R, W.dz1, E, 1, W.attn, E, 1, g.out_w, E)));
+  B2C_TRY((gemm<T, T>(st, (int)R, E, E, W.dz1, E, 0, W.Wo, E, 1, W.dattn, E)));
+  {
+    const size_t smem = ((size_t)4 * S * mha_pitch(hd) + (size_t)3 * S * mha_pitch(S)) * 4;
+    B2C_TRY(set_smem(mha_bwd_kernel<T>, smem));
+    mha_bwd_kernel<T><<<dim3(B, heads), MHA_THREADS, smem, st>>>(W.qkv, W.probs, W.dattn, W.dqkv, S, E, heads, 1.0f / sqrtf((float)hd), dr.p, dr.seed);
+    B2C_LAUNCH_CHECK("mha_bwd_kernel");
+  }
+  // qkv = x Win^T + b
+  B2C_TRY((gemm<T, float>(st, 3 * E, E, (int)R, W.dqkv, 3 * E, 1, W.x, E, 1, g.in_w, E)));
+  B2C_TRY(colsum_vec<T>(st, W.dqkv, (const T*)nullptr, R, 3 * E, 1.f, W.partial, g.in_b));
+  B2C_CUDA(cudaMemcpyAsync(dx, W.dz1f, (size_t)R * E * sizeof(float), cudaMemcpyDeviceToDevice, st));   // residual path
+  B2C_TRY((gemm<T, float>(st, (int)R, E, 3 * E, W.dqkv, 3 * E, 0, W.Win, E, 1, dx, E, 1.f)));        // dx += dqkv Win
+  return 0;
+}
+
+template <typename T> struct ProjWs {
+  T *Wp, *xb, *h, *dh; float *mean, *rstd, *lnpart, *partial;
+  size_t bytes;
+  void carve(void* base, const B2CShape& s, bool identity) {
+    Carver c{reinterpret_cast<unsigned char*>(base), 0};
+    const size_t R = (size_t)s.B * s.S, Et = s.E, Es = s.H;
+    if (!identity) {
+      Wp = c.take<T>(Es * Et); xb = c.take<T>(R * Et); h = c.take<T>(R * Es);
+      dh = c.take<T>(R * Es); mean = c.take<float>(R); rstd = c.take<float>(R);
+      lnpart = c.take<float>((size_t)LN_GRID * 3 * Es); partial = c.take<float>((size_t)COLSUM_RS * Es);
+    }
+    bytes = align_up(c.off + 256, 256);
+  }
+};
+int check_proj_shape(const B2CShape* s) {
+  B2C_CHECK_ARG(s != nullptr, "shape is NULL");
+  B2C_CHECK_ARG(s->B > 0 && s->S > 0 && s->E > 0 && s->H > 0 && s->T > 0 && s->T <= s->S, "bad projector shape B=%d St=%d Et=%d Es=%d So=%d", s->B, s->S, s->E, s->H, s->T);
+  B2C_CHECK_ARG(s->E % 8 == 0 && s->H % 8 == 0 && s->H <= 256 * LN_MAXC, "Et=%d / Es=%d must be multiples of 8 and Es <= %d", s->E, s->H, 256 * LN_MAXC);
+  return 0;
+}
+
+template <typename T>
+int projector_forward_impl(const B2CShape& s, const B2CProjParams& p, const float* x, float* out, void* ws, size_t ws_bytes,
+                           const B2CDropout& dr, cudaStream_t st) {
+  const bool identity = (p.w == nullptr);
+  const int B = s.B, St = s.S, Et = s.E, Es = s.H, So = s.T;
+  const long R = (long)B * St;
+  if (identity) {
+    B2C_CHECK_ARG(Et == Es && !p.b && !p.ln_w && !p.ln_b, "identity projection needs Et == Es and no parameters");
+    pool_fwd_kernel<float><<<ew_grid((long)B * So * Es), 256, 0, st>>>(x, out, B, St, So, Es);
+    B2C_LAUNCH_CHECK("pool_fwd_kernel");
+    return 0;
+  }
+  B2C_CHECK_ARG(p.b && p.ln_w && p.ln_b, "NULL projector parameter");
+  ProjWs<T> W; W.carve(ws, s, false);
+  B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
+  PackTable tab; tab.n = 1;
+  tab.seg[0] = PackSeg{p.w, W.Wp, nullptr, Es, Et, (long)Et, (long)Et, 0};
+  pack_params_kernel<T><<<dim3(48, 1), 256, 0, st>>>(tab);
+  B2C_LAUNCH_CHECK("pack_params_kernel");
+  cast_f32_kernel<T><<<ew_grid(R * Et / 4), 256, 0, st>>>(x, W.xb, R * Et);
+  B2C_LAUNCH_CHECK("cast_f32_kernel");
+  B2C_TRY((gemm<T, T>(st, (int)R, Es, Et, W.xb, Et, 0, W.Wp, Et, 0, W.h, Es, 0.f, p.b, 1)));
+  if (dr.p > 0.f) {
+    dropout_inplace_kernel<T><<<ew_grid(R * Es), 256, 0, st>>>(W.h, R * Es, dr.p, dr.seed, 210u);
+    B2C_LAUNCH_CHECK("dropout_inplace_kernel");
+  }
+  {
+    long grid = ((long)B * So + 7) / 8; if (grid > 148 * 8) grid = 148 * 8;
+    ln_pool_fwd_kernel<T><<<(unsigned)grid, LN_THREADS, 0, st>>>(W.h, p.ln_w, p.ln_b, out, W.mean, W.rstd, B, St, So, Es, 1e-5f);
+    B2C_LAUNCH_CHECK("ln_pool_fwd_kernel");
+  }
+  return 0;
+}
+
+template <typename T>
+int projector_backward_impl(const B2CShape& s, const B2CProjParams& p, const float* dout, const B2CProjGrads& g, void* ws,
+                            size_t ws_bytes, const B2CDropout& dr, cudaStream_t st) {
+  if (p.w == nullptr) return 0;                     // identity projection: no parameters, teacher features carry no gradient
+  B2C_CHECK_ARG(g.w && g.b && g.ln_w && g.ln_b, "NULL projector gradient");
+  ProjWs<T> W; W.carve(ws, s, false);
+  B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
+  const int B = s.B, St = s.S, Et = s.E, Es = s.H, So = s.T;
+  const long R = (long)B * St;
+  const float inv_keep = dr.p > 0.f ? 1.0f / (1.0f - dr.p) : 1.0f;
+  // un-pool + LayerNorm backward in one pass (dy is rebuilt from the pooled gradient), then ReLU mask + bias gradient in one pass
+  B2C_TRY((ln_bwd<T, T, T>(st, (const T*)nullptr, dout, St, So, W.h, (const T*)nullptr, W.mean, W.rstd, p.ln_w, W.dh, nullptr, W.lnpart,
+                           g.ln_w, g.ln_b, nullptr, R, Es)));
+  B2C_TRY(colsum_vec<T>(st, W.dh, W.h, R, Es, inv_keep, W.partial, g.b));
+  B2C_TRY((gemm<T, float>(st, Es, Et, (int)R, W.dh, Es, 1, W.xb, Et, 1, g.w, Et)));
+  return 0;
+}
+
 template <typename TS>
 int kd_token_loss_impl(const TS* y, const float* z, const int64_t* tgt, long N, int V, float temperature, float alpha,
                        float w_ce_eff, const int* n_valid, TS* dy, float* row_kl, float* row_ce, cudaStream_t st) {
@@ -504,13 +727,21 @@ const char* b2c_last_error(void) { return err_buf(); }
 uint64_t b2c_launch_count(void) { return (uint64_t)launch_counter(); }
 
 size_t b2c_workspace_bytes(const B2CShape* shape, int dtype, int mode) {
-  if (check_shape(shape) != 0) return 0;
+  if (mode != B2C_WS_REFINE && mode != B2C_WS_PROJ && check_shape(shape) != 0) return 0;
   if (mode == B2C_WS_TRAIN) {
     if (dtype == B2C_F32) { TrainWs<float> w; w.carve(nullptr, *shape); return w.bytes; }
     if (dtype == B2C_BF16) { TrainWs<bf16> w; w.carve(nullptr, *shape); return w.bytes; }
   } else if (mode == B2C_WS_DECODE) {
     if (dtype == B2C_F32) { DecodeWs<float> w; w.carve(nullptr, *shape); return w.bytes; }
     if (dtype == B2C_BF16) { DecodeWs<bf16> w; w.carve(nullptr, *shape); return w.bytes; }
+  } else if (mode == B2C_WS_REFINE) {
+    if (check_refine_shape(shape) != 0) return 0;
+    if (dtype == B2C_F32) { RefineWs<float> w; w.carve(nullptr, *shape); return w.bytes; }
+    if (dtype == B2C_BF16) { RefineWs<bf16> w; w.carve(nullptr, *shape); return w.bytes; }
+  } else if (mode == B2C_WS_PROJ) {
+    if (check_proj_shape(shape) != 0) return 0;
+    if (dtype == B2C_F32) { ProjWs<float> w; w.carve(nullptr, *shape, false); return w.bytes; }
+    if (dtype == B2C_BF16) { ProjWs<bf16> w; w.carve(nullptr, *shape, false); return w.bytes; }
   } else if (mode == B2C_WS_ATTN) {
     if (dtype == B2C_F32) { AttnWs<float> w; w.carve(nullptr, *shape); return w.bytes; }
     if (dtype == B2C_BF16) { AttnWs<bf16> w; w.carve(nullptr, *shape); return w.bytes; }
@@ -562,6 +793,52 @@ int b2c_attention_step(const B2CShape* shape, const float* attn_w, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2C_F32) return attention_step_impl<float>(*shape, attn_w, attn_b, (const float*)hidden, (const float*)feats, (float*)context, weights, workspace, ws_bytes, st);
   if (dtype == B2C_BF16) return attention_step_impl<bf16>(*shape, attn_w, attn_b, (const bf16*)hidden, (const bf16*)feats, (bf16*)context, weights, workspace, ws_bytes, st);
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_refinement_forward(const B2CShape* shape, const B2CRefineParams* params, const float* x, void* out,
+                           void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream) {
+  B2C_TRY(check_refine_shape(shape)); B2C_TRY(check_device());
+  B2C_CHECK_ARG(params && x && out && workspace, "NULL argument");
+  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0};
+  B2C_CHECK_ARG(dr.p >= 0.f && dr.p < 1.f, "dropout p=%f outside [0,1)", dr.p);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) return refinement_forward_impl<float>(*shape, *params, x, (float*)out, workspace, ws_bytes, dr, st);
+  if (dtype == B2C_BF16) return refinement_forward_impl<bf16>(*shape, *params, x, (bf16*)out, workspace, ws_bytes, dr, st);
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_refinement_backward(const B2CShape* shape, const B2CRefineParams* params, const void* dout, const B2CRefineGrads* grads,
+                            float* dx, void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream) {
+  B2C_TRY(check_refine_shape(shape)); B2C_TRY(check_device());
+  B2C_CHECK_ARG(params && dout && grads && dx && workspace, "NULL argument");
+  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) return refinement_backward_impl<float>(*shape, *params, (const float*)dout, *grads, dx, workspace, ws_bytes, dr, st);
+  if (dtype == B2C_BF16) return refinement_backward_impl<bf16>(*shape, *params, (const bf16*)dout, *grads, dx, workspace, ws_bytes, dr, st);
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_projector_forward(const B2CShape* shape, const B2CProjParams* params, const float* x, float* out,
+                          void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream) {
+  B2C_TRY(check_proj_shape(shape)); B2C_TRY(check_device());
+  B2C_CHECK_ARG(params && x && out && workspace, "NULL argument");
+  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0};
+  B2C_CHECK_ARG(dr.p >= 0.f && dr.p < 1.f, "dropout p=%f outside [0,1)", dr.p);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) return projector_forward_impl<float>(*shape, *params, x, out, workspace, ws_bytes, dr, st);
+  if (dtype == B2C_BF16) return projector_forward_impl<bf16>(*shape, *params, x, out, workspace, ws_bytes, dr, st);
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_projector_backward(const B2CShape* shape, const B2CProjParams* params, const float* dout, const B2CProjGrads* grads,
+                           void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream) {
+  B2C_TRY(check_proj_shape(shape)); B2C_TRY(check_device());
+  B2C_CHECK_ARG(params && dout && grads && workspace, "NULL argument");
+  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) return projector_backward_impl<float>(*shape, *params, dout, *grads, workspace, ws_bytes, dr, st);
+  if (dtype == B2C_BF16) return projector_backward_impl<bf16>(*shape, *params, dout, *grads, workspace, ws_bytes, dr, st);
   return set_err(B2C_EINVAL, "bad dtype %d", dtype);
 }
 

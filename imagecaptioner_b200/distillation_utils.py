@@ -134,10 +134,16 @@ class FeatureProjector(nn.Module):
         self.seq_projection = nn.AdaptiveAvgPool1d(student_seq_len) if teacher_seq_len != student_seq_len else nn.Identity()
 
     def forward(self, features):
-        out = self.feature_projection(features)
-        if self.teacher_seq_len != self.student_seq_len:
-            out = self.seq_projection(out.transpose(1, 2)).transpose(1, 2)
-        return out
+        """(B, teacher_seq_len, teacher_dim) -> (B, student_seq_len, student_dim) fp32, through b2c_projector_forward /
+        _backward (parameters stay in the reference's stock submodules).  Gradients flow to the parameters; the teacher
+        features are treated as data (the reference's TeacherWrapper produces them under no_grad)."""
+        p = 0.1 if (self.training and self.teacher_dim != self.student_dim) else 0.0
+        self._step = getattr(self, "_step", 0) + 1
+        seed = (torch.initial_seed() + 0xA24BAED4963EE407 * self._step) & 0xFFFFFFFFFFFFFFFF if p > 0 else 0
+        dt = torch.bfloat16 if torch.is_autocast_enabled() else getattr(self, "compute_dtype", torch.float32)
+        named = dict(self.named_parameters())
+        params = [named[k] for k in _ops.PROJ_PARAM_ORDER] if self.teacher_dim != self.student_dim else []
+        return _ops.ProjectorFunction.apply(features, dt, p, seed, self.student_seq_len, self.student_dim, *params)
 
 
 class TeacherWrapper(nn.Module):

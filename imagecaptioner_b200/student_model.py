@@ -82,9 +82,14 @@ class AttentionRefinement(nn.Module):
         self.norm2 = nn.LayerNorm(embed_size)
 
     def forward(self, features):
-        mixed, _ = self.attention(features, features, features)
-        features = self.norm1(features + mixed)
-        return self.norm2(features + self.ffn(features))
+        """(B,S,E) -> (B,S,E).  The parameters live in the reference's stock submodules (state_dict compatible); the
+        computation is one C-ABI call each way (b2c_refinement_forward / _backward).  bf16 under autocast, fp32 otherwise."""
+        p = 0.1 if self.training else 0.0            # the reference's attention / FFN dropout
+        self._step = getattr(self, "_step", 0) + 1
+        seed = (torch.initial_seed() + 0xD1B54A32D192ED03 * self._step) & 0xFFFFFFFFFFFFFFFF if p > 0 else 0
+        dt = torch.bfloat16 if torch.is_autocast_enabled() else getattr(self, "compute_dtype", torch.float32)
+        named = dict(self.named_parameters())
+        return _ops.RefinementFunction.apply(features, dt, p, seed, self.num_heads, *[named[k] for k in _ops.REFINE_PARAM_ORDER])
 
 
 class HiddenStateList(list):

@@ -8,6 +8,8 @@
  *   b2c_decoder_backward  <- autograd of the above (loss.backward(), src/train_student_kd.py:288)
  *   b2c_greedy_decode     <- CaptioningStudent.caption_image loop   src/student_model.py:339-381 (batched)
  *   b2c_attention_step    <- LSTMDecoder.attention_mechanism          src/student_model.py:173-203 (stand-alone accessor)
+ *   b2c_refinement_forward/backward <- AttentionRefinement.forward (+ autograd)   src/student_model.py:72-118
+ *   b2c_projector_forward/backward  <- FeatureProjector.forward (+ autograd)      src/distillation_utils.py:203-252
  *   b2c_count_valid       <- CrossEntropyLoss(ignore_index=0) normaliser  src/distillation_utils.py:22
  *   b2c_kd_token_loss     <- token_level_distillation :30-54 + CE term :154 (+ their gradient)
  *   b2c_aux_loss          <- encoder_feature_distillation :56-94 + decoder_hidden_state_distillation :96-136
@@ -40,7 +42,7 @@ extern "C" {
 
 enum { B2C_OK = 0, B2C_EINVAL = -1, B2C_EARCH = -2, B2C_ECUDA = -3, B2C_ENOMEM = -4 };
 enum { B2C_F32 = 0, B2C_BF16 = 1 };
-enum { B2C_WS_TRAIN = 0, B2C_WS_DECODE = 1, B2C_WS_ATTN = 2 };
+enum { B2C_WS_TRAIN = 0, B2C_WS_DECODE = 1, B2C_WS_ATTN = 2, B2C_WS_REFINE = 3, B2C_WS_PROJ = 4 };
 
 /* B batch (per GPU), T decode steps, S image tokens (49), E embed, H hidden, L LSTM layers, V vocab. */
 typedef struct B2CShape { int32_t B, T, S, E, H, L, V; } B2CShape;
@@ -109,6 +111,34 @@ int b2c_greedy_decode(const B2CShape* shape, const B2CParams* params, const void
  * Only shape->{B,S,E,H} are read; workspace size from b2c_workspace_bytes(shape, dtype, B2C_WS_ATTN). */
 int b2c_attention_step(const B2CShape* shape, const float* attn_w, const float* attn_b, const void* hidden, const void* feats,
                        void* context, float* weights, void* workspace, size_t ws_bytes, int dtype, void* stream);
+
+/* ---- AttentionRefinement: x1 = LN1(x + MHA(x)), out = LN2(x1 + FFN(x1)); nn.MultiheadAttention(batch_first) packing:
+ * in_w (3E,E) / in_b (3E) = in_proj_{weight,bias}, out_w (E,E) / out_b = out_proj; ffn0 (2E,E), ffn3 (E,2E); n1 / n2 = LayerNorm
+ * weight, bias.  Workspace: b2c_workspace_bytes with shape {B, S, E, H = heads}, mode B2C_WS_REFINE. */
+typedef struct B2CRefineParams {
+  const float *in_w, *in_b, *out_w, *out_b, *ffn0_w, *ffn0_b, *ffn3_w, *ffn3_b, *n1_w, *n1_b, *n2_w, *n2_b;
+} B2CRefineParams;
+typedef struct B2CRefineGrads {
+  float *in_w, *in_b, *out_w, *out_b, *ffn0_w, *ffn0_b, *ffn3_w, *ffn3_b, *n1_w, *n1_b, *n2_w, *n2_b;
+} B2CRefineGrads;
+/* x (B,S,E) fp32 -> out (B,S,E) [dtype].  dropout->p is the reference's 0.1 in training (attention probabilities and FFN), 0 in eval. */
+int b2c_refinement_forward(const B2CShape* shape, const B2CRefineParams* params, const float* x, void* out,
+                           void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream);
+/* dout (B,S,E) [dtype] -> grads (fp32, overwritten), dx (B,S,E) fp32. */
+int b2c_refinement_backward(const B2CShape* shape, const B2CRefineParams* params, const void* dout, const B2CRefineGrads* grads,
+                            float* dx, void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream);
+
+/* ---- FeatureProjector: LN(Drop(ReLU(x W^T + b))) on the channel axis, then AdaptiveAvgPool1d over tokens St -> So.
+ * w (Es,Et), b (Es), ln_w / ln_b (Es); all four NULL = identity channel projection (Et == Es): pooling only.
+ * Workspace: shape {B, S = St, E = Et, H = Es, T = So}, mode B2C_WS_PROJ. */
+typedef struct B2CProjParams { const float *w, *b, *ln_w, *ln_b; } B2CProjParams;
+typedef struct B2CProjGrads { float *w, *b, *ln_w, *ln_b; } B2CProjGrads;
+/* x (B,St,Et) fp32 (teacher features, no gradient) -> out (B,So,Es) fp32 */
+int b2c_projector_forward(const B2CShape* shape, const B2CProjParams* params, const float* x, float* out,
+                          void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream);
+/* dout (B,So,Es) fp32 -> grads (fp32, overwritten) */
+int b2c_projector_backward(const B2CShape* shape, const B2CProjParams* params, const float* dout, const B2CProjGrads* grads,
+                           void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream);
 
 /* n_valid_out[0] = #{ i < n : 0 < targets[i] < V }   (int32 on the device). */
 int b2c_count_valid(const int64_t* targets, int64_t n, int32_t V, int32_t* n_valid_out, void* stream);

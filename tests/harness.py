@@ -28,7 +28,10 @@ def run_kd_step(model, projector, batch, device, dtype=torch.float32, alpha=0.7,
     from imagecaptioner_b200.distillation_utils import DistillationLoss
     model.zero_grad(set_to_none=True)
     projector.zero_grad(set_to_none=True)
-    model.decoder.compute_dtype = dtype
+    model.decoder.compute_dtype = dtype                     # the whole native path runs in this precision mode
+    if getattr(model, "use_attention_refinement", False):
+        model.attention_refinement.compute_dtype = dtype
+    projector.compute_dtype = dtype
     feats = batch["encoder_features"].to(device).clone().requires_grad_(True)
     cap = batch["captions_input"].to(device)
     tgt = batch["targets"].to(device)

@@ -133,7 +133,8 @@ def test_host_side_helpers():
         itos = {i: f"w{i}" for i in range(20)}
     assert compute_bleu_score([1, 5, 6, 7, 2, 0], [1, 5, 6, 9, 2], V) == pytest.approx(2 / 3)
     assert compute_bleu_score([5], [0, 1, 2], V) == 0.0
-    fp = FeatureProjector(384, 256, 197, 64).eval()              # test_dimension_fix.py:16-43
-    assert tuple(fp(torch.randn(2, 197, 384)).shape) == (2, 64, 256)
+    fp = FeatureProjector(384, 256, 197, 64).eval()              # test_dimension_fix.py:16-43 (values: GPU test; shape pin: oracle test)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fp(torch.randn(2, 197, 384))
     ident = FeatureProjector(384, 384, 197, 49)
     assert sum(p.numel() for p in ident.parameters()) == 0
