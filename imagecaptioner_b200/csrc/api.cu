@@ -11,7 +11,7 @@ using namespace b2c;
 namespace {
 
 constexpr int MAXL = B2C_MAX_LAYERS;
-constexpr int COLSUM_RS = 32;
+constexpr int COLSUM_RS = 160;
 
 // ------------------------------------------------------------------ device check (sm_100 only, no fallback)
 int check_device() {
@@ -497,8 +497,9 @@ int ln_bwd(cudaStream_t st, const TDY* dy, const float* dpool, int L, int O, con
 // column sums of a contiguous (rows, cols) matrix, cols % 8 == 0, optionally fused with the in-place ReLU backward
 template <typename T>
 int colsum_vec(cudaStream_t st, T* A, const T* act, long rows, int cols, float inv_keep, float* partial, float* out) {
-  int rs = (int)((rows + 511) / 512); if (rs > COLSUM_RS) rs = COLSUM_RS; if (rs < 1) rs = 1;
-  dim3 grid(cdiv(cols, 256), rs);
+  const int gx = cdiv(cols, 256);
+  int rs = (int)((rows + 63) / 64); if (rs > 296 / gx) rs = 296 / gx; if (rs > COLSUM_RS) rs = COLSUM_RS; if (rs < 1) rs = 1;
+  dim3 grid(gx, rs);
   if (act) colsum_vec_kernel<T, true><<<grid, 256, 0, st>>>(A, act, rows, cols, inv_keep, partial);
   else colsum_vec_kernel<T, false><<<grid, 256, 0, st>>>(A, act, rows, cols, inv_keep, partial);
   B2C_LAUNCH_CHECK("colsum_vec_kernel");

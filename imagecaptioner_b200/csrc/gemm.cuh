@@ -411,21 +411,31 @@ inline bool tc_eligible(const GemmArgs& g) {
   return ((uintptr_t)g.A % 16 == 0) && ((uintptr_t)g.B % 16 == 0) && (g.lda % 8 == 0) && (g.ldb % 8 == 0);
 }
 
-// K splits for skinny outputs with a long reduction (weight gradients: M*N small, K = T*B): fill the SMs.
-template <int BN, typename TC>
-inline int pick_k_splits(const GemmArgs& g, int* kb_per_split) {
+// Tile / split-K plan.  Every CTA has to pull (128 + BN) x 64 bf16 per k-block through its L2 port, which is what bounds these
+// GEMMs (not the tensor pipe), so the plan minimises  waves x k-blocks-per-item x (128 + BN)  over BN in {256,128,64}, with K
+// splits (fp32 output, no ReLU, beta 0 or 1: partial tiles are added with red.global.add.f32) filling the SMs when M*N is small.
+struct TcPlan { int bn, splits, kb_per_split; };
+inline TcPlan plan_tc(const GemmArgs& g, int elem_c, int sms) {
   const int num_kb = cdiv(g.K, TC_BK);
-  int splits = 1;
-  if (sizeof(TC) == 4 && !g.relu && (g.beta == 0.f || g.beta == 1.f)) {
-    const long tiles = (long)cdiv(g.N, BN) * cdiv(g.M, TC_BM);
-    if (tiles <= 74 && num_kb >= 16) {
-      splits = (int)(148 / tiles);
-      if (splits > num_kb / 8) splits = num_kb / 8;          // at least 8 k-blocks (512 of K) per split
-      if (splits < 1) splits = 1;
+  const bool can_split = (elem_c == 4) && !g.relu && (g.beta == 0.f || g.beta == 1.f);
+  TcPlan best{64, 1, num_kb}; double best_cost = 1e30;
+  const int cand[3] = {256, 128, 64};
+  for (int ci = 0; ci < 3; ++ci) {
+    const int bn = cand[ci];
+    if (bn > 64 && g.N <= bn / 2) continue;                   // mostly-empty tiles
+    const long tiles = (long)cdiv(g.M, TC_BM) * cdiv(g.N, bn);
+    int splits = 1;
+    if (can_split && tiles < 2L * sms && num_kb >= 16) {
+      splits = (int)((2L * sms) / tiles); if (splits > num_kb / 8) splits = num_kb / 8; if (splits < 1) splits = 1;
     }
+    const int kbs = cdiv(num_kb, splits); splits = cdiv(num_kb, kbs);
+    const long items = tiles * splits;
+    const long waves = (items + sms - 1) / sms;
+    // per item: k-block feed + fixed cost (pipeline fill, epilogue of a 128 x bn tile); split items pay the atomics
+    const double cost = (double)waves * ((double)kbs * (128 + bn) + 6.0 * (128 + bn) + (splits > 1 ? 2.0 : 1.0) * bn * 4.0);
+    if (cost < best_cost) { best_cost = cost; best = TcPlan{bn, splits, kbs}; }
   }
-  *kb_per_split = cdiv(num_kb, splits);
-  return cdiv(num_kb, *kb_per_split);                      // no empty split
+  return best;
 }
 
 inline int sm_count() {
@@ -435,7 +445,7 @@ inline int sm_count() {
 }
 
 template <int BN, bool A_MN, bool B_MN, typename TC>
-int launch_tc(const GemmArgs& g, cudaStream_t st) {
+int launch_tc(const GemmArgs& g, const TcPlan& plan, cudaStream_t st) {
   CUtensorMap ta, tb;
   if (!A_MN) B2C_TRY(make_tmap_bf16(&ta, g.A, g.K, g.M, g.lda, TC_BM)); else B2C_TRY(make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, 64));
   if (!B_MN) B2C_TRY(make_tmap_bf16(&tb, g.B, g.K, g.N, g.ldb, BN)); else B2C_TRY(make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, 64));
@@ -445,8 +455,7 @@ int launch_tc(const GemmArgs& g, cudaStream_t st) {
     B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
-  int kb_per_split = 0;
-  const int splits = pick_k_splits<BN, TC>(g, &kb_per_split);
+  const int kb_per_split = plan.kb_per_split, splits = plan.splits;
   if (splits > 1 && g.beta == 0.f)
     B2C_CUDA(cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(TC), 0, (size_t)g.N * sizeof(TC), (size_t)g.M, st));
   const int tiles_m = cdiv(g.M, TC_BM), tiles_n = cdiv(g.N, BN);
@@ -459,21 +468,20 @@ int launch_tc(const GemmArgs& g, cudaStream_t st) {
 }
 
 template <int BN, typename TC>
-int launch_tc_major(const GemmArgs& g, cudaStream_t st) {
-  if (!g.a_mn && !g.b_mn) return launch_tc<BN, false, false, TC>(g, st);
-  if (!g.a_mn && g.b_mn) return launch_tc<BN, false, true, TC>(g, st);
-  if (g.a_mn && g.b_mn) return launch_tc<BN, true, true, TC>(g, st);
-  return launch_tc<BN, true, false, TC>(g, st);
+int launch_tc_major(const GemmArgs& g, const TcPlan& plan, cudaStream_t st) {
+  if (!g.a_mn && !g.b_mn) return launch_tc<BN, false, false, TC>(g, plan, st);
+  if (!g.a_mn && g.b_mn) return launch_tc<BN, false, true, TC>(g, plan, st);
+  if (g.a_mn && g.b_mn) return launch_tc<BN, true, true, TC>(g, plan, st);
+  return launch_tc<BN, true, false, TC>(g, plan, st);
 }
 
 // bf16 operands on tensor cores; TC = bf16 or float output.
 template <typename TC>
 int gemm_bf16_tc(const GemmArgs& g, cudaStream_t st) {
-  const long tm = cdiv(g.M, TC_BM);
-  const long tiles128 = tm * cdiv(g.N, 128), tiles256 = tm * cdiv(g.N, 256);
-  if (g.N >= 1024 && tiles256 >= 2L * sm_count()) return launch_tc_major<256, TC>(g, st);   // wide outputs: fewest operand re-reads
-  if (g.N <= 64 || tiles128 < 120) return launch_tc_major<64, TC>(g, st);
-  return launch_tc_major<128, TC>(g, st);
+  const TcPlan plan = plan_tc(g, (int)sizeof(TC), sm_count());
+  if (plan.bn == 256) return launch_tc_major<256, TC>(g, plan, st);
+  if (plan.bn == 128) return launch_tc_major<128, TC>(g, plan, st);
+  return launch_tc_major<64, TC>(g, plan, st);
 }
 
 template <typename TA, typename TB, typename TC>
