@@ -160,7 +160,7 @@ int attn_fwd(cudaStream_t st, const B2CShape& s, const float* P, const T* F, con
   const size_t smem = (size_t)s.S * s.E * sizeof(T) + (size_t)(s.E + s.S) * 4;
   const int nq = cdiv(s.E / 4, 32);
 #define B2C_ATT(NQ) do { B2C_TRY(set_smem(attn_step_fwd_kernel<T, NQ>, smem)); \
-    attn_step_fwd_kernel<T, NQ><<<s.B, ATT_THREADS, smem, st>>>(P, F, u, s.E, s.S, s.E, ctx, s.E, attw); } while (0)
+    B2C_CUDA(launch_pdl(attn_step_fwd_kernel<T, NQ>, dim3(s.B), dim3(ATT_THREADS), smem, st, P, F, u, (long)s.E, s.S, s.E, ctx, (long)s.E, attw)); } while (0)
   if (nq == 1) B2C_ATT(1); else if (nq == 2) B2C_ATT(2); else if (nq == 3) B2C_ATT(3); else B2C_ATT(0);
 #undef B2C_ATT
   B2C_LAUNCH_CHECK("attn_step_fwd_kernel");
@@ -174,8 +174,8 @@ int lstm_layer_fwd(cudaStream_t st, const B2CShape& s, const Weights<T>& w, int 
                    const B2CDropout& dr, long row_base) {
   const int in = in_dim(s, k), ld = in + s.H;
   B2C_TRY((gemm<T, float>(st, s.B, 4 * s.H, ld, xh_t, ld, 0, w.Wcat[k], ld, 0, pre, 4 * s.H, 0.f, w.bcat[k])));
-  lstm_pointwise_fwd_kernel<T><<<ew_grid((long)s.B * s.H), 256, 0, st>>>(pre, c_prev, c_out, gates_out, h_rec, ld, h_next, 2 * s.H, h_top, s.H,
-                                                                       s.B, s.H, dr.p, dr.seed, (uint32_t)k, row_base);
+  B2C_CUDA(launch_pdl(lstm_pointwise_fwd_kernel<T>, dim3(ew_grid((long)s.B * s.H)), dim3(256), 0, st, (const float*)pre, c_prev, c_out, gates_out,
+                      h_rec, (long)ld, h_next, (long)(2 * s.H), h_top, (long)s.H, s.B, s.H, dr.p, dr.seed, (uint32_t)k, row_base));
   B2C_LAUNCH_CHECK("lstm_pointwise_fwd_kernel");
   return 0;
 }
@@ -324,10 +324,10 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
         const T* carry = last ? nullptr : (k == 0 ? W.dxh0 + (row + B) * (E + H) + E : W.dxh[k] + b0 * 2 * H + H);
         const T* above = (k < L - 1) ? W.dxh[k + 1] + b0 * 2 * H : nullptr;
         const bool top = (k == L - 1);
-        lstm_pointwise_bwd_kernel<T><<<ew_grid((long)Bh * H), 256, 0, ss>>>(
-            W.gates[k] + row * 4 * H, W.c[k] + row * H, W.c[k] + (row + B) * H, W.dc[k] + b0 * H, last ? 1 : 0,
-            carry, ld, above, 2 * H, top ? W.dHext + row * H : nullptr, (top && dhid) ? dhid + row * H : nullptr,
-            (top && !last) ? W.dq + b0 * H : nullptr, H, W.dgates[k] + row * 4 * H, Bh, H, dr.p, dr.seed, (uint32_t)k, row);
+        B2C_CUDA(launch_pdl(lstm_pointwise_bwd_kernel<T>, dim3(ew_grid((long)Bh * H)), dim3(256), 0, ss,
+            (const T*)(W.gates[k] + row * 4 * H), (const float*)(W.c[k] + row * H), (const float*)(W.c[k] + (row + B) * H), W.dc[k] + b0 * H, last ? 1 : 0,
+            carry, (long)ld, above, (long)(2 * H), (const float*)(top ? W.dHext + row * H : nullptr), (const T*)((top && dhid) ? dhid + row * H : nullptr),
+            (const T*)((top && !last) ? W.dq + b0 * H : nullptr), (long)H, W.dgates[k] + row * 4 * H, Bh, H, dr.p, dr.seed, (uint32_t)k, row));
         B2C_LAUNCH_CHECK("lstm_pointwise_bwd_kernel");
         T* out = (k == 0) ? W.dxh0 + row * (E + H) : W.dxh[k] + b0 * 2 * H;
         B2C_TRY((gemm<T, T>(ss, Bh, ld, 4 * H, W.dgates[k] + row * 4 * H, 4 * H, 0, W.w.Wcat[k], ld, 1, out, ld)));
@@ -336,8 +336,8 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
       T* dctx_t = W.dctx + row * E;
       T* du_t = W.du + row * E;
       B2C_TRY((gemm<T, T>(ss, Bh, E, E, dx, E + H, 0, W.w.Wcc, E, 1, dctx_t, E)));
-      attn_step_bwd_kernel<T><<<Bh, ATT_THREADS, att_smem, ss>>>(W.P + b0 * S * E, feats + b0 * S * E, W.u + row * E, E, attw + row * S, dctx_t, E,
-                                                               S, E, W.ds + row * S, du_t, E);
+      B2C_CUDA(launch_pdl(attn_step_bwd_kernel<T>, dim3(Bh), dim3(ATT_THREADS), att_smem, ss, (const float*)(W.P + b0 * S * E), feats + b0 * S * E,
+                          (const float*)(W.u + row * E), (long)E, attw + row * S, (const T*)dctx_t, (long)E, S, E, W.ds + row * S, du_t, (long)E));
       B2C_LAUNCH_CHECK("attn_step_bwd_kernel");
       if (t > 0) B2C_TRY((gemm<T, T>(ss, Bh, H, E, du_t, E, 0, W.w.Wh, H, 1, W.dq + b0 * H, H)));
     }

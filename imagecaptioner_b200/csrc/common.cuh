@@ -8,6 +8,7 @@
 #include <string.h>
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/b2c.h"
 
@@ -81,6 +82,30 @@ __device__ __forceinline__ uint32_t mix32(uint64_t seed, uint32_t stream, uint64
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t stream, uint64_t idx, float p, float inv_keep) {
   const uint32_t thr = (uint32_t)(p * 4294967296.0f);
   return mix32(seed, stream, idx) >= thr ? inv_keep : 0.0f;
+}
+
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// The recurrence is a chain of ~280 dependent small kernels per training step.  Kernels on that chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: each calls pdl_launch_dependents() first (the next kernel may start its
+// prologue: barrier init, TMEM allocation, descriptor prefetch) and pdl_wait() before it touches global memory (blocks until
+// every prerequisite grid has completed and flushed).  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("B2C_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // ------------------------------------------------------------------ PTX wrappers (mbarrier / bulk copies)

@@ -89,6 +89,8 @@ attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATT_THREADS / 32;
   const int b = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   att_stage_F<T>(F, b, SE, Fs, &bar);
   for (int e = tid; e < E; e += ATT_THREADS) us[e] = u[(long)b * ldu + e];
   __syncthreads();
@@ -173,6 +175,8 @@ attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATT_THREADS / 32;
   const int b = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   att_stage_F<T>(F, b, SE, Fs, &bar);
   for (int e = tid; e < E; e += ATT_THREADS) dcs[e] = to_f<T>(dctx[(long)b * lddctx + e]);
   __syncthreads();
@@ -243,6 +247,8 @@ lstm_pointwise_fwd_kernel(const float* __restrict__ pre, const float* __restrict
                           T* __restrict__ gates_out, T* __restrict__ h_rec, long ld_rec, T* __restrict__ h_next, long ld_next,
                           T* __restrict__ h_top, long ld_top, int B, int H,
                           float drop_p, uint64_t seed, uint32_t site, long row_base) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long total = (long)B * H;
   const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -274,6 +280,8 @@ lstm_pointwise_bwd_kernel(const T* __restrict__ gates, const float* __restrict__
                           const T* __restrict__ dh_carry, long ld_carry, const T* __restrict__ dh_above, long ld_above,
                           const float* __restrict__ dh_ext, const T* __restrict__ dh_hid, const T* __restrict__ dh_q, long ld_q,
                           T* __restrict__ dgates, int B, int H, float drop_p, uint64_t seed, uint32_t site, long row_base) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long total = (long)B * H;
   const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {

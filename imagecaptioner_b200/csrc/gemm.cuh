@@ -32,6 +32,8 @@ gemm_simt_kernel(int M, int N, int K, float alpha, const TA* __restrict__ A, lon
                  const float* __restrict__ bias, int relu) {
   __shared__ float As[SG_BK][SG_BM + 4];
   __shared__ float Bs[SG_BK][SG_BN + 4];
+  pdl_launch_dependents();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
   const int tx = tid & 15, ty = tid >> 4;      // 16 x 16 threads, 4x4 outputs each
@@ -199,6 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int total = tiles_mn * splits;                  // work items (M tile, N tile, K split), dealt round-robin to the CTAs
   const bool split = splits > 1;
 
+  pdl_launch_dependents();                   // the next kernel on the chain may begin its own prologue
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1) {
     if (lane == 0) {
@@ -214,6 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                // prologue done; operands / C of the previous kernels are complete from here on
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
@@ -461,8 +465,8 @@ int launch_tc(const GemmArgs& g, const TcPlan& plan, cudaStream_t st) {
   const int tiles_m = cdiv(g.M, TC_BM), tiles_n = cdiv(g.N, BN);
   const long total = (long)tiles_m * tiles_n * splits;
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(ta, tb, g.M, g.N, g.K, g.alpha, g.beta, (TC*)g.C, g.ldc, g.bias, g.relu,
-                                                        kb_per_split, tiles_m, tiles_n, splits);
+  B2C_CUDA(launch_pdl(kern, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES, st, ta, tb, g.M, g.N, g.K, g.alpha, g.beta, (TC*)g.C, g.ldc,
+                      g.bias, g.relu, kb_per_split, tiles_m, tiles_n, splits));
   B2C_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -487,8 +491,8 @@ int gemm_bf16_tc(const GemmArgs& g, cudaStream_t st) {
 template <typename TA, typename TB, typename TC>
 int gemm_simt(const GemmArgs& g, cudaStream_t st) {
   dim3 grid(cdiv(g.N, SG_BN), cdiv(g.M, SG_BM));
-  gemm_simt_kernel<TA, TB, TC><<<grid, 256, 0, st>>>(g.M, g.N, g.K, g.alpha, (const TA*)g.A, g.lda, g.a_mn,
-                                                      (const TB*)g.B, g.ldb, g.b_mn, g.beta, (TC*)g.C, g.ldc, g.bias, g.relu);
+  B2C_CUDA(launch_pdl(gemm_simt_kernel<TA, TB, TC>, grid, dim3(256), 0, st, g.M, g.N, g.K, g.alpha, (const TA*)g.A, g.lda, g.a_mn,
+                      (const TB*)g.B, g.ldb, g.b_mn, g.beta, (TC*)g.C, g.ldc, g.bias, g.relu));
   B2C_LAUNCH_CHECK("gemm_simt_kernel");
   return 0;
 }
