@@ -99,7 +99,7 @@ gemm_simt_kernel(int M, int N, int K, float alpha, const TA* __restrict__ A, lon
 // ======================================================================================
 // tcgen05 / TMEM / TMA bf16 GEMM
 // ======================================================================================
-constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;     // 16 KiB per stage
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -152,13 +152,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 constexpr int TC_EPI_PITCH = 144;                       // bytes per staged row: 128 B of payload + 16 B pad (bank-conflict free)
-constexpr int TC_EPI_BYTES = 4 * 32 * TC_EPI_PITCH;    // one 32-row staging tile per epilogue warp
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_BYTES = TC_EPI_WARPS * 32 * TC_EPI_PITCH;    // one 32-row staging tile per epilogue warp
 
 template <int BN> struct TcCfg {
+  static constexpr int STAGES = BN == 256 ? 3 : 4;      // 48 KB stages at BN = 256: three fit beside the epilogue staging
   static constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   static constexpr uint32_t STAGE_BYTES = TC_A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (128 / 256 / 512 columns)
-  static constexpr size_t SMEM_BYTES = (size_t)TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + TC_EPI_BYTES;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + TC_EPI_BYTES;
 };
 
 __device__ __forceinline__ uint4 epi_combine_bf16(uint4 acc, uint4 old, float beta) {
@@ -186,12 +188,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                int M, int N, int K, float alpha, float beta, TC* __restrict__ C, long ldc,
                const float* __restrict__ bias, int relu, int kb_per_split, int tiles_m, int tiles_n, int splits) {
   using Cfg = TcCfg<BN>;
+  constexpr int TC_STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + (size_t)TC_STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + TC_STAGES;
   uint64_t* tfull_bar = empty_bar + TC_STAGES;          // [2] accumulator stage complete (MMA -> epilogue)
-  uint64_t* tempty_bar = tfull_bar + 2;                 // [2] accumulator stage drained  (epilogue -> MMA), 4 arrivals
+  uint64_t* tempty_bar = tfull_bar + 2;                 // [2] accumulator stage drained  (epilogue -> MMA), one arrival per epilogue warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   unsigned char* epi_stage = base + (size_t)TC_STAGES * Cfg::STAGE_BYTES + 256;
 
@@ -206,7 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TC_EPI_WARPS); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -283,7 +286,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------ epilogue: warps 2..5 -> TMEM lane quarters (warp % 4).
     // TMEM -> registers (one accumulator row per lane) -> alpha/bias/ReLU -> 128-byte row chunks staged in shared memory
     // -> written out with each quarter-warp covering one contiguous 128-byte row segment (full sectors, 16-byte accesses).
-    const int q = warp & 3;
+    const int q = warp & 3;                              // TMEM lane quarter this warp may read (warp id % 4)
+    const int half = (warp - 2) >> 2;                    // two warps per quarter: each drains half of the tile's columns
     unsigned char* my = epi_stage + (size_t)(warp - 2) * 32 * TC_EPI_PITCH;
     constexpr int PER = 16 / (int)sizeof(TC);           // elements per 16-byte unit: 8 (bf16) or 4 (fp32)
     constexpr int CH = 128 / (int)sizeof(TC);           // columns per staged chunk: 64 (bf16) or 32 (fp32)
@@ -297,8 +301,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(&tfull_bar[as], aph);
     tc_fence_after();
     const uint32_t tacc = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(q * 32) << 16);
+    constexpr int NCHUNK = BN / CH;                      // 128-byte column chunks per tile row
+    constexpr int C_PER = (NCHUNK + 1) / 2;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += CH) {
+    for (int ci = half * C_PER; ci < (half + 1) * C_PER && ci < NCHUNK; ++ci) {
+      const int c0 = ci * CH;
       if (n0 + c0 >= N) break;
 #pragma unroll
       for (int h = 0; h < CH / 32; ++h) {
