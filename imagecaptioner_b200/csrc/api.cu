@@ -47,22 +47,30 @@ int check_shape(const B2CShape* s) {
 }
 
 // ------------------------------------------------------------------ packed operand weights (compute type)
+// Gate rows are INTERLEAVED in every 4H-sized object (row 4j+g = gate g of hidden unit j) so that the gate contraction's
+// epilogue holds the four pre-activations of one unit together (fused cell, gemm.cuh).  attention_combine is folded into
+// layer 0 (oracle/manual_backward.py v2):  Wcat[0] = [W_ih0 W_cc | W_hh0],  We = W_ih0 W_ce,  bx = W_ih0 b_c + b_ih0 + b_hh0.
 template <typename T> struct Weights {
-  T *Wf, *Wh, *Wce, *Wcc, *W1, *W2; T* Wcat[MAXL]; float* bcat[MAXL];
+  T *Wf, *Wh, *Wce, *Wcc, *W1, *W2, *Wih0, *We; T* Wcat[MAXL]; float* bcat[MAXL]; float* bx;
   void carve(Carver& c, const B2CShape& s) {
     Wf = c.take<T>((size_t)s.E * s.E); Wh = c.take<T>((size_t)s.E * s.H);
     Wce = c.take<T>((size_t)s.E * s.E); Wcc = c.take<T>((size_t)s.E * s.E);
     W1 = c.take<T>((size_t)s.E * s.H); W2 = c.take<T>((size_t)s.V * s.E);
+    Wih0 = c.take<T>((size_t)4 * s.H * s.E); We = c.take<T>((size_t)4 * s.H * s.E); bx = c.take<float>((size_t)4 * s.H);
     for (int k = 0; k < s.L; ++k) { Wcat[k] = c.take<T>((size_t)4 * s.H * (in_dim(s, k) + s.H)); bcat[k] = c.take<float>((size_t)4 * s.H); }
   }
 };
+
+template <typename T, typename TC>
+int gemm(cudaStream_t st, int M, int N, int K, const T* A, long lda, int a_mn, const T* B, long ldb, int b_mn,
+         TC* C, long ldc, float beta = 0.f, const float* bias = nullptr, int relu = 0, float alpha = 1.f, int row_unperm_h = 0);
 
 template <typename T>
 int pack_params(const B2CShape& s, const B2CParams& p, const Weights<T>& w, cudaStream_t st) {
   B2C_CHECK_ARG(p.embedding && p.attn_w && p.attn_b && p.comb_w && p.comb_b && p.out0_w && p.out0_b && p.out3_w && p.out3_b, "NULL parameter pointer");
   PackTable tab; tab.n = 0;
-  auto add = [&](const float* src, void* dst, int rows, int cols, long lds, long ldd, const float* src2 = nullptr, int as_float = 0) {
-    PackSeg& g = tab.seg[tab.n++]; g.src = src; g.dst = dst; g.src2 = src2; g.rows = rows; g.cols = cols; g.lds = lds; g.ldd = ldd; g.as_float = as_float;
+  auto add = [&](const float* src, void* dst, int rows, int cols, long lds, long ldd, int perm_h = 0, const float* src2 = nullptr, int as_float = 0) {
+    PackSeg& g = tab.seg[tab.n++]; g.src = src; g.dst = dst; g.src2 = src2; g.rows = rows; g.cols = cols; g.lds = lds; g.ldd = ldd; g.as_float = as_float; g.perm_h = perm_h;
   };
   const int E = s.E, H = s.H;
   add(p.attn_w, w.Wh, E, H, H + E, H);
@@ -74,40 +82,47 @@ int pack_params(const B2CShape& s, const B2CParams& p, const Weights<T>& w, cuda
   for (int k = 0; k < s.L; ++k) {
     B2C_CHECK_ARG(p.w_ih[k] && p.w_hh[k] && p.b_ih[k] && p.b_hh[k], "NULL LSTM parameter pointer (layer %d)", k);
     const int in = in_dim(s, k);
-    add(p.w_ih[k], w.Wcat[k], 4 * H, in, in, in + H);
-    add(p.w_hh[k], w.Wcat[k] + in, 4 * H, H, H, in + H);
-    add(p.b_ih[k], w.bcat[k], 1, 4 * H, 4 * H, 4 * H, p.b_hh[k], 1);
+    if (k == 0) add(p.w_ih[0], w.Wih0, 4 * H, E, E, E, H);                      // its product with W_cc fills Wcat[0][:, :E] below
+    else add(p.w_ih[k], w.Wcat[k], 4 * H, in, in, in + H, H);
+    add(p.w_hh[k], w.Wcat[k] + in, 4 * H, H, H, in + H, H);
+    if (k > 0) add(p.b_ih[k], w.bcat[k], 4 * H, 1, 1, 1, H, p.b_hh[k], 1);
   }
   pack_params_kernel<T><<<dim3(96, tab.n), 256, 0, st>>>(tab);
   B2C_LAUNCH_CHECK("pack_params_kernel");
+  // W_x = W_ih0 W_cc -> Wcat[0][:, :E];  W_e = W_ih0 W_ce;  b_x
+  B2C_TRY((gemm<T, T>(st, 4 * H, E, E, w.Wih0, E, 0, w.Wcc, E, 1, w.Wcat[0], E + H)));
+  B2C_TRY((gemm<T, T>(st, 4 * H, E, E, w.Wih0, E, 0, w.Wce, E, 1, w.We, E)));
+  bias_fold_kernel<<<cdiv(4 * H * 32, 256), 256, 0, st>>>(p.w_ih[0], p.comb_b, p.b_ih[0], p.b_hh[0], H, E, w.bx);
+  B2C_LAUNCH_CHECK("bias_fold_kernel");
   return 0;
 }
 
 // ------------------------------------------------------------------ workspaces
 template <typename T> struct TrainWs {
   Weights<T> w;
-  float *P, *u; T *emb, *ctx, *o1; T* xh[MAXL]; T* gates[MAXL]; float* c[MAXL]; float* pre;
-  T* dgates[MAXL]; T* dxh0; T* dxh[MAXL]; float* dc[MAXL]; T* do1; float* dHext; T* dctx; float* ds; T* du; T* dq; T* dP; float* demb; float* partial;
+  float *P, *u; T *emb, *G0, *o1; T* xh[MAXL]; T* gates[MAXL]; float* c[MAXL];
+  T* dgates[MAXL]; T* dxh0; T* dxh[MAXL]; float* dc[MAXL]; T* do1; float* dHext; float* ds; T* du; T* dq; T* dP; float* demb; float* partial;
+  float *dWx32, *dWe32; T *dWxT, *dWeT;
   size_t bytes;
   void carve(void* base, const B2CShape& s) {
     Carver c{reinterpret_cast<unsigned char*>(base), 0};
     const size_t B = s.B, Tn = s.T, S = s.S, E = s.E, H = s.H, TB = Tn * B;
     w.carve(c, s);
-    P = c.take<float>(B * S * E); emb = c.take<T>(TB * E); u = c.take<float>(TB * E); ctx = c.take<T>(TB * E); o1 = c.take<T>(TB * E);
+    P = c.take<float>(B * S * E); emb = c.take<T>(TB * E); u = c.take<float>(TB * E); G0 = c.take<T>(TB * 4 * H); o1 = c.take<T>(TB * E);
     for (int k = 0; k < s.L; ++k) {
-      xh[k] = c.take<T>((Tn + 1) * B * (in_dim(s, k) + H));
+      xh[k] = c.take<T>((Tn + 1) * B * (in_dim(s, k) + H));        // layer 0: [ctx_t ; h0_{t-1}]
       gates[k] = c.take<T>(TB * 4 * H);
       this->c[k] = c.take<float>((Tn + 1) * B * H);
     }
-    pre = c.take<float>(B * 4 * H);
     for (int k = 0; k < s.L; ++k) {
       dgates[k] = c.take<T>(TB * 4 * H);
       dxh[k] = k == 0 ? nullptr : c.take<T>(B * 2 * H);
       dc[k] = c.take<float>(B * H);
     }
-    dxh0 = c.take<T>(TB * (E + H));
-    do1 = c.take<T>(TB * E); dHext = c.take<float>(TB * H); dctx = c.take<T>(TB * E); ds = c.take<float>(TB * S);
+    dxh0 = c.take<T>(TB * (E + H));                                 // [dctx_t ; dh0 carry]
+    do1 = c.take<T>(TB * E); dHext = c.take<float>(TB * H); ds = c.take<float>(TB * S);
     du = c.take<T>(TB * E); dq = c.take<T>(B * H); dP = c.take<T>(B * S * E); demb = c.take<float>(TB * E);
+    dWx32 = c.take<float>(4 * H * E); dWe32 = c.take<float>(4 * H * E); dWxT = c.take<T>(4 * H * E); dWeT = c.take<T>(4 * H * E);
     size_t mc = (size_t)s.V; if ((size_t)4 * H > mc) mc = 4 * H; if (E > mc) mc = E;
     partial = c.take<float>((size_t)COLSUM_RS * mc);
     bytes = align_up(c.off, 256);
@@ -116,35 +131,44 @@ template <typename T> struct TrainWs {
 
 template <typename T> struct DecodeWs {
   Weights<T> w;
-  float *P, *u; T *emb, *ctx, *o1; T* xh[MAXL]; float* c[MAXL]; float* pre; float* logits; int64_t* cur; int32_t* done;
+  float *P, *u; T *emb, *G0, *o1; T* xh[MAXL]; float* c[MAXL]; float* logits; int64_t* cur; int32_t* done;
   size_t bytes;
   void carve(void* base, const B2CShape& s) {
     Carver c{reinterpret_cast<unsigned char*>(base), 0};
     const size_t B = s.B, S = s.S, E = s.E, H = s.H;
     w.carve(c, s);
-    P = c.take<float>(B * S * E); emb = c.take<T>(B * E); u = c.take<float>(B * E); ctx = c.take<T>(B * E); o1 = c.take<T>(B * E);
-    for (int k = 0; k < s.L; ++k) { xh[k] = c.take<T>(B * (in_dim(s, k) + H)); this->c[k] = c.take<float>(B * H); }
-    pre = c.take<float>(B * 4 * H); logits = c.take<float>(B * (size_t)s.V); cur = c.take<int64_t>(B); done = c.take<int32_t>(B);
+    P = c.take<float>(B * S * E); emb = c.take<T>(B * E); u = c.take<float>(B * E); G0 = c.take<T>(B * 4 * H); o1 = c.take<T>(B * E);
+    for (int k = 0; k < s.L; ++k) { xh[k] = c.take<T>(2 * B * (in_dim(s, k) + H)); this->c[k] = c.take<float>(B * H); }   // two [input;h] slots (ping-pong)
+    logits = c.take<float>(B * (size_t)s.V); cur = c.take<int64_t>(B); done = c.take<int32_t>(B);
     bytes = align_up(c.off, 256);
   }
 };
 
+
 // ------------------------------------------------------------------ launch helpers
 template <typename T, typename TC>
 int gemm(cudaStream_t st, int M, int N, int K, const T* A, long lda, int a_mn, const T* B, long ldb, int b_mn,
-         TC* C, long ldc, float beta = 0.f, const float* bias = nullptr, int relu = 0, float alpha = 1.f) {
+         TC* C, long ldc, float beta, const float* bias, int relu, float alpha, int row_unperm_h) {
   GemmArgs g{M, N, K, alpha, beta, A, lda, a_mn, B, ldb, b_mn, C, ldc, bias, relu};
+  g.row_unperm_h = row_unperm_h;
   return Gemm<T, TC>::run(g, st);
+}
+// gate contraction with the LSTM cell fused into the epilogue (no C is written)
+template <typename T>
+int gemm_lstm(cudaStream_t st, int M, int H, int K, const T* A, long lda, const T* Wcat, long ldb, const LstmEpi& le) {
+  GemmArgs g{M, 4 * H, K, 1.f, 0.f, A, lda, 0, Wcat, ldb, 0, nullptr, 4 * H, nullptr, 0};
+  g.lstm = &le;
+  return Gemm<T, float>::run(g, st);
 }
 
 inline int ew_grid(long n) { long g = (n + 255) / 256; if (g > 148 * 8) g = 148 * 8; if (g < 1) g = 1; return (int)g; }
 
 template <typename T>
-int colsum(cudaStream_t st, const T* A, long rows, int cols, long ld, float* partial, float* out, float* out2 = nullptr) {
+int colsum(cudaStream_t st, const T* A, long rows, int cols, long ld, float* partial, float* out, float* out2 = nullptr, int unperm_h = 0) {
   int rs = (int)((rows + 255) / 256); if (rs > COLSUM_RS) rs = COLSUM_RS; if (rs < 1) rs = 1;
   colsum_partial_kernel<T><<<dim3(cdiv(cols, 32), rs), 256, 0, st>>>(A, rows, cols, ld, partial);
   B2C_LAUNCH_CHECK("colsum_partial_kernel");
-  colsum_final_kernel<<<cdiv(cols, 256), 256, 0, st>>>(partial, rs, cols, out, out2);
+  colsum_final_kernel<<<cdiv(cols, 256), 256, 0, st>>>(partial, rs, cols, out, out2, unperm_h);
   B2C_LAUNCH_CHECK("colsum_final_kernel");
   return 0;
 }
@@ -156,28 +180,29 @@ template <typename K> int set_smem(K kern, size_t bytes) {
 }
 
 template <typename T>
-int attn_fwd(cudaStream_t st, const B2CShape& s, const float* P, const T* F, const float* u, T* ctx, float* attw) {
+int attn_fwd(cudaStream_t st, const B2CShape& s, const float* P, const T* F, const float* u, T* ctx, long ldctx, float* attw) {
   const size_t smem = (size_t)s.S * s.E * sizeof(T) + (size_t)(s.E + s.S) * 4;
   const int nq = cdiv(s.E / 4, 32);
 #define B2C_ATT(NQ) do { B2C_TRY(set_smem(attn_step_fwd_kernel<T, NQ>, smem)); \
-    B2C_CUDA(launch_pdl(attn_step_fwd_kernel<T, NQ>, dim3(s.B), dim3(ATT_THREADS), smem, st, P, F, u, (long)s.E, s.S, s.E, ctx, (long)s.E, attw)); } while (0)
+    B2C_CUDA(launch_pdl(attn_step_fwd_kernel<T, NQ>, dim3(s.B), dim3(ATT_THREADS), smem, st, P, F, u, (long)s.E, s.S, s.E, ctx, ldctx, attw)); } while (0)
   if (nq == 1) B2C_ATT(1); else if (nq == 2) B2C_ATT(2); else if (nq == 3) B2C_ATT(3); else B2C_ATT(0);
 #undef B2C_ATT
   B2C_LAUNCH_CHECK("attn_step_fwd_kernel");
   return 0;
 }
 
-// one LSTM layer step: pre = [in;h] Wcat^T + b, then the cell pointwise
+// one LSTM layer step: gates = [in ; h] Wcat^T (+ bias | + time-batched addend), cell fused into the contraction's epilogue
 template <typename T>
-int lstm_layer_fwd(cudaStream_t st, const B2CShape& s, const Weights<T>& w, int k, const T* xh_t, float* pre,
+int lstm_layer_fwd(cudaStream_t st, const B2CShape& s, const Weights<T>& w, int k, const T* xh_t, const T* addend,
                    const float* c_prev, float* c_out, T* gates_out, T* h_rec, T* h_next, T* h_top,
                    const B2CDropout& dr, long row_base) {
   const int in = in_dim(s, k), ld = in + s.H;
-  B2C_TRY((gemm<T, float>(st, s.B, 4 * s.H, ld, xh_t, ld, 0, w.Wcat[k], ld, 0, pre, 4 * s.H, 0.f, w.bcat[k])));
-  B2C_CUDA(launch_pdl(lstm_pointwise_fwd_kernel<T>, dim3(ew_grid((long)s.B * s.H)), dim3(256), 0, st, (const float*)pre, c_prev, c_out, gates_out,
-                      h_rec, (long)ld, h_next, (long)(2 * s.H), h_top, (long)s.H, s.B, s.H, dr.p, dr.seed, (uint32_t)k, row_base));
-  B2C_LAUNCH_CHECK("lstm_pointwise_fwd_kernel");
-  return 0;
+  LstmEpi le{};
+  le.enabled = 1; le.H = s.H; le.addend = addend; le.bias = (k == 0) ? nullptr : w.bcat[k];     // layer 0: b_x is inside the addend
+  le.c_prev = c_prev; le.c_out = c_out; le.gates_out = gates_out;
+  le.h_rec = h_rec; le.ld_rec = ld; le.h_next = h_next; le.ld_next = 2 * s.H; le.h_top = h_top; le.ld_top = s.H;
+  le.drop_p = dr.p; le.seed = dr.seed; le.site = (unsigned)k; le.row_base = row_base;
+  return gemm_lstm<T>(st, s.B, s.H, ld, xh_t, ld, w.Wcat[k], ld, le);
 }
 
 // ------------------------------------------------------------------ sub-batch streams
@@ -232,6 +257,7 @@ int join_subs(SubPlan& sp) {
 }
 
 // ------------------------------------------------------------------ decoder forward (teacher forced)
+// Per step: u = q W_h^T  ->  attention (ctx lands in layer 0's operand)  ->  L fused gate-GEMM + cell kernels.
 template <typename T>
 int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, const int64_t* cap, T* logits, T* hid_top,
                          float* attw, void* ws, size_t ws_bytes, const B2CDropout& dr, cudaStream_t st) {
@@ -248,26 +274,25 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
     B2C_CUDA(cudaMemsetAsync(W.xh[k], 0, (size_t)B * (in_dim(s, k) + H) * sizeof(T), st));   // h_{-1} = 0
     B2C_CUDA(cudaMemsetAsync(W.c[k], 0, (size_t)B * H * sizeof(float), st));                  // c_{-1} = 0
   }
-  // embedding half of attention_combine for all steps, straight into layer 0's input slots
-  B2C_TRY((gemm<T, T>(st, (int)TB, E, E, W.emb, E, 0, W.w.Wce, E, 0, W.xh[0], E + H, 0.f, p.comb_b)));
+  // embedding half of layer 0's gate pre-activations for all steps:  G0 = emb (W_ih0 W_ce)^T + b_x
+  B2C_TRY((gemm<T, T>(st, (int)TB, 4 * H, E, W.emb, E, 0, W.w.We, E, 0, W.G0, 4 * H, 0.f, W.w.bx)));
   const int inL = in_dim(s, L - 1), ldL = inL + H;
   SubPlan sp;
   B2C_TRY(fork_subs(sp, B, st));
   for (int t = 0; t < Tn; ++t) {
-    for (int i = 0; i < sp.ns; ++i) {                          // interleaved issue: sub-batch chains advance together
+    for (int i = 0; i < sp.ns; ++i) {
       cudaStream_t ss = sp.st[i];
       const long b0 = sp.b0[i];
       B2CShape sh = s; sh.B = sp.bn[i];
       const long row = (long)t * B + b0;                       // first row of this sub-batch at step t in a (T,B,.) buffer
       const T* q = W.xh[L - 1] + row * ldL + inL;
       float* u_t = W.u + row * E;
-      T* ctx_t = W.ctx + row * E;
       B2C_TRY((gemm<T, float>(ss, sh.B, E, H, q, ldL, 0, W.w.Wh, H, 0, u_t, E)));
-      B2C_TRY(attn_fwd<T>(ss, sh, W.P + b0 * S * E, feats + b0 * S * E, u_t, ctx_t, attw + row * S));
-      B2C_TRY((gemm<T, T>(ss, sh.B, E, E, ctx_t, E, 0, W.w.Wcc, E, 0, W.xh[0] + row * (E + H), E + H, 1.f)));
+      B2C_TRY(attn_fwd<T>(ss, sh, W.P + b0 * S * E, feats + b0 * S * E, u_t, W.xh[0] + row * (E + H), E + H, attw + row * S));
       for (int k = 0; k < L; ++k) {
         const int in = in_dim(s, k), ld = in + H;
-        B2C_TRY(lstm_layer_fwd<T>(ss, sh, W.w, k, W.xh[k] + row * ld, W.pre + b0 * 4 * H, W.c[k] + row * H, W.c[k] + (row + B) * H,
+        B2C_TRY(lstm_layer_fwd<T>(ss, sh, W.w, k, W.xh[k] + row * ld, k == 0 ? W.G0 + row * 4 * H : (const T*)nullptr,
+                                  W.c[k] + row * H, W.c[k] + (row + B) * H,
                                   W.gates[k] + row * 4 * H, W.xh[k] + (row + B) * ld + in,
                                   k + 1 < L ? W.xh[k + 1] + row * 2 * H : nullptr, k == L - 1 ? hid_top + row * H : nullptr,
                                   dr, row));
@@ -285,12 +310,12 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
   return 0;
 }
 
-// ------------------------------------------------------------------ decoder backward (BPTT)
+
+// ------------------------------------------------------------------ decoder backward (BPTT), oracle/manual_backward.py v2
 template <typename T>
 int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats, const int64_t* cap, const T* hid_top,
                           const float* attw, const T* dlogits, const T* dhid, const B2CGrads& g, float* dfeats,
                           void* ws, size_t ws_bytes, const B2CDropout& dr, cudaStream_t st) {
-  (void)p;
   TrainWs<T> W; W.carve(ws, s);
   B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
   B2C_CHECK_ARG(g.embedding && g.attn_w && g.attn_b && g.comb_w && g.comb_b && g.out0_w && g.out0_b && g.out3_w && g.out3_b && dfeats, "NULL gradient pointer");
@@ -332,44 +357,63 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
         T* out = (k == 0) ? W.dxh0 + row * (E + H) : W.dxh[k] + b0 * 2 * H;
         B2C_TRY((gemm<T, T>(ss, Bh, ld, 4 * H, W.dgates[k] + row * 4 * H, 4 * H, 0, W.w.Wcat[k], ld, 1, out, ld)));
       }
-      const T* dx = W.dxh0 + row * (E + H);
-      T* dctx_t = W.dctx + row * E;
+      // layer 0's input gradient IS d(ctx_t): no context GEMM on the chain
+      const T* dctx_t = W.dxh0 + row * (E + H);
       T* du_t = W.du + row * E;
-      B2C_TRY((gemm<T, T>(ss, Bh, E, E, dx, E + H, 0, W.w.Wcc, E, 1, dctx_t, E)));
       B2C_CUDA(launch_pdl(attn_step_bwd_kernel<T>, dim3(Bh), dim3(ATT_THREADS), att_smem, ss, (const float*)(W.P + b0 * S * E), feats + b0 * S * E,
-                          (const float*)(W.u + row * E), (long)E, attw + row * S, (const T*)dctx_t, (long)E, S, E, W.ds + row * S, du_t, (long)E));
+                          (const float*)(W.u + row * E), (long)E, attw + row * S, dctx_t, (long)(E + H), S, E, W.ds + row * S, du_t, (long)E));
       B2C_LAUNCH_CHECK("attn_step_bwd_kernel");
       if (t > 0) B2C_TRY((gemm<T, T>(ss, Bh, H, E, du_t, E, 0, W.w.Wh, H, 1, W.dq + b0 * H, H)));
     }
   }
   B2C_TRY(join_subs(sp));
-  // ---- post-loop, time-batched weight gradients
-  for (int k = 0; k < L; ++k) {
+  // ---- post-loop, time-batched weight gradients (4H-sized rows come out interleaved and are written gate-major)
+  for (int k = 1; k < L; ++k) {
     const int in = in_dim(s, k), ld = in + H;
-    B2C_TRY((gemm<T, float>(st, 4 * H, in, (int)TB, W.dgates[k], 4 * H, 1, W.xh[k], ld, 1, g.w_ih[k], in)));
-    B2C_TRY((gemm<T, float>(st, 4 * H, H, (int)TB, W.dgates[k], 4 * H, 1, W.xh[k] + in, ld, 1, g.w_hh[k], H)));
-    B2C_TRY(colsum<T>(st, W.dgates[k], TB, 4 * H, 4 * H, W.partial, g.b_ih[k], g.b_hh[k]));
+    B2C_TRY((gemm<T, float>(st, 4 * H, in, (int)TB, W.dgates[k], 4 * H, 1, W.xh[k], ld, 1, g.w_ih[k], in, 0.f, nullptr, 0, 1.f, H)));
+    B2C_TRY((gemm<T, float>(st, 4 * H, H, (int)TB, W.dgates[k], 4 * H, 1, W.xh[k] + in, ld, 1, g.w_hh[k], H, 0.f, nullptr, 0, 1.f, H)));
+    B2C_TRY(colsum<T>(st, W.dgates[k], TB, 4 * H, 4 * H, W.partial, g.b_ih[k], g.b_hh[k], H));
+  }
+  {
+    // layer 0 with attention_combine folded in:  dW_x = dg0^T ctx,  dW_e = dg0^T emb,  db_x = colsum(dg0)
+    B2C_TRY((gemm<T, float>(st, 4 * H, E, (int)TB, W.dgates[0], 4 * H, 1, W.xh[0], E + H, 1, W.dWx32, E)));
+    B2C_TRY((gemm<T, float>(st, 4 * H, E, (int)TB, W.dgates[0], 4 * H, 1, W.emb, E, 1, W.dWe32, E)));
+    B2C_TRY((gemm<T, float>(st, 4 * H, H, (int)TB, W.dgates[0], 4 * H, 1, W.xh[0] + E, E + H, 1, g.w_hh[0], H, 0.f, nullptr, 0, 1.f, H)));
+    B2C_TRY(colsum<T>(st, W.dgates[0], TB, 4 * H, 4 * H, W.partial, g.b_ih[0], g.b_hh[0], H));
+    cast_f32_kernel<T><<<ew_grid((long)4 * H * E / 8), 256, 0, st>>>(W.dWx32, W.dWxT, (long)4 * H * E);
+    B2C_LAUNCH_CHECK("cast_f32_kernel");
+    cast_f32_kernel<T><<<ew_grid((long)4 * H * E / 8), 256, 0, st>>>(W.dWe32, W.dWeT, (long)4 * H * E);
+    B2C_LAUNCH_CHECK("cast_f32_kernel");
+    // dW_ih0 = dW_x W_cc^T + dW_e W_ce^T + db_x (x) b_c
+    B2C_TRY((gemm<T, float>(st, 4 * H, E, E, W.dWxT, E, 0, W.w.Wcc, E, 0, g.w_ih[0], E, 0.f, nullptr, 0, 1.f, H)));
+    B2C_TRY((gemm<T, float>(st, 4 * H, E, E, W.dWeT, E, 0, W.w.Wce, E, 0, g.w_ih[0], E, 1.f, nullptr, 0, 1.f, H)));
+    rank1_add_kernel<<<ew_grid((long)4 * H * E), 256, 0, st>>>(g.w_ih[0], g.b_ih[0], p.comb_b, (long)4 * H, E);
+    B2C_LAUNCH_CHECK("rank1_add_kernel");
+    // dW_c = [W_ih0^T dW_e | W_ih0^T dW_x],  db_c = W_ih0^T db_x
+    B2C_TRY((gemm<T, float>(st, E, E, 4 * H, W.w.Wih0, E, 1, W.dWeT, E, 1, g.comb_w, 2 * E)));
+    B2C_TRY((gemm<T, float>(st, E, E, 4 * H, W.w.Wih0, E, 1, W.dWxT, E, 1, g.comb_w + E, 2 * E)));
+    bias_fold_bwd_kernel<<<cdiv(E, 32), 256, 0, st>>>(p.w_ih[0], g.b_ih[0], 4 * H, E, g.comb_b);
+    B2C_LAUNCH_CHECK("bias_fold_bwd_kernel");
+    // embedding rows: demb = dg0 W_e
+    B2C_TRY((gemm<T, float>(st, (int)TB, E, 4 * H, W.dgates[0], 4 * H, 0, W.w.We, E, 1, W.demb, E)));
+    B2C_CUDA(cudaMemsetAsync(g.embedding, 0, (size_t)V * E * sizeof(float), st));
+    embedding_scatter_add_kernel<<<ew_grid(TB * E), 256, 0, st>>>(W.demb, cap, TB, E, V, g.embedding);
+    B2C_LAUNCH_CHECK("embedding_scatter_add_kernel");
   }
   const int inL = in_dim(s, L - 1), ldL = inL + H;
   B2C_TRY((gemm<T, float>(st, E, H, (int)TB, W.du, E, 1, W.xh[L - 1] + inL, ldL, 1, g.attn_w, H + E)));          // dW_a[:, :H]
   {
     const size_t smem = (size_t)Tn * (2 * E + 2 * S) * 4;
     B2C_TRY(set_smem(attn_post_kernel<T>, smem));
-    attn_post_kernel<T><<<B, ATT_THREADS, smem, st>>>(W.P, W.u, W.dctx, attw, W.ds, Tn, B, S, E, W.dP, dfeats);
+    attn_post_kernel<T><<<B, ATT_THREADS, smem, st>>>(W.P, W.u, W.dxh0, (long)(E + H), attw, W.ds, Tn, B, S, E, W.dP, dfeats);
     B2C_LAUNCH_CHECK("attn_post_kernel");
   }
   B2C_TRY((gemm<T, float>(st, E, E, B * S, W.dP, E, 1, feats, E, 1, g.attn_w + H, H + E)));                        // dW_a[:, H:]
   B2C_TRY(colsum<T>(st, W.dP, (long)B * S, E, E, W.partial, g.attn_b));
   B2C_TRY((gemm<T, float>(st, B * S, E, E, W.dP, E, 0, W.w.Wf, E, 1, dfeats, E, 1.f)));                             // dF += dP W_f
-  B2C_TRY((gemm<T, float>(st, E, E, (int)TB, W.dxh0, E + H, 1, W.emb, E, 1, g.comb_w, 2 * E)));                    // dW_c[:, :E]
-  B2C_TRY((gemm<T, float>(st, E, E, (int)TB, W.dxh0, E + H, 1, W.ctx, E, 1, g.comb_w + E, 2 * E)));                // dW_c[:, E:]
-  B2C_TRY(colsum<T>(st, W.dxh0, TB, E, E + H, W.partial, g.comb_b));
-  B2C_TRY((gemm<T, float>(st, (int)TB, E, E, W.dxh0, E + H, 0, W.w.Wce, E, 1, W.demb, E)));
-  B2C_CUDA(cudaMemsetAsync(g.embedding, 0, (size_t)V * E * sizeof(float), st));
-  embedding_scatter_add_kernel<<<ew_grid(TB * E), 256, 0, st>>>(W.demb, cap, TB, E, V, g.embedding);
-  B2C_LAUNCH_CHECK("embedding_scatter_add_kernel");
   return 0;
 }
+
 
 // ------------------------------------------------------------------ greedy decode (eval, argmax fed back on device)
 template <typename T>
@@ -382,25 +426,28 @@ int greedy_decode_impl(const B2CShape& s, const B2CParams& p, const T* feats, in
   B2C_TRY(pack_params<T>(s, p, W.w, st));
   B2C_TRY((gemm<T, float>(st, B * S, E, E, feats, E, 0, W.w.Wf, E, 0, W.P, E, 0.f, p.attn_b)));
   for (int k = 0; k < L; ++k) {
-    B2C_CUDA(cudaMemsetAsync(W.xh[k], 0, (size_t)B * (in_dim(s, k) + H) * sizeof(T), st));
+    B2C_CUDA(cudaMemsetAsync(W.xh[k], 0, (size_t)2 * B * (in_dim(s, k) + H) * sizeof(T), st));
     B2C_CUDA(cudaMemsetAsync(W.c[k], 0, (size_t)B * H * sizeof(float), st));
   }
   fill_i64_kernel<<<ew_grid(B), 256, 0, st>>>(W.cur, B, start_id);
   B2C_LAUNCH_CHECK("fill_i64_kernel");
   const int inL = in_dim(s, L - 1), ldL = inL + H;
   for (int t = 0; t < Tn; ++t) {
+    // The fused cell writes h_t while other CTAs of the same gate GEMM still read [input ; h_{t-1}]: two slots per layer,
+    // step t reads slot t & 1 and writes the recurrent h into the other one.
+    const int pcur = t & 1, pnxt = pcur ^ 1;
+    auto slot = [&](int k, int which) { return W.xh[k] + (size_t)which * B * (in_dim(s, k) + H); };
     embedding_gather_kernel<T><<<ew_grid((long)B * E / 4), 256, 0, st>>>(p.embedding, W.cur, B, E, V, W.emb, E);
     B2C_LAUNCH_CHECK("embedding_gather_kernel");
-    B2C_TRY((gemm<T, T>(st, B, E, E, W.emb, E, 0, W.w.Wce, E, 0, W.xh[0], E + H, 0.f, p.comb_b)));
-    B2C_TRY((gemm<T, float>(st, B, E, H, W.xh[L - 1] + inL, ldL, 0, W.w.Wh, H, 0, W.u, E)));
-    B2C_TRY(attn_fwd<T>(st, s, W.P, feats, W.u, W.ctx, nullptr));
-    B2C_TRY((gemm<T, T>(st, B, E, E, W.ctx, E, 0, W.w.Wcc, E, 0, W.xh[0], E + H, 1.f)));
+    B2C_TRY((gemm<T, T>(st, B, 4 * H, E, W.emb, E, 0, W.w.We, E, 0, W.G0, 4 * H, 0.f, W.w.bx)));
+    B2C_TRY((gemm<T, float>(st, B, E, H, slot(L - 1, pcur) + inL, ldL, 0, W.w.Wh, H, 0, W.u, E)));
+    B2C_TRY(attn_fwd<T>(st, s, W.P, feats, W.u, slot(0, pcur), E + H, nullptr));
     for (int k = 0; k < L; ++k) {
       const int in = in_dim(s, k);
-      B2C_TRY(lstm_layer_fwd<T>(st, s, W.w, k, W.xh[k], W.pre, W.c[k], W.c[k], (T*)nullptr, W.xh[k] + in,
-                                k + 1 < L ? W.xh[k + 1] : nullptr, (T*)nullptr, nodrop, 0));
+      B2C_TRY(lstm_layer_fwd<T>(st, s, W.w, k, slot(k, pcur), k == 0 ? W.G0 : (const T*)nullptr, W.c[k], W.c[k], (T*)nullptr, slot(k, pnxt) + in,
+                                k + 1 < L ? slot(k + 1, pcur) : nullptr, (T*)nullptr, nodrop, 0));
     }
-    B2C_TRY((gemm<T, T>(st, B, E, H, W.xh[L - 1] + inL, ldL, 0, W.w.W1, H, 0, W.o1, E, 0.f, p.out0_b, 1)));
+    B2C_TRY((gemm<T, T>(st, B, E, H, slot(L - 1, pnxt) + inL, ldL, 0, W.w.W1, H, 0, W.o1, E, 0.f, p.out0_b, 1)));
     B2C_TRY((gemm<T, float>(st, B, V, E, W.o1, E, 0, W.w.W2, E, 0, W.logits, V, 0.f, p.out3_b)));
     argmax_feedback_kernel<<<B, 256, 0, st>>>(W.logits, V, V, end_id, t, W.cur, tokens + (long)t * B, lengths, W.done);
     B2C_LAUNCH_CHECK("argmax_feedback_kernel");
@@ -409,6 +456,7 @@ int greedy_decode_impl(const B2CShape& s, const B2CParams& p, const T* feats, in
   B2C_LAUNCH_CHECK("finish_lengths_kernel");
   return 0;
 }
+
 
 template <typename T> struct AttnWs {
   T *Wh, *Wf; float *P, *u; size_t bytes;
@@ -433,7 +481,7 @@ int attention_step_impl(const B2CShape& s, const float* attn_w, const float* att
   B2C_LAUNCH_CHECK("pack_params_kernel");
   B2C_TRY((gemm<T, float>(st, B * S, E, E, feats, E, 0, W.Wf, E, 0, W.P, E, 0.f, attn_b)));
   B2C_TRY((gemm<T, float>(st, B, E, H, hidden, H, 0, W.Wh, H, 0, W.u, E)));
-  return attn_fwd<T>(st, s, W.P, feats, W.u, context, weights);
+  return attn_fwd<T>(st, s, W.P, feats, W.u, context, (long)s.E, weights);
 }
 
 // ------------------------------------------------------------------ AttentionRefinement / FeatureProjector

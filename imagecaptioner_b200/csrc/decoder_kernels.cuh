@@ -13,6 +13,7 @@ struct PackSeg {
   const float* src2;        // optional: dst = src + src2 (bias_ih + bias_hh)
   int rows, cols; long lds, ldd;
   int as_float;             // 1: dst is fp32 regardless of T (bias vectors)
+  int perm_h;               // != 0 (= H): gate-interleave the rows, dst row r <- src row (r & 3) * H + (r >> 2)
 };
 constexpr int PACK_MAX_SEGS = 20;
 struct PackTable { PackSeg seg[PACK_MAX_SEGS]; int n; };
@@ -23,8 +24,9 @@ __global__ void __launch_bounds__(256) pack_params_kernel(const __grid_constant_
   const long total = (long)s.rows * s.cols;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long r = i / s.cols; const int c = (int)(i - r * s.cols);
-    float v = s.src[r * s.lds + c];
-    if (s.src2) v += s.src2[r * s.lds + c];
+    const long rs = s.perm_h ? (long)(r & 3) * s.perm_h + (r >> 2) : r;
+    float v = s.src[rs * s.lds + c];
+    if (s.src2) v += s.src2[rs * s.lds + c];
     if (s.as_float) reinterpret_cast<float*>(s.dst)[r * s.ldd + c] = v;
     else reinterpret_cast<T*>(s.dst)[r * s.ldd + c] = from_f<T>(v);
   }
@@ -209,7 +211,7 @@ attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
 // u/dctx/w/ds for all T steps of this sample sit in shared memory (T*(2E+2S) floats).
 template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS)
-attn_post_kernel(const float* __restrict__ P, const float* __restrict__ u /*(T,B,E)*/, const T* __restrict__ dctx /*(T,B,E)*/,
+attn_post_kernel(const float* __restrict__ P, const float* __restrict__ u /*(T,B,E)*/, const T* __restrict__ dctx /*(T,B,.) pitch lddctx*/, long lddctx,
                  const float* __restrict__ attw /*(T,B,S)*/, const float* __restrict__ ds /*(T,B,S)*/,
                  int Tn, int B, int S, int E, T* __restrict__ dP, float* __restrict__ dF) {
   extern __shared__ __align__(128) unsigned char att_smem[];
@@ -218,7 +220,7 @@ attn_post_kernel(const float* __restrict__ P, const float* __restrict__ u /*(T,B
   float* ws = dcs + (long)Tn * E;                      // Tn*S
   float* dss = ws + (long)Tn * S;                      // Tn*S
   const int tid = threadIdx.x, b = blockIdx.x;
-  for (int i = tid; i < Tn * E; i += ATT_THREADS) { const int t = i / E, e = i - t * E; us[i] = u[((long)t * B + b) * E + e]; dcs[i] = to_f<T>(dctx[((long)t * B + b) * E + e]); }
+  for (int i = tid; i < Tn * E; i += ATT_THREADS) { const int t = i / E, e = i - t * E; us[i] = u[((long)t * B + b) * E + e]; dcs[i] = to_f<T>(dctx[((long)t * B + b) * lddctx + e]); }
   for (int i = tid; i < Tn * S; i += ATT_THREADS) { const int t = i / S, l = i - t * S; ws[i] = attw[((long)t * B + b) * S + l]; dss[i] = ds[((long)t * B + b) * S + l]; }
   __syncthreads();
   const long base = (long)b * S * E;
@@ -237,7 +239,42 @@ attn_post_kernel(const float* __restrict__ P, const float* __restrict__ u /*(T,B
 }
 
 // ======================================================================================
-// LSTM cell pointwise (gate order i,f,g,o; pre already holds both biases)
+// attention_combine folded into layer 0 (oracle/manual_backward.py v2):  b_x = W_ih0 b_c + b_ih0 + b_hh0  (interleaved rows),
+// and the pieces of its adjoint that are not contractions:  db_c = W_ih0^T db_x,  dW_ih0 += db_x (x) b_c   (natural row order)
+// ======================================================================================
+__global__ void __launch_bounds__(256)
+bias_fold_kernel(const float* __restrict__ w_ih0, const float* __restrict__ b_c, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                 int H, int E, float* __restrict__ bx) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= 4 * H) return;
+  const int src = (warp & 3) * H + (warp >> 2);           // interleaved row `warp` <- gate-major row `src`
+  float a = 0.f;
+  for (int e = lane; e < E; e += 32) a = fmaf(w_ih0[(long)src * E + e], b_c[e], a);
+  a = warp_sum(a);
+  if (lane == 0) bx[warp] = a + b_ih[src] + b_hh[src];
+}
+// db_c[e] = sum_n W_ih0[n,e] dbx[n]     (one block per 32 columns, 8 row lanes)
+__global__ void __launch_bounds__(256)
+bias_fold_bwd_kernel(const float* __restrict__ w_ih0, const float* __restrict__ dbx, int H4, int E, float* __restrict__ db_c) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, e = blockIdx.x * 32 + tx;
+  float a = 0.f;
+  if (e < E) for (int n = ty; n < H4; n += 8) a = fmaf(w_ih0[(long)n * E + e], dbx[n], a);
+  red[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && e < E) { float s = 0.f; for (int i = 0; i < 8; ++i) s += red[i][tx]; db_c[e] = s; }
+}
+// dW[n,e] += dbx[n] * b_c[e]
+__global__ void __launch_bounds__(256)
+rank1_add_kernel(float* __restrict__ dW, const float* __restrict__ dbx, const float* __restrict__ b_c, long rows, int E) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * E; i += (long)gridDim.x * blockDim.x) {
+    const long n = i / E; const int e = (int)(i - n * E);
+    dW[i] = fmaf(dbx[n], b_c[e], dW[i]);
+  }
+}
+
+// ======================================================================================
+// LSTM cell pointwise.  Gate storage is INTERLEAVED: element (b, 4j+g) is gate g (i,f,g,o) of hidden unit j.
 // ======================================================================================
 // h goes to up to three places: the recurrent slot (next step's [input;h] row block), the next layer's input
 // (inter-layer dropout applied in training) and the top-layer output buffer.
@@ -253,15 +290,15 @@ lstm_pointwise_fwd_kernel(const float* __restrict__ pre, const float* __restrict
   const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const long b = idx / H; const int j = (int)(idx - b * H);
-    const float* pr = pre + b * 4 * H;
-    const float i = Math<T>::sigmoid_(pr[j]), f = Math<T>::sigmoid_(pr[H + j]);
-    const float g = Math<T>::tanh_(pr[2 * H + j]), o = Math<T>::sigmoid_(pr[3 * H + j]);
+    const float* pr = pre + b * 4 * H + 4 * j;
+    const float i = Math<T>::sigmoid_(pr[0]), f = Math<T>::sigmoid_(pr[1]);
+    const float g = Math<T>::tanh_(pr[2]), o = Math<T>::sigmoid_(pr[3]);
     const float c = fmaf(f, c_prev[idx], i * g);
     const float h = o * Math<T>::tanh_(c);
     c_out[idx] = c;
     if (gates_out) {
-      T* go = gates_out + b * 4 * H;
-      go[j] = from_f<T>(i); go[H + j] = from_f<T>(f); go[2 * H + j] = from_f<T>(g); go[3 * H + j] = from_f<T>(o);
+      T* go = gates_out + b * 4 * H + 4 * j;
+      go[0] = from_f<T>(i); go[1] = from_f<T>(f); go[2] = from_f<T>(g); go[3] = from_f<T>(o);
     }
     if (h_rec) h_rec[b * ld_rec + j] = from_f<T>(h);
     if (h_next) {
@@ -295,15 +332,15 @@ lstm_pointwise_bwd_kernel(const T* __restrict__ gates, const float* __restrict__
     if (dh_ext) dh += dh_ext[idx];
     if (dh_hid) dh += to_f<T>(dh_hid[idx]);
     if (dh_q) dh += to_f<T>(dh_q[b * ld_q + j]);
-    const T* gt = gates + b * 4 * H;
-    const float i = to_f<T>(gt[j]), f = to_f<T>(gt[H + j]), g = to_f<T>(gt[2 * H + j]), o = to_f<T>(gt[3 * H + j]);
+    const T* gt = gates + b * 4 * H + 4 * j;
+    const float i = to_f<T>(gt[0]), f = to_f<T>(gt[1]), g = to_f<T>(gt[2]), o = to_f<T>(gt[3]);
     const float tc = Math<T>::tanh_(c_cur[idx]);
     const float dcc = (dc_is_zero ? 0.f : dc[idx]) + dh * o * (1.0f - tc * tc);
-    T* dg = dgates + b * 4 * H;
-    dg[j] = from_f<T>(dcc * g * i * (1.0f - i));
-    dg[H + j] = from_f<T>(dcc * c_prev[idx] * f * (1.0f - f));
-    dg[2 * H + j] = from_f<T>(dcc * i * (1.0f - g * g));
-    dg[3 * H + j] = from_f<T>(dh * tc * o * (1.0f - o));
+    T* dg = dgates + b * 4 * H + 4 * j;
+    dg[0] = from_f<T>(dcc * g * i * (1.0f - i));
+    dg[1] = from_f<T>(dcc * c_prev[idx] * f * (1.0f - f));
+    dg[2] = from_f<T>(dcc * i * (1.0f - g * g));
+    dg[3] = from_f<T>(dh * tc * o * (1.0f - o));
     dc[idx] = dcc * f;
   }
 }
@@ -344,13 +381,15 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
     partial[(long)blockIdx.y * cols + col] = s;
   }
 }
-__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int RS, int cols, float* __restrict__ out, float* __restrict__ out2) {
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int RS, int cols, float* __restrict__ out, float* __restrict__ out2,
+                                                           int unperm_h = 0) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= cols) return;
   float s = 0.f;
   for (int r = 0; r < RS; ++r) s += partial[(long)r * cols + col];
-  out[col] = s;
-  if (out2) out2[col] = s;
+  const int oc = unperm_h ? (col & 3) * unperm_h + (col >> 2) : col;      // interleaved gate column -> gate-major index
+  out[oc] = s;
+  if (out2) out2[oc] = s;
 }
 
 // Greedy feedback: tok[b] = argmax_v logits[b,v] (lowest index on ties, like torch.argmax); records the step's

@@ -21,6 +21,31 @@
 namespace b2c {
 
 // ======================================================================================
+// Fused LSTM-cell epilogue.  With the gate rows of W_cat interleaved (row 4j+g = gate g of hidden unit j) four consecutive
+// output columns of the gate contraction are the i,f,g,o pre-activations of ONE unit, so the epilogue that already holds
+// them in registers finishes the cell: adds bias / the time-batched embedding addend, applies the gates, updates c in fp32
+// and scatters h to the recurrent slot, the next layer's input (inter-layer dropout) and the top-layer output.
+// ======================================================================================
+struct LstmEpi {
+  int enabled, H;
+  const void* addend;          // (rows, 4H) operand type, interleaved columns, or null
+  const float* bias;           // (4H) interleaved, or null
+  const float* c_prev; float* c_out;
+  void* gates_out;             // (rows, 4H) post-activation gates, interleaved (null in decode)
+  void* h_rec; long ld_rec; void* h_next; long ld_next; void* h_top; long ld_top;
+  float drop_p; unsigned long long seed; unsigned int site; long row_base;
+};
+
+// one hidden unit: pre[4] = i,f,g,o pre-activations (bias/addend already added) -> act[4], c, h
+template <typename TL>
+__device__ __forceinline__ void lstm_cell_unit(const float (&pre)[4], float c_prev, float (&act)[4], float& c, float& h) {
+  act[0] = Math<TL>::sigmoid_(pre[0]); act[1] = Math<TL>::sigmoid_(pre[1]);
+  act[2] = Math<TL>::tanh_(pre[2]);    act[3] = Math<TL>::sigmoid_(pre[3]);
+  c = fmaf(act[1], c_prev, act[0] * act[2]);
+  h = act[3] * Math<TL>::tanh_(c);
+}
+
+// ======================================================================================
 // SIMT fp32-accumulate GEMM (any operand type, any majorness)
 // ======================================================================================
 constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
@@ -29,7 +54,7 @@ template <typename TA, typename TB, typename TC>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(int M, int N, int K, float alpha, const TA* __restrict__ A, long lda, int a_mn,
                  const TB* __restrict__ B, long ldb, int b_mn, float beta, TC* __restrict__ C, long ldc,
-                 const float* __restrict__ bias, int relu) {
+                 const float* __restrict__ bias, int relu, int row_unperm_h, const __grid_constant__ LstmEpi le) {
   __shared__ float As[SG_BK][SG_BM + 4];
   __shared__ float Bs[SG_BK][SG_BN + 4];
   pdl_launch_dependents();
@@ -79,10 +104,41 @@ gemm_simt_kernel(int M, int N, int K, float alpha, const TA* __restrict__ A, lon
     }
     __syncthreads();
   }
+  if (le.enabled) {                          // this thread's 4 columns are the 4 gates of hidden unit `unit` (N = 4H, N % 4 == 0)
+    const int gn = n0 + tx * 4, unit = gn >> 2, H = le.H;
+    if (gn >= N) return;
+    const float inv_keep = le.drop_p > 0.f ? 1.0f / (1.0f - le.drop_p) : 1.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gm = m0 + ty * 4 + i;
+      if (gm >= M) continue;
+      float pre[4], act[4], c, h;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        pre[j] = acc[i][j];
+        if (le.bias) pre[j] += le.bias[gn + j];
+        if (le.addend) pre[j] += to_f<TA>(reinterpret_cast<const TA*>(le.addend)[(long)gm * N + gn + j]);
+      }
+      lstm_cell_unit<TA>(pre, le.c_prev[(long)gm * H + unit], act, c, h);
+      le.c_out[(long)gm * H + unit] = c;
+      if (le.gates_out) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) reinterpret_cast<TA*>(le.gates_out)[(long)gm * N + gn + j] = from_f<TA>(act[j]);
+      }
+      if (le.h_rec) reinterpret_cast<TA*>(le.h_rec)[(long)gm * le.ld_rec + unit] = from_f<TA>(h);
+      if (le.h_next) {
+        const float m = le.drop_p > 0.f ? dropout_scale(le.seed, le.site, (uint64_t)((le.row_base + gm) * H + unit), le.drop_p, inv_keep) : 1.0f;
+        reinterpret_cast<TA*>(le.h_next)[(long)gm * le.ld_next + unit] = from_f<TA>(h * m);
+      }
+      if (le.h_top) reinterpret_cast<TA*>(le.h_top)[(long)gm * le.ld_top + unit] = from_f<TA>(h);
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int gm = m0 + ty * 4 + i;
     if (gm >= M) continue;
+    const long orow = row_unperm_h ? (long)(gm & 3) * row_unperm_h + (gm >> 2) : (long)gm;     // interleaved row -> gate-major row
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gn = n0 + tx * 4 + j;
@@ -90,8 +146,8 @@ gemm_simt_kernel(int M, int N, int K, float alpha, const TA* __restrict__ A, lon
       float v = alpha * acc[i][j];
       if (bias) v += bias[gn];
       if (relu) v = fmaxf(v, 0.f);
-      if (beta != 0.f) v += beta * to_f<TC>(C[(long)gm * ldc + gn]);
-      C[(long)gm * ldc + gn] = from_f<TC>(v);
+      if (beta != 0.f) v += beta * to_f<TC>(C[orow * ldc + gn]);
+      C[orow * ldc + gn] = from_f<TC>(v);
     }
   }
 }
@@ -186,7 +242,8 @@ template <int BN, bool A_MN, bool B_MN, typename TC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, float alpha, float beta, TC* __restrict__ C, long ldc,
-               const float* __restrict__ bias, int relu, int kb_per_split, int tiles_m, int tiles_n, int splits) {
+               const float* __restrict__ bias, int relu, int kb_per_split, int tiles_m, int tiles_n, int splits,
+               int row_unperm_h, const __grid_constant__ LstmEpi le) {
   using Cfg = TcCfg<BN>;
   constexpr int TC_STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_dyn[];
@@ -301,6 +358,71 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(&tfull_bar[as], aph);
     tc_fence_after();
     const uint32_t tacc = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(q * 32) << 16);
+    if (le.enabled) {
+      // ---- fused LSTM cell: 32 accumulator columns = 8 hidden units x (i,f,g,o); straight from TMEM to the cell state buffers
+      const int H = le.H, N4 = N;                        // N == 4H
+      const int grow = m0 + q * 32 + lane;
+      const float inv_keep = le.drop_p > 0.f ? 1.0f / (1.0f - le.drop_p) : 1.0f;
+      constexpr int NC32 = BN / 32, C32_PER = (NC32 + 1) / 2;
+#pragma unroll 1
+      for (int ci = half * C32_PER; ci < (half + 1) * C32_PER && ci < NC32; ++ci) {
+        const int col0 = n0 + ci * 32;
+        if (col0 >= N) break;
+        float v[32];
+        tmem_ld32(tacc + (uint32_t)(ci * 32), v);
+        if (grow < M) {
+          if (le.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) { const float4 b4 = *reinterpret_cast<const float4*>(le.bias + col0 + j); v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w; }
+          }
+          if (le.addend) {
+            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(le.addend) + (long)grow * N4 + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 a = ap[j];
+              v[j * 8 + 0] += bf16_lo(a.x); v[j * 8 + 1] += bf16_hi(a.x); v[j * 8 + 2] += bf16_lo(a.y); v[j * 8 + 3] += bf16_hi(a.y);
+              v[j * 8 + 4] += bf16_lo(a.z); v[j * 8 + 5] += bf16_hi(a.z); v[j * 8 + 6] += bf16_lo(a.w); v[j * 8 + 7] += bf16_hi(a.w);
+            }
+          }
+          const int u0 = col0 >> 2;
+          const float4 cp0 = *reinterpret_cast<const float4*>(le.c_prev + (long)grow * H + u0);
+          const float4 cp1 = *reinterpret_cast<const float4*>(le.c_prev + (long)grow * H + u0 + 4);
+          const float cp[8] = {cp0.x, cp0.y, cp0.z, cp0.w, cp1.x, cp1.y, cp1.z, cp1.w};
+          float cn[8], hn[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float pre[4] = {v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]}, act[4];
+            lstm_cell_unit<bf16>(pre, cp[u], act, cn[u], hn[u]);
+            v[4 * u] = act[0]; v[4 * u + 1] = act[1]; v[4 * u + 2] = act[2]; v[4 * u + 3] = act[3];
+          }
+          *reinterpret_cast<float4*>(le.c_out + (long)grow * H + u0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          *reinterpret_cast<float4*>(le.c_out + (long)grow * H + u0 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+          if (le.gates_out) {
+            uint4* gp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(le.gates_out) + (long)grow * N4 + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              gp[j] = make_uint4(pack_bf16(v[j * 8], v[j * 8 + 1]), pack_bf16(v[j * 8 + 2], v[j * 8 + 3]), pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
+          }
+          const uint4 hp = make_uint4(pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]), pack_bf16(hn[4], hn[5]), pack_bf16(hn[6], hn[7]));
+          if (le.h_rec) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(le.h_rec) + (long)grow * le.ld_rec + u0) = hp;
+          if (le.h_top) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(le.h_top) + (long)grow * le.ld_top + u0) = hp;
+          if (le.h_next) {
+            uint4 hd = hp;
+            if (le.drop_p > 0.f) {
+              float hm[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) hm[u] = hn[u] * dropout_scale(le.seed, le.site, (uint64_t)((le.row_base + grow) * H + u0 + u), le.drop_p, inv_keep);
+              hd = make_uint4(pack_bf16(hm[0], hm[1]), pack_bf16(hm[2], hm[3]), pack_bf16(hm[4], hm[5]), pack_bf16(hm[6], hm[7]));
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(le.h_next) + (long)grow * le.ld_next + u0) = hd;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      continue;
+    }
     constexpr int NCHUNK = BN / CH;                      // 128-byte column chunks per tile row
     constexpr int C_PER = (NCHUNK + 1) / 2;
 #pragma unroll 1
@@ -337,7 +459,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int grow = m0 + q * 32 + r, gcol = n0 + c0 + part * PER;
         if (grow < M && gcol < N) {
           const uint4 acc = *reinterpret_cast<const uint4*>(my + r * TC_EPI_PITCH + part * 16);
-          TC* cp = C + (long)grow * ldc + gcol;
+          const long orow = row_unperm_h ? (long)(grow & 3) * row_unperm_h + (grow >> 2) : (long)grow;   // interleaved -> gate-major row
+          TC* cp = C + orow * ldc + gcol;
           if (split) {
             const float* a = reinterpret_cast<const float*>(&acc);
 #pragma unroll
@@ -416,6 +539,8 @@ struct GemmArgs {
   const void* B; long ldb; int b_mn;
   void* C; long ldc;
   const float* bias; int relu;
+  int row_unperm_h = 0;              // != 0: output row m is written to row (m & 3) * H + (m >> 2) (gate-interleaved -> gate-major)
+  const LstmEpi* lstm = nullptr;     // fused LSTM-cell epilogue instead of writing C
 };
 
 inline bool tc_eligible(const GemmArgs& g) {
@@ -428,7 +553,7 @@ inline bool tc_eligible(const GemmArgs& g) {
 struct TcPlan { int bn, splits, kb_per_split; };
 inline TcPlan plan_tc(const GemmArgs& g, int elem_c, int sms) {
   const int num_kb = cdiv(g.K, TC_BK);
-  const bool can_split = (elem_c == 4) && !g.relu && (g.beta == 0.f || g.beta == 1.f);
+  const bool can_split = (elem_c == 4) && !g.relu && (g.beta == 0.f || g.beta == 1.f) && (g.lstm == nullptr);
   TcPlan best{64, 1, num_kb}; double best_cost = 1e30;
   const int cand[3] = {256, 128, 64};
   for (int ci = 0; ci < 3; ++ci) {
@@ -473,7 +598,7 @@ int launch_tc(const GemmArgs& g, const TcPlan& plan, cudaStream_t st) {
   const long total = (long)tiles_m * tiles_n * splits;
   const int grid = (int)(total < sm_count() ? total : sm_count());
   B2C_CUDA(launch_pdl(kern, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES, st, ta, tb, g.M, g.N, g.K, g.alpha, g.beta, (TC*)g.C, g.ldc,
-                      g.bias, g.relu, kb_per_split, tiles_m, tiles_n, splits));
+                      g.bias, g.relu, kb_per_split, tiles_m, tiles_n, splits, g.row_unperm_h, g.lstm ? *g.lstm : LstmEpi{}));
   B2C_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -499,7 +624,7 @@ template <typename TA, typename TB, typename TC>
 int gemm_simt(const GemmArgs& g, cudaStream_t st) {
   dim3 grid(cdiv(g.N, SG_BN), cdiv(g.M, SG_BM));
   B2C_CUDA(launch_pdl(gemm_simt_kernel<TA, TB, TC>, grid, dim3(256), 0, st, g.M, g.N, g.K, g.alpha, (const TA*)g.A, g.lda, g.a_mn,
-                      (const TB*)g.B, g.ldb, g.b_mn, g.beta, (TC*)g.C, g.ldc, g.bias, g.relu));
+                      (const TB*)g.B, g.ldb, g.b_mn, g.beta, (TC*)g.C, g.ldc, g.bias, g.relu, g.row_unperm_h, g.lstm ? *g.lstm : LstmEpi{}));
   B2C_LAUNCH_CHECK("gemm_simt_kernel");
   return 0;
 }

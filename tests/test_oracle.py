@@ -90,6 +90,30 @@ def test_manual_backward_blueprint_matches_autograd(dims):
         assert relerr(G[k], P[k].grad) < 1e-10, k
 
 
+@pytest.mark.parametrize("dims", [(4, 6, 104, 32, 64, 2), (3, 5, 203, 48, 96, 3), (2, 3, 57, 16, 24, 1)])
+def test_manual_backward_v2_fold_matches_autograd(dims):
+    """v2 dataflow (attention_combine folded into layer 0's gate contraction — what csrc/api.cu runs) vs autograd."""
+    B, T, V, E, H, L = dims
+    p = {k: v.double() for k, v in O.init_student_params(V, E, H, L, False, seed=3).items()}
+    gen = torch.Generator().manual_seed(1)
+    for k in p:
+        if "bias" in k:
+            p[k] = torch.randn(p[k].shape, generator=gen, dtype=torch.float64) * 0.05
+    b = O.synthetic_batch(B, T, V, E, H, seed=5)
+    feats, caps = b["encoder_features"].double(), b["captions_input"]
+    P = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    f = feats.clone().requires_grad_(True)
+    out, hids, atts = O.decoder_forward(P, f, caps)
+    dlog, dh = torch.randn(out.shape, generator=gen, dtype=torch.float64), torch.randn(T, B, H, generator=gen, dtype=torch.float64)
+    ((out * dlog).sum() + sum((hids[t] * dh[t]).sum() for t in range(T))).backward()
+    lg, hid, w, sv = M.decoder_forward_saved_v2(p, feats, caps)
+    assert relerr(lg, out.detach()) < 1e-12 and relerr(w, torch.stack(atts).detach()) < 1e-12
+    G, dF = M.decoder_backward_manual_v2(p, feats, caps, sv, dlog, dh)
+    assert relerr(dF, f.grad) < 1e-10
+    for k in P:
+        assert relerr(G[k], P[k].grad) < 1e-10, k
+
+
 def test_closed_form_token_gradient():
     torch.manual_seed(1)
     y = torch.randn(5, 3, 50, dtype=torch.float64, requires_grad=True)
