@@ -392,7 +392,8 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
     // dW_c = [W_ih0^T dW_e | W_ih0^T dW_x],  db_c = W_ih0^T db_x
     B2C_TRY((gemm<T, float>(st, E, E, 4 * H, W.w.Wih0, E, 1, W.dWeT, E, 1, g.comb_w, 2 * E)));
     B2C_TRY((gemm<T, float>(st, E, E, 4 * H, W.w.Wih0, E, 1, W.dWxT, E, 1, g.comb_w + E, 2 * E)));
-    bias_fold_bwd_kernel<<<cdiv(E, 32), 256, 0, st>>>(p.w_ih[0], g.b_ih[0], 4 * H, E, g.comb_b);
+    B2C_CUDA(cudaMemsetAsync(g.comb_b, 0, (size_t)E * sizeof(float), st));
+    bias_fold_bwd_kernel<<<dim3(cdiv(E, 32), 32), 256, 0, st>>>(p.w_ih[0], g.b_ih[0], 4 * H, E, g.comb_b);
     B2C_LAUNCH_CHECK("bias_fold_bwd_kernel");
     // embedding rows: demb = dg0 W_e
     B2C_TRY((gemm<T, float>(st, (int)TB, E, 4 * H, W.dgates[0], 4 * H, 0, W.w.We, E, 1, W.demb, E)));
@@ -485,7 +486,7 @@ int attention_step_impl(const B2CShape& s, const float* attn_w, const float* att
 }
 
 // ------------------------------------------------------------------ AttentionRefinement / FeatureProjector
-constexpr int LN_GRID = 148 * 2;
+constexpr int LN_GRID = 148 * 3;
 template <typename T> struct RefineWs {
   T *Win, *Wo, *W1, *W2;                                         // packed operand weights
   T *x, *qkv, *probs, *attn, *proj, *x1, *f1, *f2;               // forward saves
@@ -518,7 +519,8 @@ int check_refine_shape(const B2CShape* s) {
 template <typename TX, typename TY>
 int ln_fwd(cudaStream_t st, const TX* x, const TX* res, const float* g, const float* b, TY* y, float* mean, float* rstd, long R, int E) {
   long grid = (R + 7) / 8; if (grid > 148 * 8) grid = 148 * 8;
-  ln_fwd_kernel<TX, TY><<<(unsigned)grid, LN_THREADS, 0, st>>>(x, res, g, b, y, mean, rstd, R, E, 1e-5f);
+  if (E <= 256) ln_fwd_kernel<TX, TY, 1><<<(unsigned)grid, LN_THREADS, 0, st>>>(x, res, g, b, y, mean, rstd, R, E, 1e-5f);
+  else ln_fwd_kernel<TX, TY, 2><<<(unsigned)grid, LN_THREADS, 0, st>>>(x, res, g, b, y, mean, rstd, R, E, 1e-5f);
   B2C_LAUNCH_CHECK("ln_fwd_kernel");
   return 0;
 }
@@ -529,13 +531,11 @@ int ln_bwd(cudaStream_t st, const TDY* dy, const float* dpool, int L, int O, con
            const float* gamma, TDZ* dz, float* dz32, float* part, float* dgamma, float* dbeta, float* dbias_prev, long R, int E) {
   long grid = (R + 7) / 8; if (grid > LN_GRID) grid = LN_GRID;
   const size_t smem = (size_t)(LN_THREADS / 32) * 3 * E * 4;
-  if (dpool) {
-    B2C_TRY(set_smem(ln_bwd_kernel<TX, TDY, TDZ, true>, smem));
-    ln_bwd_kernel<TX, TDY, TDZ, true><<<(unsigned)grid, LN_THREADS, smem, st>>>(dy, dpool, L, O, x, res, mean, rstd, gamma, dz, dz32, part, R, E);
-  } else {
-    B2C_TRY(set_smem(ln_bwd_kernel<TX, TDY, TDZ, false>, smem));
-    ln_bwd_kernel<TX, TDY, TDZ, false><<<(unsigned)grid, LN_THREADS, smem, st>>>(dy, dpool, L, O, x, res, mean, rstd, gamma, dz, dz32, part, R, E);
-  }
+#define B2C_LNB(POOLED, NC) do { B2C_TRY(set_smem(ln_bwd_kernel<TX, TDY, TDZ, POOLED, NC>, smem)); \
+    ln_bwd_kernel<TX, TDY, TDZ, POOLED, NC><<<(unsigned)grid, LN_THREADS, smem, st>>>(dy, dpool, L, O, x, res, mean, rstd, gamma, dz, dz32, part, R, E); } while (0)
+  if (dpool) { if (E <= 256) B2C_LNB(true, 1); else B2C_LNB(true, 2); }
+  else { if (E <= 256) B2C_LNB(false, 1); else B2C_LNB(false, 2); }
+#undef B2C_LNB
   B2C_LAUNCH_CHECK("ln_bwd_kernel");
   ln_param_grad_kernel<<<cdiv(3 * E, 256), 256, 0, st>>>(part, (int)grid, E, dgamma, dbeta, dbias_prev);
   B2C_LAUNCH_CHECK("ln_param_grad_kernel");
@@ -683,7 +683,8 @@ int projector_forward_impl(const B2CShape& s, const B2CProjParams& p, const floa
   }
   {
     long grid = ((long)B * So + 7) / 8; if (grid > 148 * 8) grid = 148 * 8;
-    ln_pool_fwd_kernel<T><<<(unsigned)grid, LN_THREADS, 0, st>>>(W.h, p.ln_w, p.ln_b, out, W.mean, W.rstd, B, St, So, Es, 1e-5f);
+    if (Es <= 256) ln_pool_fwd_kernel<T, 1><<<(unsigned)grid, LN_THREADS, 0, st>>>(W.h, p.ln_w, p.ln_b, out, W.mean, W.rstd, B, St, So, Es, 1e-5f);
+    else ln_pool_fwd_kernel<T, 2><<<(unsigned)grid, LN_THREADS, 0, st>>>(W.h, p.ln_w, p.ln_b, out, W.mean, W.rstd, B, St, So, Es, 1e-5f);
     B2C_LAUNCH_CHECK("ln_pool_fwd_kernel");
   }
   return 0;

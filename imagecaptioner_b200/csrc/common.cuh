@@ -48,10 +48,14 @@ template <> struct Math<float> {
 };
 // bf16 mode: MUFU ex2/rcp based forms (abs error ~1e-7).  tanh.approx (rel 2^-11) is NOT used: the attention score is a sum
 // of E tanh values, and its error goes straight into the softmax weights and from there into ReLU-mask flips downstream.
+__device__ __forceinline__ float ex2_ftz_(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz_(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 template <> struct Math<bf16> {
-  static __device__ __forceinline__ float tanh_(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
-  static __device__ __forceinline__ float sigmoid_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-  static __device__ __forceinline__ float exp_(float x) { return __expf(x); }
+  // tanh(x) = 1 - 2 / (1 + e^{2x}),  sigmoid(x) = 1 / (1 + e^{-x}):  FMUL + MUFU.EX2 + FADD + MUFU.RCP + FFMA, no range fix-ups
+  // (x -> +inf: e^{2x} = inf, rcp = 0 -> 1;  x -> -inf: e^{2x} = 0 -> 1 - 2 = -1)
+  static __device__ __forceinline__ float tanh_(float x) { return fmaf(-2.0f, rcp_ftz_(1.0f + ex2_ftz_(2.8853900817779268f * x)), 1.0f); }
+  static __device__ __forceinline__ float sigmoid_(float x) { return rcp_ftz_(1.0f + ex2_ftz_(-1.4426950408889634f * x)); }
+  static __device__ __forceinline__ float exp_(float x) { return ex2_ftz_(1.4426950408889634f * x); }
   static __device__ __forceinline__ float log_(float x) { return __logf(x); }
 };
 

@@ -253,16 +253,18 @@ bias_fold_kernel(const float* __restrict__ w_ih0, const float* __restrict__ b_c,
   a = warp_sum(a);
   if (lane == 0) bx[warp] = a + b_ih[src] + b_hh[src];
 }
-// db_c[e] = sum_n W_ih0[n,e] dbx[n]     (one block per 32 columns, 8 row lanes)
+// db_c[e] = sum_n W_ih0[n,e] dbx[n]:  grid (ceil(E/32), row splits), 8 row lanes per block, partial sums added atomically
+// into a zeroed db_c (E floats)
 __global__ void __launch_bounds__(256)
 bias_fold_bwd_kernel(const float* __restrict__ w_ih0, const float* __restrict__ dbx, int H4, int E, float* __restrict__ db_c) {
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, e = blockIdx.x * 32 + tx;
+  const int per = (H4 + gridDim.y - 1) / gridDim.y, n0 = blockIdx.y * per, n1 = min(H4, n0 + per);
   float a = 0.f;
-  if (e < E) for (int n = ty; n < H4; n += 8) a = fmaf(w_ih0[(long)n * E + e], dbx[n], a);
+  if (e < E) for (int n = n0 + ty; n < n1; n += 8) a = fmaf(w_ih0[(long)n * E + e], dbx[n], a);
   red[ty][tx] = a;
   __syncthreads();
-  if (ty == 0 && e < E) { float s = 0.f; for (int i = 0; i < 8; ++i) s += red[i][tx]; db_c[e] = s; }
+  if (ty == 0 && e < E) { float s = 0.f; for (int i = 0; i < 8; ++i) s += red[i][tx]; atomicAdd(db_c + e, s); }
 }
 // dW[n,e] += dbx[n] * b_c[e]
 __global__ void __launch_bounds__(256)

@@ -52,13 +52,13 @@ template <> struct Vec8<float> {
 // ------------------------------------------------------------------ LayerNorm over the last dim (eps inside the sqrt, biased variance)
 // One warp per row; lane owns 8-element chunks lane, lane+32 (E % 8 == 0, E <= 512): coalesced 16-byte accesses.
 constexpr int LN_THREADS = 256;
-constexpr int LN_MAXC = 2;
+constexpr int LN_MAXC = 2;          // kernels are templated on NC = ceil(E / 256) <= LN_MAXC chunks per lane
 
-template <typename TX>
-__device__ __forceinline__ void ln_load_row(const TX* x, const TX* res, long r, int E, int nch, int lane, float (&v)[LN_MAXC][8], float& sum) {
+template <typename TX, int NC>
+__device__ __forceinline__ void ln_load_row(const TX* x, const TX* res, long r, int E, int nch, int lane, float (&v)[NC][8], float& sum) {
   sum = 0.f;
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; ++c) {
+  for (int c = 0; c < NC; ++c) {
     const int ch = lane + 32 * c;
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[c][j] = 0.f;
@@ -72,11 +72,12 @@ __device__ __forceinline__ void ln_load_row(const TX* x, const TX* res, long r, 
     }
   }
 }
-__device__ __forceinline__ void ln_stats(const float (&v)[LN_MAXC][8], float sum, int E, int nch, int lane, float eps, float& mu, float& rs) {
+template <int NC>
+__device__ __forceinline__ void ln_stats(const float (&v)[NC][8], float sum, int E, int nch, int lane, float eps, float& mu, float& rs) {
   mu = warp_sum(sum) / (float)E;
   float q = 0.f;
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; ++c) if (lane + 32 * c < nch) {
+  for (int c = 0; c < NC; ++c) if (lane + 32 * c < nch) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mu; q = fmaf(d, d, q); }
   }
@@ -84,18 +85,18 @@ __device__ __forceinline__ void ln_stats(const float (&v)[LN_MAXC][8], float sum
 }
 
 // y = LN(x + res) * gamma + beta
-template <typename TX, typename TY>
+template <typename TX, typename TY, int NC>
 __global__ void __launch_bounds__(LN_THREADS)
 ln_fwd_kernel(const TX* __restrict__ x, const TX* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ beta,
               TY* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, long R, int E, float eps) {
   const int lane = threadIdx.x & 31, wpb = LN_THREADS / 32, nch = E >> 3;
   for (long r = (long)blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += (long)gridDim.x * wpb) {
-    float v[LN_MAXC][8], sum, mu, rs;
-    ln_load_row<TX>(x, res, r, E, nch, lane, v, sum);
-    ln_stats(v, sum, E, nch, lane, eps, mu, rs);
+    float v[NC][8], sum, mu, rs;
+    ln_load_row<TX, NC>(x, res, r, E, nch, lane, v, sum);
+    ln_stats<NC>(v, sum, E, nch, lane, eps, mu, rs);
     if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
 #pragma unroll
-    for (int c = 0; c < LN_MAXC; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nch) {
         float g[8], b[8], o[8];
@@ -110,7 +111,7 @@ ln_fwd_kernel(const TX* __restrict__ x, const TX* __restrict__ res, const float*
 
 // FeatureProjector tail, fused: out[b,o,:] = mean over the token window of LN(x[b,l,:]) * gamma + beta.  One warp per (b,o);
 // rows shared by two windows are normalised twice (no (B,L,E) intermediate is written); mean / rstd kept per row.
-template <typename TX>
+template <typename TX, int NC>
 __global__ void __launch_bounds__(LN_THREADS)
 ln_pool_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
                    float* __restrict__ mean, float* __restrict__ rstd, int B, int L, int O, int E, float eps) {
@@ -119,25 +120,25 @@ ln_pool_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, co
   for (long w = (long)blockIdx.x * wpb + (threadIdx.x >> 5); w < total; w += (long)gridDim.x * wpb) {
     const long b = w / O; const int o = (int)(w - b * O);
     const int lo = (int)(((long)o * L) / O), hi = (int)(((long)(o + 1) * L + O - 1) / O);
-    float acc[LN_MAXC][8];
+    float acc[NC][8];
 #pragma unroll
-    for (int c = 0; c < LN_MAXC; ++c)
+    for (int c = 0; c < NC; ++c)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
     for (int l = lo; l < hi; ++l) {
       const long r = b * L + l;
-      float v[LN_MAXC][8], sum, mu, rs;
-      ln_load_row<TX>(x, (const TX*)nullptr, r, E, nch, lane, v, sum);
-      ln_stats(v, sum, E, nch, lane, eps, mu, rs);
+      float v[NC][8], sum, mu, rs;
+      ln_load_row<TX, NC>(x, (const TX*)nullptr, r, E, nch, lane, v, sum);
+      ln_stats<NC>(v, sum, E, nch, lane, eps, mu, rs);
       if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
 #pragma unroll
-      for (int c = 0; c < LN_MAXC; ++c)
+      for (int c = 0; c < NC; ++c)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[c][j] += (v[c][j] - mu) * rs;
     }
     const float inv = 1.0f / (float)(hi - lo);
 #pragma unroll
-    for (int c = 0; c < LN_MAXC; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nch) {
         float g[8], bb[8], o8[8];
@@ -154,25 +155,25 @@ ln_pool_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, co
 // dy comes either from `dy` or, for the projector (POOLED), from the pooled output gradient: dy[b,l,:] = sum over windows o
 // containing l of dpool[b,o,:] / len(o).  Per-CTA partial sums of dgamma = sum_r dy*xhat, dbeta = sum_r dy and (the bias
 // gradient of the Linear in front) sum_r dz go to part[(blockIdx, {0,1,2}, e)].
-template <typename TX, typename TDY, typename TDZ, bool POOLED>
-__global__ void __launch_bounds__(LN_THREADS)
+template <typename TX, typename TDY, typename TDZ, bool POOLED, int NC>
+__global__ void __launch_bounds__(LN_THREADS, NC == 1 ? 3 : 2)
 ln_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ dpool, int L, int O,
               const TX* __restrict__ x, const TX* __restrict__ res, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, TDZ* __restrict__ dz, float* __restrict__ dz32,
               float* __restrict__ part, long R, int E) {
   extern __shared__ float ln_sm[];          // [wpb][3][E]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = LN_THREADS / 32, nch = E >> 3;
-  float ag[LN_MAXC][8], ab[LN_MAXC][8], az[LN_MAXC][8], gm[LN_MAXC][8];
+  float ag[NC][8], ab[NC][8], az[NC][8], gm[NC][8];
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; ++c) {
+  for (int c = 0; c < NC; ++c) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { ag[c][j] = 0.f; ab[c][j] = 0.f; az[c][j] = 0.f; gm[c][j] = 0.f; }
     if (lane + 32 * c < nch) Vec8<float>::load(gamma + (lane + 32 * c) * 8, gm[c]);
   }
   for (long r = (long)blockIdx.x * wpb + warp; r < R; r += (long)gridDim.x * wpb) {
     const float mu = mean[r], rs = rstd[r];
-    float v[LN_MAXC][8], d[LN_MAXC][8], sum;
-    ln_load_row<TX>(x, res, r, E, nch, lane, v, sum);
+    float v[NC][8], d[NC][8], sum;
+    ln_load_row<TX, NC>(x, res, r, E, nch, lane, v, sum);
     int o_min = 0, o_max = -1; long bo = 0;
     if (POOLED) {
       const long b = r / L; const int l = (int)(r - b * L);
@@ -180,7 +181,7 @@ ln_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ dpool, int L
     }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < LN_MAXC; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int ch = lane + 32 * c;
 #pragma unroll
       for (int j = 0; j < 8; ++j) d[c][j] = 0.f;
@@ -207,7 +208,7 @@ ln_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ dpool, int L
     }
     const float m1 = warp_sum(s1) / (float)E, m2 = warp_sum(s2) / (float)E;
 #pragma unroll
-    for (int c = 0; c < LN_MAXC; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nch) {
         float o8[8];
@@ -219,7 +220,7 @@ ln_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ dpool, int L
     }
   }
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; ++c) {
+  for (int c = 0; c < NC; ++c) {
     const int ch = lane + 32 * c;
     if (ch < nch) {
 #pragma unroll
