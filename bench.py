@@ -322,6 +322,39 @@ def finish(world):
         os._exit(0)
 
 
+def run_decode(args):
+    """BASELINE configs[3]: greedy caption decode, batch 2048, max length 30 (one device-side decode per step of this leg).
+    Reports captions/s and tokens/s for the bf16 throughput mode and the fp32 token-id-parity mode, plus the oracle on the CPU."""
+    from imagecaptioner_b200 import _ops
+    from oracle import kd_oracle as O
+    from tests.harness import build_student
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    V, E, H, L, B, max_len = CFG["V"], CFG["E"], CFG["H"], CFG["L"], 2048, 30
+    params = O.init_student_params(V, E, H, L, False, seed=0, logit_scale=8.0)
+    model, _ = build_student(params, {}, V, E, H, L, False, E, dev)
+    feats = torch.randn(B, CFG["S"], E, device=dev)
+    out = {"workload": "BASELINE configs[3]: greedy decode batch 2048, max len 30, default student", "steps": args.steps}
+    for name, dt in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
+        model.decoder.compute_dtype = dt
+        for _ in range(3):
+            model.decoder.greedy(feats, max_len)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(args.steps):
+            toks, lens = model.decoder.greedy(feats, max_len)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out[name] = {"ms_per_decode": ms, "captions_per_s": B / ms * 1e3, "tokens_per_s": B * max_len / ms * 1e3}
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    Bc = 64
+    fc = torch.randn(Bc, CFG["S"], E)
+    t0 = time.perf_counter(); O.greedy_decode(params, fc, max_len); dt_cpu = time.perf_counter() - t0
+    out["cpu_baseline"] = {"captions_per_s": Bc / dt_cpu, "tokens_per_s": Bc * max_len / dt_cpu, "cores": threads, "kind": "port", "sample": f"one batched oracle decode of B={Bc}"}
+    print(json.dumps(out), flush=True)
+
+
 def kernel_rooflines(lib, _ops, dev, cfg, peaks):
     """Per-kernel achieved bandwidth / FLOP rate: algorithmic bytes / CUDA-event time per launch."""
     B, T, V, E, H = cfg["B"], cfg["T"], cfg["V"], cfg["E"], cfg["H"]
@@ -378,10 +411,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b2c", choices=["b2c", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="kd_step", choices=["kd_step", "decode"], help="kd_step = the contract's metric (default); decode = configs[3] greedy decode leg")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--profile", action="store_true", help="only warm-up + timed steps (for ncu launch lists); prints a reduced line")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "decode":
+        run_decode(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -235,3 +235,21 @@ def test_larger_batch_matches_oracle(B):
     got = run_kd_step(model, projector, batch, DEV, torch.float32)
     ref = O.kd_step(params, pparams, batch)
     compare_step(got, ref, FP32_TOL, verbose=False)
+
+
+def test_large_variant_real_dims_fp32_and_bf16():
+    """BASELINE config 5 dimensions (E384 H768 3-layer LSTM, V10000, refinement with head_dim 96, identity channel projection
+    384 -> 384) at a small batch against the oracle: exercises the E > 256 kernel variants (two LayerNorm chunks per lane,
+    three float4 per lane in the attention score phase, 3 stacked fused gate GEMMs)."""
+    V, E, H, L, B, T = 10000, 384, 768, 3, 4, 3
+    params = O.init_student_params(V, E, H, L, True, seed=11)
+    pparams = O.init_projector_params(384, E, seed=12)            # {} : identity projection, pooling only
+    batch = O.synthetic_batch(B, T, V, E, H, Et=384, seed=13)
+    ref = O.kd_step(params, pparams, batch, dtype=torch.float64)    # fp64 oracle: isolates the kernel error from fp32-CPU noise
+    model, projector = build_student(params, pparams, V, E, H, L, True, 384, DEV)
+    got = run_kd_step(model, projector, batch, DEV, torch.float32)
+    compare_step(got, ref, FP32_TOL, verbose=False)
+    got16 = run_kd_step(model, projector, batch, DEV, torch.bfloat16)
+    compare_step(got16, ref, 3 * BF16_TOL, verbose=False, loosen={k: 4.0 for k in GATED})   # 196 rows: one flipped ReLU is ~1/14 of a column
+    toks, lens = model.decoder.greedy(model.attention_refinement(batch["encoder_features"].to(DEV)).float(), 6)
+    assert tuple(toks.shape) == (6, B) and int(lens.max()) <= 6
