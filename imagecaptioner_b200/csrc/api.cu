@@ -101,7 +101,7 @@ int pack_params(const B2CShape& s, const B2CParams& p, const Weights<T>& w, cuda
 template <typename T> struct TrainWs {
   Weights<T> w;
   float *P, *u; T *emb, *G0, *o1; T* xh[MAXL]; T* gates[MAXL]; float* c[MAXL];
-  T* dgates[MAXL]; T* dxh0; T* dxh[MAXL]; float* dc[MAXL]; T* do1; float* dHext; float* ds; T* du; T* dq; T* dP; float* demb; float* partial;
+  T* dgates[MAXL]; float* dxh0; float* dxh[MAXL]; float* dc[MAXL]; T* do1; float* dHext; float* ds; T* du; T* dq; T* dP; float* demb; float* partial;
   float *dWx32, *dWe32; T *dWxT, *dWeT;
   size_t bytes;
   void carve(void* base, const B2CShape& s) {
@@ -116,10 +116,10 @@ template <typename T> struct TrainWs {
     }
     for (int k = 0; k < s.L; ++k) {
       dgates[k] = c.take<T>(TB * 4 * H);
-      dxh[k] = k == 0 ? nullptr : c.take<T>(B * 2 * H);
+      dxh[k] = k == 0 ? nullptr : c.take<float>(TB * 2 * H);       // fp32, one slot per step (split-K GEMMs add into zeroed slots)
       dc[k] = c.take<float>(B * H);
     }
-    dxh0 = c.take<T>(TB * (E + H));                                 // [dctx_t ; dh0 carry]
+    dxh0 = c.take<float>(TB * (E + H));                             // [dctx_t ; dh0 carry], fp32
     do1 = c.take<T>(TB * E); dHext = c.take<float>(TB * H); ds = c.take<float>(TB * S);
     du = c.take<T>(TB * E); dq = c.take<T>(B * H); dP = c.take<T>(B * S * E); demb = c.take<float>(TB * E);
     dWx32 = c.take<float>(4 * H * E); dWe32 = c.take<float>(4 * H * E); dWxT = c.take<T>(4 * H * E); dWeT = c.take<T>(4 * H * E);
@@ -335,6 +335,9 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
   const size_t att_smem = (size_t)S * E * sizeof(T) + (size_t)(E + S) * 4;
   B2C_TRY(set_smem(attn_step_bwd_kernel<T>, att_smem));
   for (int k = 0; k < L; ++k) B2C_CHECK_ARG(g.w_ih[k] && g.w_hh[k] && g.b_ih[k] && g.b_hh[k], "NULL LSTM gradient pointer (layer %d)", k);
+  // input-gradient slots of every layer and step, zeroed once: the dxh GEMMs accumulate (beta = 1) so they may split K
+  B2C_CUDA(cudaMemsetAsync(W.dxh0, 0, (size_t)TB * (E + H) * sizeof(float), st));
+  for (int k = 1; k < L; ++k) B2C_CUDA(cudaMemsetAsync(W.dxh[k], 0, (size_t)TB * 2 * H * sizeof(float), st));
   SubPlan sp;
   B2C_TRY(fork_subs(sp, B, st));
   for (int t = Tn - 1; t >= 0; --t) {
@@ -346,19 +349,19 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
       const long row = (long)t * B + b0;
       for (int k = L - 1; k >= 0; --k) {
         const int in = in_dim(s, k), ld = in + H;
-        const T* carry = last ? nullptr : (k == 0 ? W.dxh0 + (row + B) * (E + H) + E : W.dxh[k] + b0 * 2 * H + H);
-        const T* above = (k < L - 1) ? W.dxh[k + 1] + b0 * 2 * H : nullptr;
+        const float* carry = last ? nullptr : (k == 0 ? W.dxh0 + (row + B) * (E + H) + E : W.dxh[k] + (row + B) * 2 * H + H);
+        const float* above = (k < L - 1) ? W.dxh[k + 1] + row * 2 * H : nullptr;
         const bool top = (k == L - 1);
         B2C_CUDA(launch_pdl(lstm_pointwise_bwd_kernel<T>, dim3(ew_grid((long)Bh * H)), dim3(256), 0, ss,
             (const T*)(W.gates[k] + row * 4 * H), (const float*)(W.c[k] + row * H), (const float*)(W.c[k] + (row + B) * H), W.dc[k] + b0 * H, last ? 1 : 0,
             carry, (long)ld, above, (long)(2 * H), (const float*)(top ? W.dHext + row * H : nullptr), (const T*)((top && dhid) ? dhid + row * H : nullptr),
             (const T*)((top && !last) ? W.dq + b0 * H : nullptr), (long)H, W.dgates[k] + row * 4 * H, Bh, H, dr.p, dr.seed, (uint32_t)k, row));
         B2C_LAUNCH_CHECK("lstm_pointwise_bwd_kernel");
-        T* out = (k == 0) ? W.dxh0 + row * (E + H) : W.dxh[k] + b0 * 2 * H;
-        B2C_TRY((gemm<T, T>(ss, Bh, ld, 4 * H, W.dgates[k] + row * 4 * H, 4 * H, 0, W.w.Wcat[k], ld, 1, out, ld)));
+        float* out = (k == 0) ? W.dxh0 + row * (E + H) : W.dxh[k] + row * 2 * H;
+        B2C_TRY((gemm<T, float>(ss, Bh, ld, 4 * H, W.dgates[k] + row * 4 * H, 4 * H, 0, W.w.Wcat[k], ld, 1, out, ld, 1.f)));
       }
       // layer 0's input gradient IS d(ctx_t): no context GEMM on the chain
-      const T* dctx_t = W.dxh0 + row * (E + H);
+      const float* dctx_t = W.dxh0 + row * (E + H);
       T* du_t = W.du + row * E;
       B2C_CUDA(launch_pdl(attn_step_bwd_kernel<T>, dim3(Bh), dim3(ATT_THREADS), att_smem, ss, (const float*)(W.P + b0 * S * E), feats + b0 * S * E,
                           (const float*)(W.u + row * E), (long)E, attw + row * S, dctx_t, (long)(E + H), S, E, W.ds + row * S, du_t, (long)E));

@@ -167,7 +167,7 @@ attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
 template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const float* __restrict__ u, long ldu,
-                     const float* __restrict__ attw, const T* __restrict__ dctx, long lddctx,
+                     const float* __restrict__ attw, const float* __restrict__ dctx, long lddctx,
                      int S, int E, float* __restrict__ ds_out, T* __restrict__ du, long lddu) {
   extern __shared__ __align__(128) unsigned char att_smem[];
   const int SE = S * E;
@@ -180,7 +180,7 @@ attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
   pdl_launch_dependents();
   pdl_wait();
   att_stage_F<T>(F, b, SE, Fs, &bar);
-  for (int e = tid; e < E; e += ATT_THREADS) dcs[e] = to_f<T>(dctx[(long)b * lddctx + e]);
+  for (int e = tid; e < E; e += ATT_THREADS) dcs[e] = dctx[(long)b * lddctx + e];
   __syncthreads();
   mbar_wait(&bar, 0);
   for (int l = warp; l < S; l += nwarp) {
@@ -211,7 +211,7 @@ attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
 // u/dctx/w/ds for all T steps of this sample sit in shared memory (T*(2E+2S) floats).
 template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS)
-attn_post_kernel(const float* __restrict__ P, const float* __restrict__ u /*(T,B,E)*/, const T* __restrict__ dctx /*(T,B,.) pitch lddctx*/, long lddctx,
+attn_post_kernel(const float* __restrict__ P, const float* __restrict__ u /*(T,B,E)*/, const float* __restrict__ dctx /*(T,B,.) pitch lddctx*/, long lddctx,
                  const float* __restrict__ attw /*(T,B,S)*/, const float* __restrict__ ds /*(T,B,S)*/,
                  int Tn, int B, int S, int E, T* __restrict__ dP, float* __restrict__ dF) {
   extern __shared__ __align__(128) unsigned char att_smem[];
@@ -220,7 +220,7 @@ attn_post_kernel(const float* __restrict__ P, const float* __restrict__ u /*(T,B
   float* ws = dcs + (long)Tn * E;                      // Tn*S
   float* dss = ws + (long)Tn * S;                      // Tn*S
   const int tid = threadIdx.x, b = blockIdx.x;
-  for (int i = tid; i < Tn * E; i += ATT_THREADS) { const int t = i / E, e = i - t * E; us[i] = u[((long)t * B + b) * E + e]; dcs[i] = to_f<T>(dctx[((long)t * B + b) * lddctx + e]); }
+  for (int i = tid; i < Tn * E; i += ATT_THREADS) { const int t = i / E, e = i - t * E; us[i] = u[((long)t * B + b) * E + e]; dcs[i] = dctx[((long)t * B + b) * lddctx + e]; }
   for (int i = tid; i < Tn * S; i += ATT_THREADS) { const int t = i / S, l = i - t * S; ws[i] = attw[((long)t * B + b) * S + l]; dss[i] = ds[((long)t * B + b) * S + l]; }
   __syncthreads();
   const long base = (long)b * S * E;
@@ -316,7 +316,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 lstm_pointwise_bwd_kernel(const T* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_cur,
                           float* __restrict__ dc, int dc_is_zero,
-                          const T* __restrict__ dh_carry, long ld_carry, const T* __restrict__ dh_above, long ld_above,
+                          const float* __restrict__ dh_carry, long ld_carry, const float* __restrict__ dh_above, long ld_above,
                           const float* __restrict__ dh_ext, const T* __restrict__ dh_hid, const T* __restrict__ dh_q, long ld_q,
                           T* __restrict__ dgates, int B, int H, float drop_p, uint64_t seed, uint32_t site, long row_base) {
   pdl_launch_dependents();
@@ -326,10 +326,10 @@ lstm_pointwise_bwd_kernel(const T* __restrict__ gates, const float* __restrict__
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const long b = idx / H; const int j = (int)(idx - b * H);
     float dh = 0.f;
-    if (dh_carry) dh += to_f<T>(dh_carry[b * ld_carry + j]);
+    if (dh_carry) dh += dh_carry[b * ld_carry + j];
     if (dh_above) {
       const float m = drop_p > 0.f ? dropout_scale(seed, site, (uint64_t)((row_base + b) * H + j), drop_p, inv_keep) : 1.0f;
-      dh += to_f<T>(dh_above[b * ld_above + j]) * m;
+      dh += dh_above[b * ld_above + j] * m;
     }
     if (dh_ext) dh += dh_ext[idx];
     if (dh_hid) dh += to_f<T>(dh_hid[idx]);

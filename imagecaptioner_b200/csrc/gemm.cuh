@@ -462,9 +462,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const long orow = row_unperm_h ? (long)(grow & 3) * row_unperm_h + (grow >> 2) : (long)grow;   // interleaved -> gate-major row
           TC* cp = C + orow * ldc + gcol;
           if (split) {
-            const float* a = reinterpret_cast<const float*>(&acc);
+            if (vec_ok && gcol + 4 <= N) {         // one 16-byte vector reduction instead of four scalar atomics
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(cp), "f"(__uint_as_float(acc.x)), "f"(__uint_as_float(acc.y)),
+                           "f"(__uint_as_float(acc.z)), "f"(__uint_as_float(acc.w)) : "memory");
+            } else {
+              const float* a = reinterpret_cast<const float*>(&acc);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) if (gcol + e < N) atomicAdd(reinterpret_cast<float*>(cp) + e, a[e]);
+              for (int e = 0; e < 4; ++e) if (gcol + e < N) atomicAdd(reinterpret_cast<float*>(cp) + e, a[e]);
+            }
           } else if (vec_ok && gcol + PER <= N) {
             uint4 o = acc;
             if (beta != 0.f) {
