@@ -386,8 +386,14 @@ def kernel_rooflines(lib, _ops, dev, cfg, peaks):
 
     t_kd = timeit(kd)
     kd_bytes = N * V * (2 + 4 + 2) + 8 * N                     # read bf16 student + fp32 teacher, write bf16 dlogits, read targets
-    roof = {"kernel": "kd_token_loss_kernel<bf16> (b2c_kd_token_loss)", "bound": "hbm", "achieved": kd_bytes / t_kd / 1e9, "peak": peaks["hbm"],
-            "unit": "GB/s", "frac": kd_bytes / t_kd / 1e9 / peaks["hbm"], "traffic": None, "peak_source": peaks["src"] + " (MEASURED_PEAKS.json hbm_gbs)",
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")       # dram__bytes_read + write of ONE ncu --set full capture
+    if os.path.exists(tpath):
+        rec = json.load(open(tpath)).get("kd_token_loss_pipe_kernel<bf16,3,true>")
+        if rec:
+            traffic, traffic_src = rec["dram_bytes_read"] + rec["dram_bytes_write"], rec["source"]
+    roof = {"kernel": "kd_token_loss_pipe_kernel<bf16,3,true> (b2c_kd_token_loss)", "bound": "hbm", "achieved": kd_bytes / t_kd / 1e9, "peak": peaks["hbm"],
+            "unit": "GB/s", "frac": kd_bytes / t_kd / 1e9 / peaks["hbm"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["src"] + " (MEASURED_PEAKS.json hbm_gbs)",
             "algorithmic_bytes_per_launch": kd_bytes, "us_per_launch": t_kd * 1e6}
     # vocabulary head GEMM (time-batched, tcgen05): logits = o1 W2^T, M = T*B, N = V, K = E
     A = torch.randn(N, E, device=dev).bfloat16(); W = torch.randn(V, E, device=dev).bfloat16(); C = torch.empty(N, V, device=dev, dtype=torch.bfloat16)
