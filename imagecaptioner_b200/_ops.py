@@ -171,6 +171,31 @@ def _master(params: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     return out
 
 
+# Optional gradient destinations: parameter data_ptr -> fp32 tensor (a view into the flat all-reduce buffer of
+# imagecaptioner_b200.ddp).  When registered (GraphedKDStep does, for one-micro-batch-per-step training), the backward
+# kernels write a parameter's gradient straight into its slot and return that view; with `.grad = None` autograd adopts it
+# without a copy or an add kernel.  The kernels OVERWRITE, so this must stay off when gradients are accumulated over
+# several backward passes (the default).
+_GRAD_DEST = {}
+
+
+def set_grad_destinations(mapping) -> None:
+    _GRAD_DEST.clear()
+    if mapping:
+        _GRAD_DEST.update(mapping)
+
+
+def _grad_buffers(params, master):
+    out = []
+    for p, m in zip(params, master):
+        dst = _GRAD_DEST.get(p.data_ptr()) if _GRAD_DEST else None
+        if dst is not None and dst.dtype == torch.float32 and dst.shape == m.shape and dst.is_contiguous():
+            out.append(dst.view(dst.shape))      # a fresh view object: autograd adopts it as .grad only if nothing else holds it
+        else:
+            out.append(torch.empty_like(m))
+    return out
+
+
 def workspace_bytes(shape: B2CShape, code: int, mode: int) -> int:
     lib = load_library()
     n = lib.b2c_workspace_bytes(ctypes.byref(shape), code, mode)
@@ -205,6 +230,7 @@ class DecoderFunction(torch.autograd.Function):
                                        hid.data_ptr(), attw.data_ptr(), ws.data_ptr(), ws.numel(), code, ctypes.byref(drop), _stream()),
                "b2c_decoder_forward")
         ctx.b2c = (shape, code, drop, L, ws, f, cap, master, hid, attw, feats.dtype, [p.dtype for p in params])
+        ctx.b2c_params = params
         ctx.mark_non_differentiable(attw)
         return logits, hid, attw
 
@@ -218,7 +244,7 @@ class DecoderFunction(torch.autograd.Function):
         dlogits = dlogits.to(cdt).contiguous()
         if dhid is not None:
             dhid = dhid.to(cdt).contiguous()
-        grads = [torch.empty_like(m) for m in master]
+        grads = _grad_buffers(ctx.b2c_params, master)
         dfeats = torch.empty(shape.B, shape.S, shape.E, dtype=torch.float32, device=f.device)
         prm = _fill_struct(B2CParams(), master, L)
         grd = _fill_struct(B2CGrads(), grads, L)
@@ -394,6 +420,7 @@ class RefinementFunction(torch.autograd.Function):
         _check(lib.b2c_refinement_forward(ctypes.byref(shape), ctypes.byref(prm), xf.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
                                           code, ctypes.byref(drop), _stream()), "b2c_refinement_forward")
         ctx.b2c = (shape, code, drop, ws, master, x.dtype, [p.dtype for p in params], compute_dtype)
+        ctx.b2c_params = params
         return out
 
     @staticmethod
@@ -401,7 +428,7 @@ class RefinementFunction(torch.autograd.Function):
         lib = load_library()
         shape, code, drop, ws, master, x_dtype, pdtypes, cdt = ctx.b2c
         dout = dout.to(cdt).contiguous()
-        grads = [torch.empty_like(m) for m in master]
+        grads = _grad_buffers(ctx.b2c_params, master)
         dx = torch.empty(shape.B, shape.S, shape.E, dtype=torch.float32, device=dout.device)
         prm = _fill_flat(B2CRefineParams(), master)
         grd = _fill_flat(B2CRefineGrads(), grads)
@@ -432,6 +459,7 @@ class ProjectorFunction(torch.autograd.Function):
         _check(lib.b2c_projector_forward(ctypes.byref(shape), ctypes.byref(prm), xf.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
                                          code, ctypes.byref(drop), _stream()), "b2c_projector_forward")
         ctx.b2c = (shape, code, drop, ws, master, [p.dtype for p in params])
+        ctx.b2c_params = params
         return out
 
     @staticmethod
@@ -441,7 +469,7 @@ class ProjectorFunction(torch.autograd.Function):
         if not master:
             return (None,) * 6
         dout = dout.to(torch.float32).contiguous()
-        grads = [torch.empty_like(m) for m in master]
+        grads = _grad_buffers(ctx.b2c_params, master)
         prm = _fill_flat(B2CProjParams(), master)
         grd = _fill_flat(B2CProjGrads(), grads)
         _check(lib.b2c_projector_backward(ctypes.byref(shape), ctypes.byref(prm), dout.data_ptr(), ctypes.byref(grd), ws.data_ptr(), ws.numel(),

@@ -102,7 +102,7 @@ template <typename T> struct TrainWs {
   Weights<T> w;
   float *P, *u; T *emb, *G0, *o1; T* xh[MAXL]; T* gates[MAXL]; float* c[MAXL];
   T* dgates[MAXL]; float* dxh0; float* dxh[MAXL]; float* dc[MAXL]; T* do1; float* dHext; float* ds; T* du; T* dq; T* dP; float* demb; float* partial;
-  float *dWx32, *dWe32; T *dWxT, *dWeT;
+  float *dWx32, *dWe32; T *dWxT, *dWeT; float* partial_side;
   size_t bytes;
   void carve(void* base, const B2CShape& s) {
     Carver c{reinterpret_cast<unsigned char*>(base), 0};
@@ -124,7 +124,7 @@ template <typename T> struct TrainWs {
     du = c.take<T>(TB * E); dq = c.take<T>(B * H); dP = c.take<T>(B * S * E); demb = c.take<float>(TB * E);
     dWx32 = c.take<float>(4 * H * E); dWe32 = c.take<float>(4 * H * E); dWxT = c.take<T>(4 * H * E); dWeT = c.take<T>(4 * H * E);
     size_t mc = (size_t)s.V; if ((size_t)4 * H > mc) mc = 4 * H; if (E > mc) mc = E;
-    partial = c.take<float>((size_t)COLSUM_RS * mc);
+    partial = c.take<float>((size_t)COLSUM_RS * mc); partial_side = c.take<float>((size_t)COLSUM_RS * mc);
     bytes = align_up(c.off, 256);
   }
 };
@@ -211,7 +211,7 @@ int lstm_layer_fwd(cudaStream_t st, const B2CShape& s, const Weights<T>& w, int 
 // so the batch is cut into NS contiguous sub-batches whose chains run on NS forked streams and overlap on the GPU; all
 // buffers keep their (T, B, .) layout (a sub-batch is a row range), so the time-batched GEMMs before and after the loop
 // still see whole tensors.  Fork / join use events, which CUDA graph capture records as parallel branches.
-constexpr int MAX_SUB = 4;
+constexpr int MAX_SUB = 5;          // 4 sub-batch branches (B2C_SUB_BATCHES) + 1 side stream for work hidden under the recurrence
 struct SubStreams { cudaStream_t s[MAX_SUB]; cudaEvent_t fork; cudaEvent_t join[MAX_SUB]; };
 int get_substreams(SubStreams** out) {
   static SubStreams ss; static bool ready = false;
@@ -322,15 +322,22 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
   const int B = s.B, Tn = s.T, S = s.S, E = s.E, H = s.H, L = s.L, V = s.V;
   const long TB = (long)Tn * B;
   const float inv_keep = dr.p > 0.f ? 1.0f / (1.0f - dr.p) : 1.0f;
-  // ---- output head (time-batched)
+  // ---- output head (time-batched).  Only d(o1) -> dH_ext feeds the time loop; the head's weight gradients run on a side
+  // stream underneath the (latency-bound) recurrence and are joined after it.
   B2C_TRY((gemm<T, T>(st, (int)TB, E, V, dlogits, V, 0, W.w.W2, E, 1, W.do1, E)));
   relu_bwd_inplace_kernel<T><<<ew_grid(TB * E), 256, 0, st>>>(W.do1, W.o1, TB * E, inv_keep);
   B2C_LAUNCH_CHECK("relu_bwd_inplace_kernel");
-  B2C_TRY((gemm<T, float>(st, V, E, (int)TB, dlogits, V, 1, W.o1, E, 1, g.out3_w, E)));
-  B2C_TRY(colsum<T>(st, dlogits, TB, V, V, W.partial, g.out3_b));
+  SubStreams* hs = nullptr;
+  B2C_TRY(get_substreams(&hs));
+  cudaStream_t side = hs->s[MAX_SUB - 1];
+  B2C_CUDA(cudaEventRecord(hs->fork, st));
+  B2C_CUDA(cudaStreamWaitEvent(side, hs->fork, 0));
+  B2C_TRY((gemm<T, float>(side, V, E, (int)TB, dlogits, V, 1, W.o1, E, 1, g.out3_w, E)));
+  B2C_TRY(colsum<T>(side, dlogits, TB, V, V, W.partial_side, g.out3_b));
+  B2C_TRY((gemm<T, float>(side, E, H, (int)TB, W.do1, E, 1, hid_top, H, 1, g.out0_w, H)));
+  B2C_TRY(colsum<T>(side, W.do1, TB, E, E, W.partial_side, g.out0_b));
+  B2C_CUDA(cudaEventRecord(hs->join[MAX_SUB - 1], side));
   B2C_TRY((gemm<T, float>(st, (int)TB, H, E, W.do1, E, 0, W.w.W1, H, 1, W.dHext, H)));
-  B2C_TRY((gemm<T, float>(st, E, H, (int)TB, W.do1, E, 1, hid_top, H, 1, g.out0_w, H)));
-  B2C_TRY(colsum<T>(st, W.do1, TB, E, E, W.partial, g.out0_b));
   // ---- reverse time loop
   const size_t att_smem = (size_t)S * E * sizeof(T) + (size_t)(E + S) * 4;
   B2C_TRY(set_smem(attn_step_bwd_kernel<T>, att_smem));
@@ -370,6 +377,7 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
     }
   }
   B2C_TRY(join_subs(sp));
+  B2C_CUDA(cudaStreamWaitEvent(st, hs->join[MAX_SUB - 1], 0));      // head weight gradients (side stream) are complete
   // ---- post-loop, time-batched weight gradients (4H-sized rows come out interleaved and are written gate-major)
   for (int k = 1; k < L; ++k) {
     const int in = in_dim(s, k), ld = in + H;

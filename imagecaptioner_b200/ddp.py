@@ -40,6 +40,29 @@ class FlatGradAllReducer:
             p.grad = self.flat[off:off + n].view_as(p)
             off += n
 
+    def grad_views(self):
+        """parameter data_ptr -> its fp32 slot in the flat buffer (for _ops.set_grad_destinations)."""
+        out, off = {}, 0
+        for p in self.params:
+            n = p.numel()
+            out[p.data_ptr()] = self.flat[off:off + n].view_as(p)
+            off += n
+        return out
+
+    def detach_grads(self) -> None:
+        """`.grad = None` on every parameter: the next backward's gradient tensors are adopted as-is (no add kernel)."""
+        for p in self.params:
+            p.grad = None
+
+    def attach_views(self) -> None:
+        """Point every parameter's .grad at its slot of the flat buffer (host-side only, no kernel)."""
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * 4 or p.grad.dtype != torch.float32:
+                p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
     def zero_grad(self) -> None:
         """Zero the buffer in place (keeps the .grad views; do NOT call optimizer.zero_grad(set_to_none=True))."""
         self.flat.zero_()
