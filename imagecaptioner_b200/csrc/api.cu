@@ -548,7 +548,7 @@ int ln_bwd(cudaStream_t st, const TDY* dy, const float* dpool, int L, int O, con
   else { if (E <= 256) B2C_LNB(false, 1); else B2C_LNB(false, 2); }
 #undef B2C_LNB
   B2C_LAUNCH_CHECK("ln_bwd_kernel");
-  ln_param_grad_kernel<<<cdiv(3 * E, 256), 256, 0, st>>>(part, (int)grid, E, dgamma, dbeta, dbias_prev);
+  ln_param_grad_kernel<<<dim3(cdiv(E, 32), 3), 256, 0, st>>>(part, (int)grid, E, dgamma, dbeta, dbias_prev);
   B2C_LAUNCH_CHECK("ln_param_grad_kernel");
   return 0;
 }

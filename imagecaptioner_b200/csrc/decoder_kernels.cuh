@@ -200,7 +200,6 @@ attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
   const float* Pb = P + (long)b * SE;
   for (int e = tid; e < E; e += ATT_THREADS) {
     float a = 0.f; const float ue = u[(long)b * ldu + e];
-#pragma unroll 7
     for (int l = 0; l < S; ++l) { const float th = Math<T>::tanh_(__ldg(Pb + l * E + e) + ue); a = fmaf(dw[l], 1.0f - th * th, a); }
     du[(long)b * lddu + e] = from_f<T>(a);
   }

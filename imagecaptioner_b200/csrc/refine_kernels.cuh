@@ -238,16 +238,18 @@ ln_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ dpool, int L
   }
 }
 // dgamma / dbeta / (optional) dbias_prev [e] = sum over blocks of part[b, {0,1,2}, e]   (fixed order: deterministic)
+// grid (ceil(E/32), 3): 32 columns x 8 row lanes per block
 __global__ void __launch_bounds__(256) ln_param_grad_kernel(const float* __restrict__ part, int nblk, int E, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, float* __restrict__ dbias_prev) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 3 * E) return;
-  const int which = idx / E, e = idx - which * E;
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, e = blockIdx.x * 32 + tx, which = blockIdx.y;
   float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias_prev);
   if (!dst) return;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += part[((long)b * 3 + which) * E + e];
-  dst[e] = s;
+  if (e < E) for (int b = ty; b < nblk; b += 8) s += part[((long)b * 3 + which) * E + e];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && e < E) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i][tx]; dst[e] = t; }
 }
 
 // ------------------------------------------------------------------ column sums (bias gradients), optionally fused with the ReLU backward
@@ -299,15 +301,17 @@ constexpr int MHA_THREADS = 256;
 constexpr uint32_t MHA_DROP_SITE = 200u;
 
 // C[i][j] = sum_k A[i][k] * B[j][k]          (A: Mi x K, B: Nj x K, both with pitch pk)
+// A thread owns the STRIDED 4x4 tile rows {it + a*ti} x {jt + b*tj}: the threads of a quarter warp then read CONSECUTIVE rows
+// (pitch = odd multiple of 16 bytes -> conflict free); contiguous 4-row blocks would put them 4 rows apart (7-way conflicts).
 template <typename F>
 __device__ __forceinline__ void mha_tile_nt(const float* A, const float* Bm, int Mi, int Nj, int K, int pk, F&& emit) {
   const int ti = (Mi + 3) >> 2, tj = (Nj + 3) >> 2;
   for (int t = threadIdx.x; t < ti * tj; t += MHA_THREADS) {
-    const int i0 = (t / tj) * 4, j0 = (t % tj) * 4;
+    const int it = t / tj, jt = t - it * tj;
     float acc[4][4] = {};
     const float* ar[4]; const float* br[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) { ar[a] = A + min(i0 + a, Mi - 1) * pk; br[a] = Bm + min(j0 + a, Nj - 1) * pk; }
+    for (int a = 0; a < 4; ++a) { ar[a] = A + min(it + a * ti, Mi - 1) * pk; br[a] = Bm + min(jt + a * tj, Nj - 1) * pk; }
     for (int k = 0; k < K; k += 4) {
       float4 av[4], bv[4];
 #pragma unroll
@@ -321,7 +325,7 @@ __device__ __forceinline__ void mha_tile_nt(const float* A, const float* Bm, int
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) if (i0 + a < Mi && j0 + b < Nj) emit(i0 + a, j0 + b, acc[a][b]);
+      for (int b = 0; b < 4; ++b) if (it + a * ti < Mi && jt + b * tj < Nj) emit(it + a * ti, jt + b * tj, acc[a][b]);
   }
 }
 // C[i][d] = sum_j P[i][j] * V[j][d]          (P: Mi x J pitch pp; V: J x D pitch pd)

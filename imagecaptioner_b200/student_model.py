@@ -163,9 +163,41 @@ class LSTMDecoder(nn.Module):
         return logits, hidden_states, list(attw.unbind(0))
 
     @torch.no_grad()
-    def greedy(self, image_features, max_length, start_id=1, end_id=2):
-        """Batched greedy decode of already-refined features -> tokens (max_length,B) int64, lengths (B) int32."""
-        return _ops.greedy_decode(image_features, self._param_list(), self.num_layers, max_length, start_id, end_id, self._mode())
+    def greedy(self, image_features, max_length, start_id=1, end_id=2, use_graph=None):
+        """Batched greedy decode of already-refined features -> tokens (max_length,B) int64, lengths (B) int32.
+
+        One decode is ~9 small kernels per token with the argmax fed back on the device; issued eagerly it is bound by host
+        launch latency, so for batches >= 64 (or use_graph=True) the whole decode is captured once per (shape, dtype, ids) into
+        a CUDA graph over a static feature buffer and replayed.  The parameters are read through their pointers at replay
+        time, so in-place weight updates are seen; the returned tensors are copies of the graph's static outputs."""
+        B = image_features.shape[0]
+        if use_graph is None:
+            use_graph = B >= 64
+        if not use_graph:
+            return _ops.greedy_decode(image_features, self._param_list(), self.num_layers, max_length, start_id, end_id, self._mode())
+        plist = self._param_list()
+        key = (tuple(image_features.shape), int(max_length), int(start_id), int(end_id), self._mode(), image_features.device,
+               tuple(p.data_ptr() for p in plist))
+        cache = self.__dict__.setdefault("_greedy_graphs", {})
+        ent = cache.get(key)
+        if ent is None:
+            static_feats = image_features.detach().float().clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                      # warm-up outside capture (lazy module/attribute initialisation)
+                _ops.greedy_decode(static_feats, plist, self.num_layers, max_length, start_id, end_id, self._mode())
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                toks, lens = _ops.greedy_decode(static_feats, plist, self.num_layers, max_length, start_id, end_id, self._mode())
+            if len(cache) >= 8:
+                cache.clear()
+            ent = cache[key] = (graph, static_feats, toks, lens)
+        graph, static_feats, toks, lens = ent
+        static_feats.copy_(image_features)
+        graph.replay()
+        return toks.clone(), lens.clone()
 
 
 class CaptioningStudent(nn.Module):
