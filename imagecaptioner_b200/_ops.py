@@ -317,7 +317,7 @@ class KDLossFunction(torch.autograd.Function):
     def forward(ctx, logits, teacher_logits, targets, feats_s, feats_t, hid_s, hid_t, cfg):
         lib = load_library()
         _require_cuda(logits, "student logits")
-        alpha, beta, gamma, temperature, w_ce, ce_mult, group, nval_global = cfg
+        alpha, beta, gamma, temperature, w_ce, ce_mult, group, nval_global, unit_grad = cfg
         T, B, V = logits.shape
         N = T * B
         dev = logits.device
@@ -362,7 +362,7 @@ class KDLossFunction(torch.autograd.Function):
         _check(lib.b2c_loss_finalize(rows[0].data_ptr(), rows[1].data_ptr(), N, nval.data_ptr(), float(ce_mult), _ptr(feat_part), B, E,
                                      _ptr(hid_part), Th, H, float(temperature), float(alpha), float(beta), float(gamma), float(w_ce),
                                      out5.data_ptr(), st), "b2c_loss_finalize")
-        ctx.b2c = dict(dlogits=dlogits, dfs=dfs, dft=dft, dhs=dhs, code=code, used=False,
+        ctx.b2c = dict(dlogits=dlogits, dfs=dfs, dft=dft, dhs=dhs, code=code, used=False, unit_grad=bool(unit_grad),
                        dtypes=(logits.dtype, None if feats_s is None else feats_s.dtype,
                                None if feats_t is None else feats_t.dtype, None if hid_s is None else hid_s.dtype))
         ctx.mark_non_differentiable(out5)
@@ -375,12 +375,13 @@ class KDLossFunction(torch.autograd.Function):
         if sv["used"]:
             raise RuntimeError("KDLossFunction.backward ran twice: its gradients are scaled in place (retain_graph is not supported)")
         sv["used"] = True
-        scale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
-        st = _stream()
-        for key, code in (("dlogits", sv["code"]), ("dfs", B2C_F32), ("dft", B2C_F32), ("dhs", sv["code"])):
-            t = sv[key]
-            if t is not None:
-                _check(lib.b2c_scale_inplace(t.data_ptr(), t.numel(), code, scale.data_ptr(), st), "b2c_scale_inplace")
+        if not sv["unit_grad"]:          # unit_grad: the caller guarantees loss.backward() with grad_output == 1 (GraphedKDStep)
+            scale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+            st = _stream()
+            for key, code in (("dlogits", sv["code"]), ("dfs", B2C_F32), ("dft", B2C_F32), ("dhs", sv["code"])):
+                t = sv[key]
+                if t is not None:
+                    _check(lib.b2c_scale_inplace(t.data_ptr(), t.numel(), code, scale.data_ptr(), st), "b2c_scale_inplace")
         dt_l, dt_fs, dt_ft, dt_hs = sv["dtypes"]
 
         def cast(t, dt):

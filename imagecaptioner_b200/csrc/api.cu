@@ -632,7 +632,7 @@ int refinement_backward_impl(const B2CShape& s, const B2CRefineParams& p, const 
   B2C_TRY((gemm<T, float>(st, E, E, (int)R, W.dz1, E, 1, W.attn, E, 1, g.out_w, E)));
   B2C_TRY((gemm<T, T>(st, (int)R, E, E, W.dz1, E, 0, W.Wo, E, 1, W.dattn, E)));
   {
-    const size_t smem = ((size_t)4 * S * mha_pitch(hd) + (size_t)3 * S * mha_pitch(S)) * 4;
+    const size_t smem = ((size_t)4 * S * mha_pitch(hd) + (size_t)(dr.p > 0.f ? 3 : 2) * S * mha_pitch(S)) * 4;
     B2C_TRY(set_smem(mha_bwd_kernel<T>, smem));
     mha_bwd_kernel<T><<<dim3(B, heads), MHA_THREADS, smem, st>>>(W.qkv, W.probs, W.dattn, W.dqkv, S, E, heads, 1.0f / sqrtf((float)hd), dr.p, dr.seed);
     B2C_LAUNCH_CHECK("mha_bwd_kernel");

@@ -433,7 +433,7 @@ mha_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ probs, const T* 
   extern __shared__ __align__(16) float mh_sm[];
   const int hd = E / heads, ph = mha_pitch(hd), ps = mha_pitch(S);
   float* Qs = mh_sm; float* Ks = Qs + S * ph; float* Vs = Ks + S * ph; float* dOs = Vs + S * ph;
-  float* Ps = dOs + S * ph; float* Pd = Ps + S * ps; float* dS = Pd + S * ps;                   // S x ps each
+  float* Ps = dOs + S * ph; float* dS = Ps + S * ps; float* Pd = drop_p > 0.f ? dS + S * ps : Ps;     // S x ps each; Pd aliases Ps without dropout
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   mha_load_heads<T>(qkv, b, h, S, E, hd, ph, Qs, Ks, Vs);
@@ -446,7 +446,7 @@ mha_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ probs, const T* 
     const int i = idx / ps, j = idx - i * ps;
     float p = 0.f, m = 1.f;
     if (j < S) { p = to_f<T>(probs[pb + i * S + j]); if (drop_p > 0.f) m = dropout_scale(seed, MHA_DROP_SITE, (uint64_t)(pb + i * S + j), drop_p, inv_keep); }
-    Ps[idx] = p; Pd[idx] = p * m; dS[idx] = m;                          // dS holds the mask until dP overwrites it
+    Ps[idx] = p; if (drop_p > 0.f) Pd[idx] = p * m; dS[idx] = m;        // dS holds the mask until dP overwrites it
   }
   __syncthreads();
   // dV = Pd^T dO

@@ -46,6 +46,8 @@ class DistillationLoss(nn.Module):
         # optional int32 device scalar holding the (global) non-PAD target count, set by a caller that computes it
         # itself (GraphedKDStep keeps the NCCL all-reduce of the count outside its CUDA graphs)
         self.n_valid_global = None
+        # set by a caller that runs `loss.backward()` itself with grad_output == 1 (GraphedKDStep): skips the rescaling pass
+        self.assume_unit_grad = False
 
     # ---- the fused path -------------------------------------------------------------------------
     def _run(self, logits, teacher_logits, targets, feats_s, feats_t, hid_s, hid_t, alpha, beta, gamma, w_ce, temperature):
@@ -60,7 +62,7 @@ class DistillationLoss(nn.Module):
             hid_s = hid_t = None
         if feats_s is None or feats_t is None:
             feats_s = feats_t = None
-        cfg = (alpha, beta, gamma, temperature, w_ce, float(self.world_size), self.process_group, self.n_valid_global)
+        cfg = (alpha, beta, gamma, temperature, w_ce, float(self.world_size), self.process_group, self.n_valid_global, self.assume_unit_grad)
         return _ops.KDLossFunction.apply(logits, teacher_logits, targets, feats_s, feats_t, hid_s, hid_t, cfg)
 
     def forward_device(self, student_outputs, teacher_outputs, targets):

@@ -40,6 +40,7 @@ class GraphedKDStep:
         # every trainable parameter here gets exactly one gradient per step from one native backward call, so the kernels may
         # write it directly into the flat all-reduce buffer (saves ~35 accumulate kernels + the buffer zeroing per step)
         self.direct_grads = direct_grads
+        loss_module.assume_unit_grad = True      # _fwd_bwd calls loss.backward() with the implicit grad_output of exactly 1
         if direct_grads:
             _ops.set_grad_destinations(reducer.grad_views())
         # Data parallel: NCCL stays OUTSIDE the graphs.  The non-PAD count is all-reduced before graph 1 (targets are an
