@@ -196,13 +196,14 @@ template <> struct RowS<float> {
   }
 };
 
+constexpr int KD_SLOTS = 2;              // row slots per CTA: the TMA prefetch runs KD_SLOTS - 1 rows ahead of the math
 template <typename TS, int NCH, bool TEMP4>
 __global__ void __launch_bounds__(KDR_THREADS, (NCH <= 3 ? 3 : (NCH <= 5 ? 2 : 1)))
 kd_token_loss_pipe_kernel(const TS* __restrict__ y, const float* __restrict__ z, const int64_t* __restrict__ tgt,
                           long N, int V, float inv_temp, float temperature, float kd_coef, float w_ce, const int* __restrict__ n_valid_ptr,
                           TS* __restrict__ dy, float* __restrict__ row_kl, float* __restrict__ row_ce) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[KD_SLOTS];
   __shared__ float scratch[KDR_THREADS / 32 * 4];
   const size_t zbytes = (size_t)V * 4, ybytes = (size_t)V * sizeof(TS), slot = zbytes + ybytes;    // both multiples of 16
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -215,17 +216,16 @@ kd_token_loss_pipe_kernel(const TS* __restrict__ y, const float* __restrict__ z,
     bulk_g2s(dst, z + row * (long)V, (uint32_t)zbytes, &full_bar[sidx]);
     bulk_g2s(dst + zbytes, y + row * (long)V, (uint32_t)ybytes, &full_bar[sidx]);
   };
-  if (tid == 0) { mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1); fence_barrier_init(); }
+  if (tid == 0) { for (int i = 0; i < KD_SLOTS; ++i) mbar_init(&full_bar[i], 1); fence_barrier_init(); }
   __syncthreads();
   const long r0 = blockIdx.x, stride = gridDim.x;
   if (tid == 0) {
-    if (r0 < N) issue(r0, 0);
-    if (r0 + stride < N) issue(r0 + stride, 1);
+    for (int i = 0; i < KD_SLOTS; ++i) if (r0 + i * stride < N) issue(r0 + i * stride, i);
   }
 
   int it = 0;
   for (long r = r0; r < N; r += stride, ++it) {
-    const int sidx = it & 1; const uint32_t ph = (it >> 1) & 1;
+    const int sidx = it % KD_SLOTS; const uint32_t ph = (it / KD_SLOTS) & 1;
     const float* zs = reinterpret_cast<const float*>(smem_raw + (size_t)sidx * slot);
     const TS* ys = reinterpret_cast<const TS*>(smem_raw + (size_t)sidx * slot + zbytes);
     mbar_wait(&full_bar[sidx], ph);
@@ -240,7 +240,7 @@ kd_token_loss_pipe_kernel(const TS* __restrict__ y, const float* __restrict__ z,
     const int t_idx = valid ? (int)t64 : -1;
     const float y_tgt = valid ? to_f<TS>(ys[t_idx]) : 0.f, z_tgt = valid ? zs[t_idx] : 0.f;
     __syncthreads();                           // every thread has taken its groups out of the slot ...
-    if (tid == 0 && r + 2 * stride < N) issue(r + 2 * stride, sidx);      // ... so the row after next can land in it
+    if (tid == 0 && r + KD_SLOTS * stride < N) issue(r + KD_SLOTS * stride, sidx);      // ... so a later row can land in it
 
     // phase 1: row maxima
     float my = -INFINITY, mz = -INFINITY;
