@@ -177,6 +177,7 @@ def run_ours(args):
     from imagecaptioner_b200.ddp import FlatGradAllReducer, attach_loss_group
     from imagecaptioner_b200.distillation_utils import DistillationLoss
     from imagecaptioner_b200.graph import GraphedKDStep
+    from imagecaptioner_b200.optim import FlatAdamW, reference_param_groups
     from oracle import kd_oracle as O
     from tests.harness import build_student
 
@@ -199,9 +200,13 @@ def run_ours(args):
     model.decoder.compute_dtype = torch.bfloat16
     loss_mod = DistillationLoss(0.7, 0.2, 0.1, 4.0, vocab_size=V)
     attach_loss_group(loss_mod)
-    trainable = [p for p in list(model.parameters()) + list(projector.parameters()) if p.requires_grad]
-    reducer = FlatGradAllReducer(trainable)
-    opt = torch.optim.AdamW(trainable, lr=1e-4, weight_decay=0.01, fused=True, capturable=not args.no_graph)
+    if args.torch_optimizer:                 # A/B: torch's fused AdamW + one global-norm clip instead of the native flat-buffer step
+        trainable = [p for p in list(model.parameters()) + list(projector.parameters()) if p.requires_grad]
+        reducer = FlatGradAllReducer(trainable)
+        opt = torch.optim.AdamW(trainable, lr=1e-4, weight_decay=0.01, fused=True, capturable=not args.no_graph)
+    else:                                    # the reference's LR groups + two clip groups (train_student_kd.py:219-234, :293-297)
+        opt = FlatAdamW(reference_param_groups(model, projector, 1e-4), weight_decay=0.01, max_grad_norm=1.0)
+        reducer = opt.reducer
 
     host = make_batch(cfg, 1234 + rank)
     keys = list(GraphedKDStep.INPUT_KEYS)
@@ -304,6 +309,7 @@ def run_ours(args):
             "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 20},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches_per_step, "cuda_graph": not args.no_graph,
+            "optimizer": "torch fused AdamW + global clip" if args.torch_optimizer else "native b2c_optimizer_step (3 LR groups, 2 clip groups)",
             "roofline": roof, "kernels": extra, "loss": final_loss}
     if rank == 0:
         line["cpu_baseline"] = cpu_baseline() if world == 1 and not args.no_cpu_baseline else None
@@ -418,6 +424,7 @@ def main():
     ap.add_argument("--impl", default="b2c", choices=["b2c", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="kd_step", choices=["kd_step", "decode"], help="kd_step = the contract's metric (default); decode = configs[3] greedy decode leg")
+    ap.add_argument("--torch-optimizer", action="store_true", help="A/B: torch fused AdamW + one global clip instead of the native optimizer step")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--profile", action="store_true", help="only warm-up + timed steps (for ncu launch lists); prints a reduced line")
     args = ap.parse_args()

@@ -66,6 +66,20 @@ class B2CDropout(ctypes.Structure):
     _fields_ = [("p", ctypes.c_float), ("seed", ctypes.c_uint64)]
 
 
+B2C_OPT_MAX_SEG, B2C_OPT_MAX_CLIP, B2C_OPT_SCRATCH_BYTES = 8, 4, 16384
+B2C_OPT_NSTATS = B2C_OPT_MAX_CLIP + 2
+
+
+class B2COptSegment(ctypes.Structure):
+    _fields_ = [("begin", ctypes.c_int64), ("end", ctypes.c_int64), ("lr_index", ctypes.c_int32), ("clip_group", ctypes.c_int32),
+                ("weight_decay", ctypes.c_float)]
+
+
+class B2COptHyper(ctypes.Structure):
+    _fields_ = [("beta1", ctypes.c_double), ("beta2", ctypes.c_double), ("eps", ctypes.c_double), ("max_norm", ctypes.c_float),
+                ("growth_factor", ctypes.c_float), ("backoff_factor", ctypes.c_float), ("growth_interval", ctypes.c_int32)]
+
+
 # every symbol include/b2c.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _f, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
 _SHP, _PRM, _GRD, _DRP = ctypes.POINTER(B2CShape), ctypes.POINTER(B2CParams), ctypes.POINTER(B2CGrads), ctypes.POINTER(B2CDropout)
@@ -87,6 +101,8 @@ SYMBOLS = {
     "b2c_aux_loss": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _f, _f, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
     "b2c_loss_finalize": (ctypes.c_int, [_vp, _vp, _i64, _vp, _f, _vp, _i32, _i32, _vp, _i32, _i32, _f, _f, _f, _f, _f, _vp, _vp]),
     "b2c_scale_inplace": (ctypes.c_int, [_vp, _i64, ctypes.c_int, _vp, _vp]),
+    "b2c_optimizer_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.POINTER(B2COptSegment), _i32, ctypes.POINTER(B2COptHyper),
+                                          _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2c_gemm": (ctypes.c_int, [_i32, _i32, _i32, _f, _vp, _i64, ctypes.c_int, _vp, _i64, ctypes.c_int, _f, _vp, _i64, _vp,
                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
 }

@@ -5,6 +5,7 @@
 #include "loss_kernels.cuh"
 #include "decoder_kernels.cuh"
 #include "refine_kernels.cuh"
+#include "optim_kernels.cuh"
 
 using namespace b2c;
 
@@ -179,15 +180,32 @@ template <typename K> int set_smem(K kern, size_t bytes) {
   return 0;
 }
 
+// Preconditions (see decoder_kernels.cuh): P and F are complete before the kernel that precedes this one in the stream
+// started -- callers issue pdl_full_dependency_next() once between the producers of P / F and that kernel.
 template <typename T>
 int attn_fwd(cudaStream_t st, const B2CShape& s, const float* P, const T* F, const float* u, T* ctx, long ldctx, float* attw) {
   const size_t smem = (size_t)s.S * s.E * sizeof(T) + (size_t)(s.E + s.S) * 4;
   const int nq = cdiv(s.E / 4, 32);
-#define B2C_ATT(NQ) do { B2C_TRY(set_smem(attn_step_fwd_kernel<T, NQ>, smem)); \
-    B2C_CUDA(launch_pdl(attn_step_fwd_kernel<T, NQ>, dim3(s.B), dim3(ATT_THREADS), smem, st, P, F, u, (long)s.E, s.S, s.E, ctx, ldctx, attw)); } while (0)
-  if (nq == 1) B2C_ATT(1); else if (nq == 2) B2C_ATT(2); else if (nq == 3) B2C_ATT(3); else B2C_ATT(0);
-#undef B2C_ATT
+  // E <= 256: 4 of the <= 7 token rows per warp are fetched in the prologue, the kernel fits 64 registers and all B = 512 CTAs
+  // are resident in one wave (measured on B200: 3.23 ms / step vs 3.28 with all 7 rows up front at 80 registers, 3 CTAs / SM)
+#define B2C_ATT_(NQ, KA) do { B2C_TRY(set_smem(attn_step_fwd_kernel<T, NQ, KA>, smem)); \
+    B2C_CUDA(launch_pdl(attn_step_fwd_kernel<T, NQ, KA>, dim3(s.B), dim3(ATT_THREADS), smem, st, P, F, u, (long)s.E, s.S, s.E, ctx, ldctx, attw)); } while (0)
+  if (nq == 1) B2C_ATT_(1, 4); else if (nq == 2) B2C_ATT_(2, 4); else if (nq == 3) B2C_ATT_(3, ATT_MAXTOK); else B2C_ATT_(0, ATT_MAXTOK);
+#undef B2C_ATT_
   B2C_LAUNCH_CHECK("attn_step_fwd_kernel");
+  return 0;
+}
+
+template <typename T>
+int attn_bwd(cudaStream_t st, int B, int S, int E, const float* P, const T* F, const float* u, const float* attw, const float* dctx, long lddctx,
+             float* ds, T* du) {
+  const size_t smem = (size_t)S * E * sizeof(T) + (size_t)(E + 2 * S) * 4;
+  constexpr int PB = 13;            // P rows per batch of the du phase (measured: 8 -> 3.25, 13 -> 3.23, 25 -> 3.32 ms / step)
+#define B2C_ATTB(PB) do { B2C_TRY(set_smem(attn_step_bwd_kernel<T, PB>, smem)); \
+    B2C_CUDA(launch_pdl(attn_step_bwd_kernel<T, PB>, dim3(B), dim3(ATT_THREADS), smem, st, P, F, u, (long)E, attw, dctx, lddctx, S, E, ds, du, (long)E)); } while (0)
+  B2C_ATTB(PB);
+#undef B2C_ATTB
+  B2C_LAUNCH_CHECK("attn_step_bwd_kernel");
   return 0;
 }
 
@@ -279,6 +297,7 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
   const int inL = in_dim(s, L - 1), ldL = inL + H;
   SubPlan sp;
   B2C_TRY(fork_subs(sp, B, st));
+  pdl_full_dependency_next();        // P / F are final before any kernel of the recurrence can start (attention prologues read them early)
   for (int t = 0; t < Tn; ++t) {
     for (int i = 0; i < sp.ns; ++i) {
       cudaStream_t ss = sp.st[i];
@@ -339,14 +358,13 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
   B2C_CUDA(cudaEventRecord(hs->join[MAX_SUB - 1], side));
   B2C_TRY((gemm<T, float>(st, (int)TB, H, E, W.do1, E, 0, W.w.W1, H, 1, W.dHext, H)));
   // ---- reverse time loop
-  const size_t att_smem = (size_t)S * E * sizeof(T) + (size_t)(E + S) * 4;
-  B2C_TRY(set_smem(attn_step_bwd_kernel<T>, att_smem));
   for (int k = 0; k < L; ++k) B2C_CHECK_ARG(g.w_ih[k] && g.w_hh[k] && g.b_ih[k] && g.b_hh[k], "NULL LSTM gradient pointer (layer %d)", k);
   // input-gradient slots of every layer and step, zeroed once: the dxh GEMMs accumulate (beta = 1) so they may split K
   B2C_CUDA(cudaMemsetAsync(W.dxh0, 0, (size_t)TB * (E + H) * sizeof(float), st));
   for (int k = 1; k < L; ++k) B2C_CUDA(cudaMemsetAsync(W.dxh[k], 0, (size_t)TB * 2 * H * sizeof(float), st));
   SubPlan sp;
   B2C_TRY(fork_subs(sp, B, st));
+  pdl_full_dependency_next();        // the forward's saves (P, u, attention weights) are final before the reverse recurrence starts
   for (int t = Tn - 1; t >= 0; --t) {
     const bool last = (t == Tn - 1);
     for (int i = 0; i < sp.ns; ++i) {
@@ -370,9 +388,7 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
       // layer 0's input gradient IS d(ctx_t): no context GEMM on the chain
       const float* dctx_t = W.dxh0 + row * (E + H);
       T* du_t = W.du + row * E;
-      B2C_CUDA(launch_pdl(attn_step_bwd_kernel<T>, dim3(Bh), dim3(ATT_THREADS), att_smem, ss, (const float*)(W.P + b0 * S * E), feats + b0 * S * E,
-                          (const float*)(W.u + row * E), (long)E, attw + row * S, dctx_t, (long)(E + H), S, E, W.ds + row * S, du_t, (long)E));
-      B2C_LAUNCH_CHECK("attn_step_bwd_kernel");
+      B2C_TRY(attn_bwd<T>(ss, Bh, S, E, W.P + b0 * S * E, feats + b0 * S * E, W.u + row * E, attw + row * S, dctx_t, (long)(E + H), W.ds + row * S, du_t));
       if (t > 0) B2C_TRY((gemm<T, T>(ss, Bh, H, E, du_t, E, 0, W.w.Wh, H, 1, W.dq + b0 * H, H)));
     }
   }
@@ -492,6 +508,7 @@ int attention_step_impl(const B2CShape& s, const float* attn_w, const float* att
   pack_params_kernel<T><<<dim3(32, 2), 256, 0, st>>>(tab);
   B2C_LAUNCH_CHECK("pack_params_kernel");
   B2C_TRY((gemm<T, float>(st, B * S, E, E, feats, E, 0, W.Wf, E, 0, W.P, E, 0.f, attn_b)));
+  pdl_full_dependency_next();        // the u contraction starts only after P is complete, so the attention prologue may read P
   B2C_TRY((gemm<T, float>(st, B, E, H, hidden, H, 0, W.Wh, H, 0, W.u, E)));
   return attn_fwd<T>(st, s, W.P, feats, W.u, context, (long)s.E, weights);
 }
@@ -958,6 +975,42 @@ int b2c_scale_inplace(void* p, int64_t n, int dtype, const float* scale, void* s
   else if (dtype == B2C_BF16) scale_inplace_kernel<bf16><<<ew_grid(n), 256, 0, st>>>((bf16*)p, (long)n, scale);
   else return set_err(B2C_EINVAL, "bad dtype %d", dtype);
   B2C_LAUNCH_CHECK("scale_inplace_kernel");
+  return 0;
+}
+
+int b2c_optimizer_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                       const B2COptSegment* segments_host, int32_t n_segments, const B2COptHyper* hyper_host,
+                       const float* lr, int32_t n_lr, int32_t* step, float* loss_scale, int32_t* growth_tracker,
+                       float* stats, void* scratch, void* stream) {
+  B2C_TRY(check_device());
+  B2C_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && segments_host && hyper_host && lr && step && stats && scratch, "null argument");
+  B2C_CHECK_ARG(n_segments >= 1 && n_segments <= B2C_OPT_MAX_SEG, "n_segments %d outside 1..%d", n_segments, B2C_OPT_MAX_SEG);
+  B2C_CHECK_ARG(((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0, "flat buffers must be 16-byte aligned");
+  B2C_CHECK_ARG(hyper_host->beta1 >= 0. && hyper_host->beta1 < 1. && hyper_host->beta2 >= 0. && hyper_host->beta2 < 1. && hyper_host->eps >= 0.,
+                "bad AdamW hyper-parameters");
+  OptSegs segs; memset(&segs, 0, sizeof(segs));
+  segs.nseg = n_segments;
+  for (int i = 0; i < n_segments; ++i) {
+    const B2COptSegment& s = segments_host[i];
+    B2C_CHECK_ARG(s.begin >= 0 && s.end >= s.begin && (s.begin & 3) == 0, "segment %d: bad range [%lld, %lld)", i, (long long)s.begin, (long long)s.end);
+    B2C_CHECK_ARG(s.lr_index >= 0 && s.lr_index < n_lr, "segment %d: lr_index %d outside 0..%d", i, s.lr_index, n_lr - 1);
+    B2C_CHECK_ARG(s.clip_group >= -1 && s.clip_group < B2C_OPT_MAX_CLIP, "segment %d: clip_group %d", i, s.clip_group);
+    segs.begin[i] = (long)s.begin; segs.end[i] = (long)s.end; segs.lr_index[i] = s.lr_index; segs.clip_group[i] = s.clip_group;
+    segs.weight_decay[i] = s.weight_decay;
+  }
+  OptHyper hp{hyper_host->beta1, hyper_host->beta2, (float)hyper_host->beta2, (float)(1.0 - hyper_host->beta1), (float)(1.0 - hyper_host->beta2),
+              (float)hyper_host->eps, hyper_host->max_norm, hyper_host->growth_factor, hyper_host->backoff_factor, hyper_host->growth_interval};
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = 4 * sm_count();
+  static_assert(16 + 4 * 160 * 4 * OPT_NPART <= B2C_OPT_SCRATCH_BYTES, "scratch too small for the partials");
+  B2C_CHECK_ARG(nblk <= 4 * 160, "unexpected SM count");
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch);
+  float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 16);
+  grad_sqnorm_kernel<<<nblk, OPT_THREADS, 0, st>>>(grad, segs, partials);
+  B2C_LAUNCH_CHECK("grad_sqnorm_kernel");
+  clip_adamw_kernel<<<nblk, OPT_THREADS, 0, st>>>(param, grad, exp_avg, exp_avg_sq, segs, hp, lr, step, loss_scale, growth_tracker,
+                                                  partials, nblk, stats, ticket);
+  B2C_LAUNCH_CHECK("clip_adamw_kernel");
   return 0;
 }
 

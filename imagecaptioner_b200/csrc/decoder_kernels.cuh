@@ -66,21 +66,15 @@ constexpr int ATT_MAXTOK = 7;     // tokens per warp held in registers (S <= 56 
 
 // F_b (the S x E feature tokens of one sample, compute type) is staged in shared memory by one 1-D TMA bulk copy on an
 // mbarrier.  P_b (the hoisted projection, fp32 in both modes because the score sums E tanh terms) is used exactly once per
-// step, so it is streamed from L2 with coalesced 128-bit loads that overlap the TMA instead of taking shared memory:
-// 26 KB per CTA at E=256 bf16, so all B CTAs of a step are co-resident and their loads overlap each other's math.
-template <typename T>
-__device__ __forceinline__ void att_stage_F(const T* F, int b, int SE, T* Fs, uint64_t* bar) {
-  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const uint32_t fb = (uint32_t)(SE * sizeof(T));
-    mbar_arrive_expect_tx(bar, fb);
-    bulk_g2s(Fs, F + (long)b * SE, fb, bar);
-  }
-}
-
-template <typename T, int NQ>       // NQ = float4 per lane per token held in registers (ceil(E/128)); 0 = generic loop
-__global__ void __launch_bounds__(ATT_THREADS)
+// step, so it is streamed from L2 with coalesced 128-bit loads into registers instead of taking shared memory:
+// 26 KB per CTA at E=256 bf16, so all B CTAs of a step are co-resident.
+//
+// Latency structure (ncu: no pipe above 35 %, the kernels are a chain of L2 round trips): P, F (and in the backward also the
+// saved u and attention weights) are LOOP INVARIANTS, so their loads are issued BEFORE griddepcontrol.wait and overlap the
+// tail of the preceding kernel; only u (forward) / d ctx (backward) wait for it.  Callers break the early-start cascade once
+// after the producers of the invariants (pdl_full_dependency_next in common.cuh).
+template <typename T, int NQ, int KA>  // NQ = float4 per lane per token (ceil(E/128)); 0 = generic loop.  KA = tokens per warp fetched in the prologue
+__global__ void __launch_bounds__(ATT_THREADS, KA >= ATT_MAXTOK ? 1 : 4)
 attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const float* __restrict__ u, long ldu,
                      int S, int E, T* __restrict__ ctx, long ldctx, float* __restrict__ attw /* (B,S) or null */) {
   extern __shared__ __align__(128) unsigned char att_smem[];
@@ -92,43 +86,67 @@ attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATT_THREADS / 32;
   const int b = blockIdx.x;
   pdl_launch_dependents();
-  pdl_wait();
-  att_stage_F<T>(F, b, SE, Fs, &bar);
-  for (int e = tid; e < E; e += ATT_THREADS) us[e] = u[(long)b * ldu + e];
-  __syncthreads();
-  // scores: warp per token, lanes over E in float4 units.  P is streamed: every warp first issues ALL its loads (its
-  // <= ATT_MAXTOK tokens x ATT_MAXQ float4 per lane) so they are in flight together, then does the tanh sums from registers.
+  // ---- prologue: independent of the preceding kernel
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
   const float4* Pb = reinterpret_cast<const float4*>(P + (long)b * SE);
   const int E4 = E >> 2;
-  if (NQ > 0 && S <= ATT_MAXTOK * nwarp) {
-    constexpr int NQR = NQ > 0 ? NQ : 1;
-    float4 pv[ATT_MAXTOK][NQR];
+  constexpr int NQR = NQ > 0 ? NQ : 1;
+  constexpr int KB = ATT_MAXTOK - KA > 0 ? ATT_MAXTOK - KA : 1;
+  const bool fast = NQ > 0 && S <= ATT_MAXTOK * nwarp;
+  float4 pa[KA][NQR];
+  if (fast) {
 #pragma unroll
-    for (int k = 0; k < ATT_MAXTOK; ++k) {
+    for (int k = 0; k < KA; ++k) {
       const int l = warp + k * nwarp;
 #pragma unroll
       for (int j = 0; j < NQR; ++j) {
         const int q = lane + j * 32;
-        if (l < S && q < E4) pv[k][j] = __ldg(Pb + l * E4 + q);
+        if (l < S && q < E4) pa[k][j] = __ldg(Pb + l * E4 + q);
       }
     }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t fb = (uint32_t)(SE * sizeof(T));
+    mbar_arrive_expect_tx(&bar, fb);
+    bulk_g2s(Fs, F + (long)b * SE, fb, &bar);
+  }
+  pdl_wait();
+  for (int e = tid; e < E; e += ATT_THREADS) us[e] = u[(long)b * ldu + e];
+  __syncthreads();
+  // scores: warp per token, lanes over E in float4 units
+  auto score = [&](const float4 (&pv)[NQR], int l) {
+    float a = 0.f;
 #pragma unroll
-    for (int k = 0; k < ATT_MAXTOK; ++k) {
-      const int l = warp + k * nwarp;
-      if (l < S) {
-        float a = 0.f;
+    for (int j = 0; j < NQR; ++j) {
+      const int q = lane + j * 32;
+      if (q < E4) {
+        const float4 p = pv[j];
+        const float4 uu = *reinterpret_cast<const float4*>(us + q * 4);
+        a += Math<T>::tanh_(p.x + uu.x) + Math<T>::tanh_(p.y + uu.y) + Math<T>::tanh_(p.z + uu.z) + Math<T>::tanh_(p.w + uu.w);
+      }
+    }
+    a = warp_sum(a);
+    if (lane == 0) sc[l] = a;
+  };
+  if (fast) {
+    float4 pb[KB][NQR];
+    if (KA < ATT_MAXTOK) {
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {
+        const int l = warp + (KA + k) * nwarp;
 #pragma unroll
         for (int j = 0; j < NQR; ++j) {
           const int q = lane + j * 32;
-          if (q < E4) {
-            const float4 p = pv[k][j];
-            const float4 uu = *reinterpret_cast<const float4*>(us + q * 4);
-            a += Math<T>::tanh_(p.x + uu.x) + Math<T>::tanh_(p.y + uu.y) + Math<T>::tanh_(p.z + uu.z) + Math<T>::tanh_(p.w + uu.w);
-          }
+          if (l < S && q < E4) pb[k][j] = __ldg(Pb + l * E4 + q);
         }
-        a = warp_sum(a);
-        if (lane == 0) sc[l] = a;
       }
+    }
+#pragma unroll
+    for (int k = 0; k < KA; ++k) { const int l = warp + k * nwarp; if (l < S) score(pa[k], l); }
+    if (KA < ATT_MAXTOK) {
+#pragma unroll
+      for (int k = 0; k < KB; ++k) { const int l = warp + (KA + k) * nwarp; if (l < S) score(pb[k], l); }
     }
   } else {
     for (int l = warp; l < S; l += nwarp) {
@@ -154,7 +172,7 @@ attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
     for (int l = lane; l < S; l += 32) { const float wv = sc[l] * inv; sc[l] = wv; if (attw) attw[(long)b * S + l] = wv; }
   }
   __syncthreads();
-  mbar_wait(&bar, 0);                          // the feature tokens have landed (their copy overlapped the score phase)
+  mbar_wait(&bar, 0);                          // the feature tokens have landed (their copy overlapped everything above)
   for (int e = tid; e < E; e += ATT_THREADS) {
     float a = 0.f;
     for (int l = 0; l < S; ++l) a = fmaf(sc[l], to_f<T>(Fs[l * E + e]), a);
@@ -164,8 +182,10 @@ attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
 
 // Backward of one attention step (inside the reverse time loop): ds (B,S) and du (B,E).
 //   dw_l = sum_e dctx_e F[l,e];  ds_l = w_l (dw_l - sum_j w_j dw_j);  du_e = sum_l ds_l (1 - tanh^2(P[l,e]+u_e))
-template <typename T>
-__global__ void __launch_bounds__(ATT_THREADS)
+// Shared memory: Fs (S*E) | dcs (E) | dw (S) | ws (S).  The du phase walks P in batches of PB rows, the next batch in flight
+// while the current one goes through the MUFU (the unbatched loop was 49 serialised L2 round trips: 58 % of all stall samples).
+template <typename T, int PB>
+__global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const float* __restrict__ u, long ldu,
                      const float* __restrict__ attw, const float* __restrict__ dctx, long lddctx,
                      int S, int E, float* __restrict__ ds_out, T* __restrict__ du, long lddu) {
@@ -174,33 +194,92 @@ attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
   T* Fs = reinterpret_cast<T*>(att_smem);
   float* dcs = reinterpret_cast<float*>(Fs + SE);
   float* dw = dcs + E;
+  float* ws = dw + S;
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATT_THREADS / 32;
   const int b = blockIdx.x;
+  const float* Pb = P + (long)b * SE;
   pdl_launch_dependents();
+  // ---- prologue: F, P, u and the attention weights were written by the forward pass
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  for (int l = tid; l < S; l += ATT_THREADS) ws[l] = attw[(long)b * S + l];
+  float cur[PB];
+  float ue0 = 0.f;
+  if (tid < E) {
+    ue0 = u[(long)b * ldu + tid];
+#pragma unroll
+    for (int i = 0; i < PB; ++i) if (i < S) cur[i] = __ldg(Pb + (long)i * E + tid);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t fb = (uint32_t)(SE * sizeof(T));
+    mbar_arrive_expect_tx(&bar, fb);
+    bulk_g2s(Fs, F + (long)b * SE, fb, &bar);
+  }
   pdl_wait();
-  att_stage_F<T>(F, b, SE, Fs, &bar);
   for (int e = tid; e < E; e += ATT_THREADS) dcs[e] = dctx[(long)b * lddctx + e];
   __syncthreads();
   mbar_wait(&bar, 0);
-  for (int l = warp; l < S; l += nwarp) {
-    float a = 0.f;
-    for (int e = lane; e < E; e += 32) a = fmaf(dcs[e], to_f<T>(Fs[l * E + e]), a);
-    a = warp_sum(a);
-    if (lane == 0) dw[l] = a;
+  // dw: warp per token, each lane owns 8-element chunks (one 16-byte shared load per token in bf16)
+  if (E <= 256) {
+    float d[8];
+    const int c = lane * 8;
+    const bool on = c < E;
+    if (on) Vec8<float>::load(dcs + c, d);
+    for (int l = warp; l < S; l += nwarp) {
+      float a = 0.f;
+      if (on) {
+        float f[8];
+        Vec8<T>::load(Fs + l * E + c, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a = fmaf(d[i], f[i], a);
+      }
+      a = warp_sum(a);
+      if (lane == 0) dw[l] = a;
+    }
+  } else {
+    for (int l = warp; l < S; l += nwarp) {
+      float a = 0.f;
+      for (int c = lane * 8; c < E; c += 256) {
+        float f[8], d[8];
+        Vec8<T>::load(Fs + l * E + c, f);
+        Vec8<float>::load(dcs + c, d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a = fmaf(d[i], f[i], a);
+      }
+      a = warp_sum(a);
+      if (lane == 0) dw[l] = a;
+    }
   }
   __syncthreads();
   if (warp == 0) {
     float dot = 0.f;
-    for (int l = lane; l < S; l += 32) dot = fmaf(attw[(long)b * S + l], dw[l], dot);
+    for (int l = lane; l < S; l += 32) dot = fmaf(ws[l], dw[l], dot);
     dot = warp_sum(dot);
-    for (int l = lane; l < S; l += 32) { const float v = attw[(long)b * S + l] * (dw[l] - dot); dw[l] = v; ds_out[(long)b * S + l] = v; }
+    for (int l = lane; l < S; l += 32) { const float v = ws[l] * (dw[l] - dot); dw[l] = v; ds_out[(long)b * S + l] = v; }
   }
   __syncthreads();
-  const float* Pb = P + (long)b * SE;
   for (int e = tid; e < E; e += ATT_THREADS) {
-    float a = 0.f; const float ue = u[(long)b * ldu + e];
-    for (int l = 0; l < S; ++l) { const float th = Math<T>::tanh_(__ldg(Pb + l * E + e) + ue); a = fmaf(dw[l], 1.0f - th * th, a); }
+    float ue = ue0;
+    if (e != tid) {
+      ue = u[(long)b * ldu + e];
+#pragma unroll
+      for (int i = 0; i < PB; ++i) if (i < S) cur[i] = __ldg(Pb + (long)i * E + e);
+    }
+    float a = 0.f;
+    for (int l0 = 0; l0 < S; l0 += PB) {
+      float nxt[PB];
+      if (l0 + PB < S) {
+#pragma unroll
+        for (int i = 0; i < PB; ++i) if (l0 + PB + i < S) nxt[i] = __ldg(Pb + (long)(l0 + PB + i) * E + e);
+      }
+#pragma unroll
+      for (int i = 0; i < PB; ++i) {
+        if (l0 + i < S) { const float th = Math<T>::tanh_(cur[i] + ue); a = fmaf(dw[l0 + i], 1.0f - th * th, a); }
+      }
+#pragma unroll
+      for (int i = 0; i < PB; ++i) cur[i] = nxt[i];
+    }
     du[(long)b * lddu + e] = from_f<T>(a);
   }
 }
@@ -276,41 +355,9 @@ rank1_add_kernel(float* __restrict__ dW, const float* __restrict__ dbx, const fl
 }
 
 // ======================================================================================
-// LSTM cell pointwise.  Gate storage is INTERLEAVED: element (b, 4j+g) is gate g (i,f,g,o) of hidden unit j.
+// LSTM cell adjoint.  Gate storage is INTERLEAVED: element (b, 4j+g) is gate g (i,f,g,o) of hidden unit j.
+// (The forward cell is the epilogue of the gate GEMM: gemm.cuh LstmEpi.)
 // ======================================================================================
-// h goes to up to three places: the recurrent slot (next step's [input;h] row block), the next layer's input
-// (inter-layer dropout applied in training) and the top-layer output buffer.
-template <typename T>
-__global__ void __launch_bounds__(256)
-lstm_pointwise_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ c_prev, float* __restrict__ c_out,
-                          T* __restrict__ gates_out, T* __restrict__ h_rec, long ld_rec, T* __restrict__ h_next, long ld_next,
-                          T* __restrict__ h_top, long ld_top, int B, int H,
-                          float drop_p, uint64_t seed, uint32_t site, long row_base) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const long total = (long)B * H;
-  const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const long b = idx / H; const int j = (int)(idx - b * H);
-    const float* pr = pre + b * 4 * H + 4 * j;
-    const float i = Math<T>::sigmoid_(pr[0]), f = Math<T>::sigmoid_(pr[1]);
-    const float g = Math<T>::tanh_(pr[2]), o = Math<T>::sigmoid_(pr[3]);
-    const float c = fmaf(f, c_prev[idx], i * g);
-    const float h = o * Math<T>::tanh_(c);
-    c_out[idx] = c;
-    if (gates_out) {
-      T* go = gates_out + b * 4 * H + 4 * j;
-      go[0] = from_f<T>(i); go[1] = from_f<T>(f); go[2] = from_f<T>(g); go[3] = from_f<T>(o);
-    }
-    if (h_rec) h_rec[b * ld_rec + j] = from_f<T>(h);
-    if (h_next) {
-      const float m = drop_p > 0.f ? dropout_scale(seed, site, (uint64_t)((row_base + b) * H + j), drop_p, inv_keep) : 1.0f;
-      h_next[b * ld_next + j] = from_f<T>(h * m);
-    }
-    if (h_top) h_top[b * ld_top + j] = from_f<T>(h);
-  }
-}
-
 // dh = [carry] + [dh_b * mask] + [dh_ext] + [dh_hid] + [dh_q]; then the cell adjoint; dc is updated in place.
 template <typename T>
 __global__ void __launch_bounds__(256)

@@ -333,8 +333,6 @@ __global__ void count_valid_kernel(const int64_t* __restrict__ tgt, long n, int 
   __syncthreads();
   if (threadIdx.x == 0) { int s = 0; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += part[i]; *out = s; }
 }
-__global__ void set_int_kernel(int* p, int v) { *p = v; }
-
 // Kernel (4).  blockIdx < n_feat_blocks : feature KD for sample b (256 threads);  above : hidden KD, one warp per
 // (t,b) row.  Gradients already carry beta / gamma; loss partials go to workspace for the finalize kernel.
 template <typename TF, typename TH>

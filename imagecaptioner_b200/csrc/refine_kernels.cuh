@@ -21,34 +21,6 @@ __global__ void __launch_bounds__(256) cast_f32_kernel(const float* __restrict__
   }
   for (long i = n8 * 8 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) out[i] = from_f<T>(in[i]);
 }
-template <typename T>
-__global__ void __launch_bounds__(256) cast_to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, long n) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) out[i] = to_f<T>(in[i]);
-}
-
-// ------------------------------------------------------------------ 8-element (16-byte for bf16) row chunks
-template <typename T> struct Vec8;
-template <> struct Vec8<bf16> {
-  static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
-    const uint4 a = *reinterpret_cast<const uint4*>(p);
-    v[0] = bf16_lo(a.x); v[1] = bf16_hi(a.x); v[2] = bf16_lo(a.y); v[3] = bf16_hi(a.y);
-    v[4] = bf16_lo(a.z); v[5] = bf16_hi(a.z); v[6] = bf16_lo(a.w); v[7] = bf16_hi(a.w);
-  }
-  static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
-    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-  }
-};
-template <> struct Vec8<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
-    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  }
-  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-  }
-};
-
 // ------------------------------------------------------------------ LayerNorm over the last dim (eps inside the sqrt, biased variance)
 // One warp per row; lane owns 8-element chunks lane, lane+32 (E % 8 == 0, E <= 512): coalesced 16-byte accesses.
 constexpr int LN_THREADS = 256;
@@ -480,24 +452,4 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const T* __restrict__ y, 
     out[idx] = a / (float)(hi - lo);
   }
 }
-template <typename T>
-__global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__ dout, T* __restrict__ dy, int B, int L, int O, int E) {
-  const long total = (long)B * L * E;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int e = (int)(idx % E); const long bl = idx / E; const int l = (int)(bl % L); const long b = bl / L;
-    const int o_min = (int)(((long)l * O) / L), o_max = (int)((((long)(l + 1) * O + L - 1) / L) - 1);
-    float a = 0.f;
-    for (int o = o_min; o <= o_max; ++o) {
-      const int lo = (int)(((long)o * L) / O), hi = (int)(((long)(o + 1) * L + O - 1) / O);
-      if (l >= lo && l < hi) a += dout[(b * O + o) * E + e] / (float)(hi - lo);
-    }
-    dy[idx] = from_f<T>(a);
-  }
-}
-
-// out += in (fp32), used to merge the residual path gradient
-__global__ void __launch_bounds__(256) add_inplace_f32_kernel(float* __restrict__ out, const float* __restrict__ in, long n) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) out[i] += in[i];
-}
-
 }  // namespace b2c

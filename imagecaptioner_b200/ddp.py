@@ -25,29 +25,35 @@ class FlatGradAllReducer:
     """Owns one contiguous fp32 buffer; every parameter's ``.grad`` is a view into it, so autograd
     accumulates straight into the buffer and the collective is a single call with no packing copies."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
+                 offsets: Optional[List[int]] = None, numel: Optional[int] = None):
+        """``offsets`` / ``numel``: optional explicit layout (element offset of every trainable parameter, total length), used
+        by optim.FlatAdamW to keep the gradient buffer congruent with its parameter and moment buffers."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
         dev = self.params[0].device
         self.group = group
         self.world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        total = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+        if offsets is None:
+            offsets, off = [], 0
+            for p in self.params:
+                offsets.append(off)
+                off += p.numel()
+            numel = off
+        if len(offsets) != len(self.params) or numel is None or any(o + p.numel() > numel for o, p in zip(offsets, self.params)):
+            raise ValueError("offsets / numel do not describe the trainable parameters")
+        self.offsets = list(offsets)
+        self.flat = torch.zeros(numel, dtype=torch.float32, device=dev)
+        self.attach_views()
+
+    def _slot(self, i: int) -> torch.Tensor:
+        p, o = self.params[i], self.offsets[i]
+        return self.flat[o:o + p.numel()].view_as(p)
 
     def grad_views(self):
         """parameter data_ptr -> its fp32 slot in the flat buffer (for _ops.set_grad_destinations)."""
-        out, off = {}, 0
-        for p in self.params:
-            n = p.numel()
-            out[p.data_ptr()] = self.flat[off:off + n].view_as(p)
-            off += n
-        return out
+        return {p.data_ptr(): self._slot(i) for i, p in enumerate(self.params)}
 
     def detach_grads(self) -> None:
         """`.grad = None` on every parameter: the next backward's gradient tensors are adopted as-is (no add kernel)."""
@@ -56,22 +62,15 @@ class FlatGradAllReducer:
 
     def attach_views(self) -> None:
         """Point every parameter's .grad at its slot of the flat buffer (host-side only, no kernel)."""
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * 4 or p.grad.dtype != torch.float32:
-                p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+        base = self.flat.data_ptr()
+        for i, p in enumerate(self.params):
+            if p.grad is None or p.grad.data_ptr() != base + self.offsets[i] * 4 or p.grad.dtype != torch.float32:
+                p.grad = self._slot(i)
 
     def zero_grad(self) -> None:
         """Zero the buffer in place (keeps the .grad views; do NOT call optimizer.zero_grad(set_to_none=True))."""
         self.flat.zero_()
-        off = 0
-        for p in self.params:                      # re-attach views if something replaced them
-            n = p.numel()
-            if p.grad is None or p.grad.data_ptr() != self.flat[off:off + n].data_ptr():
-                p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+        self.attach_views()                        # re-attach views if something replaced them
 
     def allreduce(self, async_op: bool = False):
         """Sum over ranks, then average.  With async_op the caller waits on the returned work and calls finish()."""

@@ -6,6 +6,10 @@ student forward (refinement + decoder), FeatureProjector, DistillationLoss, back
 global-norm clip and AdamW — into ONE ``torch.cuda.CUDAGraph`` over static input buffers and replays it with a
 single launch per step ("CUDA Graph over the whole sequence at minimum").
 
+``optimizer`` is either ``optim.FlatAdamW`` (native: the reference's two clip groups and three LR groups on flat buffers,
+``max_grad_norm`` then comes from the optimizer) or any capturable ``torch.optim`` optimizer (then one global-norm clip over
+the whole flat buffer precedes ``optimizer.step()``).
+
 The step structure is the reference's training loop body (src/train_student_kd.py:262-303) with the encoders
 outside the path: the caller provides encoder features, captions, targets and the teacher's outputs.
 """
@@ -22,10 +26,16 @@ from .ddp import FlatGradAllReducer
 class GraphedKDStep:
     INPUT_KEYS = ("encoder_features", "captions_input", "targets", "teacher_logits", "teacher_features", "teacher_hiddens")
 
-    def __init__(self, model, projector, loss_module, optimizer, reducer: FlatGradAllReducer, example: Dict[str, torch.Tensor],
+    def __init__(self, model, projector, loss_module, optimizer, reducer: Optional[FlatGradAllReducer], example: Dict[str, torch.Tensor],
                  max_grad_norm: float = 1.0, autocast_dtype: Optional[torch.dtype] = torch.bfloat16, use_graph: bool = True,
                  warmup_steps: int = 3, direct_grads: bool = True):
         self.model, self.projector, self.loss_module = model, projector, loss_module
+        self._native_opt = hasattr(optimizer, "flat_param") and hasattr(optimizer, "reducer")     # optim.FlatAdamW
+        if self._native_opt:
+            if reducer is None:
+                reducer = optimizer.reducer
+            if reducer is not optimizer.reducer:
+                raise ValueError("a FlatAdamW optimizer brings its own gradient buffer: pass reducer=None or optimizer.reducer")
         self.optimizer, self.reducer = optimizer, reducer
         self.max_grad_norm = max_grad_norm
         self.autocast_dtype = autocast_dtype
@@ -91,6 +101,9 @@ class GraphedKDStep:
         return out5
 
     def _clip_and_update(self):
+        if self._native_opt:                                           # optim.FlatAdamW: unscale + per-group clip + AdamW, 2 launches
+            self.optimizer.step()
+            return
         if self.max_grad_norm is not None:                             # clip_grad_norm_ on the flat buffer, no host sync
             gn = self.reducer.flat.norm()
             self.reducer.flat.mul_(torch.clamp(self.max_grad_norm / (gn + 1e-6), max=1.0))

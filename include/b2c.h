@@ -15,6 +15,7 @@
  *   b2c_aux_loss          <- encoder_feature_distillation :56-94 + decoder_hidden_state_distillation :96-136
  *   b2c_loss_finalize     <- the alpha/beta/gamma weighting and loss_dict  :184-198
  *   b2c_scale_inplace     <- the scalar grad_output of loss.backward() (GradScaler / accumulation, train_student_kd.py:285-288)
+ *   b2c_optimizer_step    <- scaler.unscale_ + clip_grad_norm_ (x2) + AdamW.step + scaler.update   src/train_student_kd.py:230-236,290-303
  *   b2c_gemm              <- test hook for the tcgen05 / SIMT contraction tiles used inside the decoder
  *
  * Conventions
@@ -169,6 +170,43 @@ int b2c_loss_finalize(const float* row_kl, const float* row_ce, int64_t N, const
 
 /* p[i] *= *scale for i < n  (scale is a device fp32 scalar: autograd's grad_output). */
 int b2c_scale_inplace(void* p, int64_t n, int dtype, const float* scale, void* stream);
+
+/* ---- optimizer side of the step on flat fp32 buffers (every trainable parameter, its gradient and both Adam moments laid
+ * out in the same order in four equally long arrays).
+ * A segment is a run of parameters that share a learning rate, a weight decay and a clip group: the reference builds
+ * AdamW with three LR groups (encoder 0.1*lr, decoder lr, refinement + projectors lr; weight_decay 0.01;
+ * src/train_student_kd.py:230-234) and clips student_model.parameters() and each projector's parameters separately with
+ * max_norm 1.0 (:293-297), i.e. two clip groups.  Segments must start on a multiple of 4 elements. */
+#define B2C_OPT_MAX_SEG 8
+#define B2C_OPT_MAX_CLIP 4
+#define B2C_OPT_SCRATCH_BYTES 16384      /* device scratch; zero-filled ONCE by the caller before the first call */
+#define B2C_OPT_NSTATS (B2C_OPT_MAX_CLIP + 2)
+typedef struct {
+  int64_t begin, end;      /* [begin, end) in elements; begin % 4 == 0 */
+  int32_t lr_index;        /* which entry of the device array lr[] */
+  int32_t clip_group;      /* 0 .. B2C_OPT_MAX_CLIP-1: gradients of one group share one global L2 norm; -1: never clipped */
+  float weight_decay;      /* decoupled (AdamW): p *= 1 - lr * weight_decay */
+} B2COptSegment;
+typedef struct {
+  double beta1, beta2, eps; /* torch.optim.AdamW defaults 0.9, 0.999, 1e-8 (doubles, as in torch: 1 - beta is formed in fp64) */
+  float max_norm;          /* clip_grad_norm_ threshold per clip group; <= 0 disables clipping */
+  float growth_factor, backoff_factor;   /* torch.amp.GradScaler defaults 2.0, 0.5 */
+  int32_t growth_interval;               /* default 2000; only read when loss_scale != NULL */
+} B2COptHyper;
+
+/* One optimizer step, two kernel launches, no host synchronisation:
+ *   g' = grad / *loss_scale (unscale_);  if any g' is non-finite the parameters, the moments and *step are left untouched
+ *   (scaler.step skips) and *loss_scale is multiplied by backoff_factor;  otherwise each clip group is scaled by
+ *   min(1, max_norm / (||g'||_2 + 1e-6)) and AdamW is applied with bias correction for step *step + 1, *step is
+ *   incremented, and *loss_scale grows by growth_factor after growth_interval consecutive clean steps (scaler.update).
+ * lr (device, one float per LR group) is read by the kernel, so a scheduler can change it between CUDA-graph replays.
+ * loss_scale / growth_tracker may be NULL (no loss scaling: bf16 autocast).  grad is not modified.
+ * stats (device, B2C_OPT_NSTATS floats, may not be NULL): [g] = unscaled pre-clip norm of clip group g,
+ * [B2C_OPT_MAX_CLIP] = 1 if the step was skipped, [B2C_OPT_MAX_CLIP+1] = the loss scale that was applied. */
+int b2c_optimizer_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                       const B2COptSegment* segments_host, int32_t n_segments, const B2COptHyper* hyper_host,
+                       const float* lr, int32_t n_lr, int32_t* step, float* loss_scale, int32_t* growth_tracker,
+                       float* stats, void* scratch, void* stream);
 
 /* C[m,n] = act(alpha * sum_k A(m,k) B(n,k) + bias[n]) + beta*C[m,n];  a_mn/b_mn = 1 when the operand is stored
  * MN-major (A[k*lda+m]) instead of K-major (A[m*lda+k]).  dtype = operand type; c_dtype = output type.
