@@ -5,6 +5,7 @@
 #include "loss_kernels.cuh"
 #include "decoder_kernels.cuh"
 #include "refine_kernels.cuh"
+#include "mha_mma.cuh"
 #include "optim_kernels.cuh"
 
 using namespace b2c;
@@ -230,7 +231,7 @@ int lstm_layer_fwd(cudaStream_t st, const B2CShape& s, const Weights<T>& w, int 
 // buffers keep their (T, B, .) layout (a sub-batch is a row range), so the time-batched GEMMs before and after the loop
 // still see whole tensors.  Fork / join use events, which CUDA graph capture records as parallel branches.
 constexpr int MAX_SUB = 5;          // 4 sub-batch branches (B2C_SUB_BATCHES) + 1 side stream for work hidden under the recurrence
-struct SubStreams { cudaStream_t s[MAX_SUB]; cudaEvent_t fork; cudaEvent_t join[MAX_SUB]; };
+struct SubStreams { cudaStream_t s[MAX_SUB]; cudaEvent_t fork; cudaEvent_t join[MAX_SUB]; cudaEvent_t ev[4]; };
 int get_substreams(SubStreams** out) {
   static SubStreams ss; static bool ready = false;
   if (!ready) {
@@ -239,6 +240,7 @@ int get_substreams(SubStreams** out) {
       B2C_CUDA(cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming));
     }
     B2C_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) B2C_CUDA(cudaEventCreateWithFlags(&ss.ev[i], cudaEventDisableTiming));
     ready = true;
   }
   *out = &ss;
@@ -341,14 +343,22 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
   const int B = s.B, Tn = s.T, S = s.S, E = s.E, H = s.H, L = s.L, V = s.V;
   const long TB = (long)Tn * B;
   const float inv_keep = dr.p > 0.f ? 1.0f / (1.0f - dr.p) : 1.0f;
+  SubStreams* hs = nullptr;
+  B2C_TRY(get_substreams(&hs));
+  cudaStream_t side = hs->s[MAX_SUB - 1];
+  // input-gradient slots of every layer and step, zeroed once (the dxh GEMMs accumulate with beta = 1 so they may split K):
+  // 70 MB of fills, on the side stream while the head runs, joined before the recurrence
+  for (int k = 0; k < L; ++k) B2C_CHECK_ARG(g.w_ih[k] && g.w_hh[k] && g.b_ih[k] && g.b_hh[k], "NULL LSTM gradient pointer (layer %d)", k);
+  B2C_CUDA(cudaEventRecord(hs->ev[3], st));
+  B2C_CUDA(cudaStreamWaitEvent(side, hs->ev[3], 0));
+  B2C_CUDA(cudaMemsetAsync(W.dxh0, 0, (size_t)TB * (E + H) * sizeof(float), side));
+  for (int k = 1; k < L; ++k) B2C_CUDA(cudaMemsetAsync(W.dxh[k], 0, (size_t)TB * 2 * H * sizeof(float), side));
+  B2C_CUDA(cudaEventRecord(hs->ev[3], side));
   // ---- output head (time-batched).  Only d(o1) -> dH_ext feeds the time loop; the head's weight gradients run on a side
   // stream underneath the (latency-bound) recurrence and are joined after it.
   B2C_TRY((gemm<T, T>(st, (int)TB, E, V, dlogits, V, 0, W.w.W2, E, 1, W.do1, E)));
   relu_bwd_inplace_kernel<T><<<ew_grid(TB * E), 256, 0, st>>>(W.do1, W.o1, TB * E, inv_keep);
   B2C_LAUNCH_CHECK("relu_bwd_inplace_kernel");
-  SubStreams* hs = nullptr;
-  B2C_TRY(get_substreams(&hs));
-  cudaStream_t side = hs->s[MAX_SUB - 1];
   B2C_CUDA(cudaEventRecord(hs->fork, st));
   B2C_CUDA(cudaStreamWaitEvent(side, hs->fork, 0));
   B2C_TRY((gemm<T, float>(side, V, E, (int)TB, dlogits, V, 1, W.o1, E, 1, g.out3_w, E)));
@@ -358,12 +368,25 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
   B2C_CUDA(cudaEventRecord(hs->join[MAX_SUB - 1], side));
   B2C_TRY((gemm<T, float>(st, (int)TB, H, E, W.do1, E, 0, W.w.W1, H, 1, W.dHext, H)));
   // ---- reverse time loop
-  for (int k = 0; k < L; ++k) B2C_CHECK_ARG(g.w_ih[k] && g.w_hh[k] && g.b_ih[k] && g.b_hh[k], "NULL LSTM gradient pointer (layer %d)", k);
-  // input-gradient slots of every layer and step, zeroed once: the dxh GEMMs accumulate (beta = 1) so they may split K
-  B2C_CUDA(cudaMemsetAsync(W.dxh0, 0, (size_t)TB * (E + H) * sizeof(float), st));
-  for (int k = 1; k < L; ++k) B2C_CUDA(cudaMemsetAsync(W.dxh[k], 0, (size_t)TB * 2 * H * sizeof(float), st));
+  B2C_CUDA(cudaStreamWaitEvent(st, hs->ev[3], 0));                 // the zeroed dxh slots
   SubPlan sp;
   B2C_TRY(fork_subs(sp, B, st));
+  // Time-batched LSTM weight gradients over rows [r0, r1) of the (T*B, .) buffers (4H-sized rows come out interleaved and are
+  // written gate-major).  They run on the side stream after the recurrence, next to the attn_post -> dF chain on the main one.
+  // (Measured on B200: contracting the finished half of the steps on the side stream UNDER the recurrence slowed the chain by
+  // as much as it hid: 3.29 vs 3.26 ms / step.)
+  auto weight_grads = [&](cudaStream_t s2, long r0, long r1, float beta) -> int {
+    const int K = (int)(r1 - r0);
+    for (int k = 1; k < L; ++k) {
+      const int in = in_dim(s, k), ld = in + H;
+      B2C_TRY((gemm<T, float>(s2, 4 * H, in, K, W.dgates[k] + r0 * 4 * H, 4 * H, 1, W.xh[k] + r0 * ld, ld, 1, g.w_ih[k], in, beta, nullptr, 0, 1.f, H)));
+      B2C_TRY((gemm<T, float>(s2, 4 * H, H, K, W.dgates[k] + r0 * 4 * H, 4 * H, 1, W.xh[k] + r0 * ld + in, ld, 1, g.w_hh[k], H, beta, nullptr, 0, 1.f, H)));
+    }
+    B2C_TRY((gemm<T, float>(s2, 4 * H, E, K, W.dgates[0] + r0 * 4 * H, 4 * H, 1, W.xh[0] + r0 * (E + H), E + H, 1, W.dWx32, E, beta)));
+    B2C_TRY((gemm<T, float>(s2, 4 * H, E, K, W.dgates[0] + r0 * 4 * H, 4 * H, 1, W.emb + r0 * E, E, 1, W.dWe32, E, beta)));
+    B2C_TRY((gemm<T, float>(s2, 4 * H, H, K, W.dgates[0] + r0 * 4 * H, 4 * H, 1, W.xh[0] + r0 * (E + H) + E, E + H, 1, g.w_hh[0], H, beta, nullptr, 0, 1.f, H)));
+    return 0;
+  };
   pdl_full_dependency_next();        // the forward's saves (P, u, attention weights) are final before the reverse recurrence starts
   for (int t = Tn - 1; t >= 0; --t) {
     const bool last = (t == Tn - 1);
@@ -393,52 +416,53 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
     }
   }
   B2C_TRY(join_subs(sp));
-  B2C_CUDA(cudaStreamWaitEvent(st, hs->join[MAX_SUB - 1], 0));      // head weight gradients (side stream) are complete
-  // ---- post-loop, time-batched weight gradients (4H-sized rows come out interleaved and are written gate-major)
-  for (int k = 1; k < L; ++k) {
-    const int in = in_dim(s, k), ld = in + H;
-    B2C_TRY((gemm<T, float>(st, 4 * H, in, (int)TB, W.dgates[k], 4 * H, 1, W.xh[k], ld, 1, g.w_ih[k], in, 0.f, nullptr, 0, 1.f, H)));
-    B2C_TRY((gemm<T, float>(st, 4 * H, H, (int)TB, W.dgates[k], 4 * H, 1, W.xh[k] + in, ld, 1, g.w_hh[k], H, 0.f, nullptr, 0, 1.f, H)));
-    B2C_TRY(colsum<T>(st, W.dgates[k], TB, 4 * H, 4 * H, W.partial, g.b_ih[k], g.b_hh[k], H));
-  }
+  // ---- post-loop.  Main stream: the chain the caller waits for (attn_post -> dF).  Side stream: every weight gradient.
+  B2C_CUDA(cudaEventRecord(hs->ev[1], st));
+  B2C_CUDA(cudaStreamWaitEvent(side, hs->ev[1], 0));
+  B2C_TRY(weight_grads(side, 0, TB, 0.f));
+  for (int k = 0; k < L; ++k) B2C_TRY(colsum<T>(side, W.dgates[k], TB, 4 * H, 4 * H, W.partial_side, g.b_ih[k], g.b_hh[k], H));
   {
     // layer 0 with attention_combine folded in:  dW_x = dg0^T ctx,  dW_e = dg0^T emb,  db_x = colsum(dg0)
-    B2C_TRY((gemm<T, float>(st, 4 * H, E, (int)TB, W.dgates[0], 4 * H, 1, W.xh[0], E + H, 1, W.dWx32, E)));
-    B2C_TRY((gemm<T, float>(st, 4 * H, E, (int)TB, W.dgates[0], 4 * H, 1, W.emb, E, 1, W.dWe32, E)));
-    B2C_TRY((gemm<T, float>(st, 4 * H, H, (int)TB, W.dgates[0], 4 * H, 1, W.xh[0] + E, E + H, 1, g.w_hh[0], H, 0.f, nullptr, 0, 1.f, H)));
-    B2C_TRY(colsum<T>(st, W.dgates[0], TB, 4 * H, 4 * H, W.partial, g.b_ih[0], g.b_hh[0], H));
-    cast_f32_kernel<T><<<ew_grid((long)4 * H * E / 8), 256, 0, st>>>(W.dWx32, W.dWxT, (long)4 * H * E);
+    cast_f32_kernel<T><<<ew_grid((long)4 * H * E / 8), 256, 0, side>>>(W.dWx32, W.dWxT, (long)4 * H * E);
     B2C_LAUNCH_CHECK("cast_f32_kernel");
-    cast_f32_kernel<T><<<ew_grid((long)4 * H * E / 8), 256, 0, st>>>(W.dWe32, W.dWeT, (long)4 * H * E);
+    cast_f32_kernel<T><<<ew_grid((long)4 * H * E / 8), 256, 0, side>>>(W.dWe32, W.dWeT, (long)4 * H * E);
     B2C_LAUNCH_CHECK("cast_f32_kernel");
     // dW_ih0 = dW_x W_cc^T + dW_e W_ce^T + db_x (x) b_c
-    B2C_TRY((gemm<T, float>(st, 4 * H, E, E, W.dWxT, E, 0, W.w.Wcc, E, 0, g.w_ih[0], E, 0.f, nullptr, 0, 1.f, H)));
-    B2C_TRY((gemm<T, float>(st, 4 * H, E, E, W.dWeT, E, 0, W.w.Wce, E, 0, g.w_ih[0], E, 1.f, nullptr, 0, 1.f, H)));
-    rank1_add_kernel<<<ew_grid((long)4 * H * E), 256, 0, st>>>(g.w_ih[0], g.b_ih[0], p.comb_b, (long)4 * H, E);
+    B2C_TRY((gemm<T, float>(side, 4 * H, E, E, W.dWxT, E, 0, W.w.Wcc, E, 0, g.w_ih[0], E, 0.f, nullptr, 0, 1.f, H)));
+    B2C_TRY((gemm<T, float>(side, 4 * H, E, E, W.dWeT, E, 0, W.w.Wce, E, 0, g.w_ih[0], E, 1.f, nullptr, 0, 1.f, H)));
+    rank1_add_kernel<<<ew_grid((long)4 * H * E), 256, 0, side>>>(g.w_ih[0], g.b_ih[0], p.comb_b, (long)4 * H, E);
     B2C_LAUNCH_CHECK("rank1_add_kernel");
     // dW_c = [W_ih0^T dW_e | W_ih0^T dW_x],  db_c = W_ih0^T db_x
-    B2C_TRY((gemm<T, float>(st, E, E, 4 * H, W.w.Wih0, E, 1, W.dWeT, E, 1, g.comb_w, 2 * E)));
-    B2C_TRY((gemm<T, float>(st, E, E, 4 * H, W.w.Wih0, E, 1, W.dWxT, E, 1, g.comb_w + E, 2 * E)));
-    B2C_CUDA(cudaMemsetAsync(g.comb_b, 0, (size_t)E * sizeof(float), st));
-    bias_fold_bwd_kernel<<<dim3(cdiv(E, 32), 32), 256, 0, st>>>(p.w_ih[0], g.b_ih[0], 4 * H, E, g.comb_b);
+    B2C_TRY((gemm<T, float>(side, E, E, 4 * H, W.w.Wih0, E, 1, W.dWeT, E, 1, g.comb_w, 2 * E)));
+    B2C_TRY((gemm<T, float>(side, E, E, 4 * H, W.w.Wih0, E, 1, W.dWxT, E, 1, g.comb_w + E, 2 * E)));
+    B2C_CUDA(cudaMemsetAsync(g.comb_b, 0, (size_t)E * sizeof(float), side));
+    bias_fold_bwd_kernel<<<dim3(cdiv(E, 32), 32), 256, 0, side>>>(p.w_ih[0], g.b_ih[0], 4 * H, E, g.comb_b);
     B2C_LAUNCH_CHECK("bias_fold_bwd_kernel");
     // embedding rows: demb = dg0 W_e
-    B2C_TRY((gemm<T, float>(st, (int)TB, E, 4 * H, W.dgates[0], 4 * H, 0, W.w.We, E, 1, W.demb, E)));
-    B2C_CUDA(cudaMemsetAsync(g.embedding, 0, (size_t)V * E * sizeof(float), st));
-    embedding_scatter_add_kernel<<<ew_grid(TB * E), 256, 0, st>>>(W.demb, cap, TB, E, V, g.embedding);
+    B2C_TRY((gemm<T, float>(side, (int)TB, E, 4 * H, W.dgates[0], 4 * H, 0, W.w.We, E, 1, W.demb, E)));
+    B2C_CUDA(cudaMemsetAsync(g.embedding, 0, (size_t)V * E * sizeof(float), side));
+    embedding_scatter_add_kernel<<<ew_grid(TB * E), 256, 0, side>>>(W.demb, cap, TB, E, V, g.embedding);
     B2C_LAUNCH_CHECK("embedding_scatter_add_kernel");
   }
   const int inL = in_dim(s, L - 1), ldL = inL + H;
-  B2C_TRY((gemm<T, float>(st, E, H, (int)TB, W.du, E, 1, W.xh[L - 1] + inL, ldL, 1, g.attn_w, H + E)));          // dW_a[:, :H]
-  {
+  B2C_TRY((gemm<T, float>(side, E, H, (int)TB, W.du, E, 1, W.xh[L - 1] + inL, ldL, 1, g.attn_w, H + E)));          // dW_a[:, :H]
+  if (Tn <= 24) {                       // u / dctx of all steps in registers (decoder_kernels.cuh)
+    const int splits = S >= 16 ? 4 : 1, per = cdiv(S, splits), TP = (Tn + 3) & ~3;
+    attn_post_reg_kernel<T, 24><<<dim3(B, splits), ATT_THREADS, (size_t)2 * per * TP * 4, st>>>(W.P, W.u, W.dxh0, (long)(E + H), attw, W.ds, Tn, B, S, E, W.dP, dfeats);
+    B2C_LAUNCH_CHECK("attn_post_reg_kernel");
+  } else {
     const size_t smem = (size_t)Tn * (2 * E + 2 * S) * 4;
     B2C_TRY(set_smem(attn_post_kernel<T>, smem));
     attn_post_kernel<T><<<B, ATT_THREADS, smem, st>>>(W.P, W.u, W.dxh0, (long)(E + H), attw, W.ds, Tn, B, S, E, W.dP, dfeats);
     B2C_LAUNCH_CHECK("attn_post_kernel");
   }
-  B2C_TRY((gemm<T, float>(st, E, E, B * S, W.dP, E, 1, feats, E, 1, g.attn_w + H, H + E)));                        // dW_a[:, H:]
-  B2C_TRY(colsum<T>(st, W.dP, (long)B * S, E, E, W.partial, g.attn_b));
+  B2C_CUDA(cudaEventRecord(hs->ev[2], st));
   B2C_TRY((gemm<T, float>(st, B * S, E, E, W.dP, E, 0, W.w.Wf, E, 1, dfeats, E, 1.f)));                             // dF += dP W_f
+  B2C_CUDA(cudaStreamWaitEvent(side, hs->ev[2], 0));
+  B2C_TRY((gemm<T, float>(side, E, E, B * S, W.dP, E, 1, feats, E, 1, g.attn_w + H, H + E)));                      // dW_a[:, H:]
+  B2C_TRY(colsum<T>(side, W.dP, (long)B * S, E, E, W.partial_side, g.attn_b));
+  B2C_CUDA(cudaEventRecord(hs->join[MAX_SUB - 1], side));
+  B2C_CUDA(cudaStreamWaitEvent(st, hs->join[MAX_SUB - 1], 0));      // every weight gradient is complete when the call's work on `stream` is
   return 0;
 }
 
@@ -525,7 +549,7 @@ template <typename T> struct RefineWs {
     Carver c{reinterpret_cast<unsigned char*>(base), 0};
     const size_t R = (size_t)s.B * s.S, E = s.E, heads = s.H;
     Win = c.take<T>(3 * E * E); Wo = c.take<T>(E * E); W1 = c.take<T>(2 * E * E); W2 = c.take<T>(2 * E * E);
-    x = c.take<T>(R * E); qkv = c.take<T>(R * 3 * E); probs = c.take<T>((size_t)s.B * heads * s.S * s.S); attn = c.take<T>(R * E);
+    x = c.take<T>(R * E); qkv = c.take<T>(R * 3 * E); probs = c.take<T>((size_t)s.B * heads * s.S * (s.S > 64 ? s.S : 64)) /* mma path: row pitch 64 */; attn = c.take<T>(R * E);
     proj = c.take<T>(R * E); x1 = c.take<T>(R * E); f1 = c.take<T>(R * 2 * E); f2 = c.take<T>(R * E);
     mean1 = c.take<float>(R); rstd1 = c.take<float>(R); mean2 = c.take<float>(R); rstd2 = c.take<float>(R);
     dz2 = c.take<T>(R * E); df1 = c.take<T>(R * 2 * E); dz1 = c.take<T>(R * E); dattn = c.take<T>(R * E); dqkv = c.take<T>(R * 3 * E);
@@ -598,6 +622,13 @@ int refine_pack(const B2CShape& s, const B2CRefineParams& p, const RefineWs<T>& 
   return 0;
 }
 
+// bf16 mode, head_dim 64, at most 64 tokens: tensor-core kernels (mha_mma.cuh); anything else: FFMA register tiles
+template <typename T> inline bool mha_use_mma(int S, int hd) { return false; }
+template <> inline bool mha_use_mma<bf16>(int S, int hd) {
+  static const bool off = getenv("B2C_MHA_FFMA") != nullptr;
+  return !off && hd == 64 && S <= 64;
+}
+
 template <typename T>
 int refinement_forward_impl(const B2CShape& s, const B2CRefineParams& p, const float* x, T* out, void* ws, size_t ws_bytes,
                             const B2CDropout& dr, cudaStream_t st) {
@@ -609,7 +640,11 @@ int refinement_forward_impl(const B2CShape& s, const B2CRefineParams& p, const f
   cast_f32_kernel<T><<<ew_grid(R * E / 4), 256, 0, st>>>(x, W.x, R * E);
   B2C_LAUNCH_CHECK("cast_f32_kernel");
   B2C_TRY((gemm<T, T>(st, (int)R, 3 * E, E, W.x, E, 0, W.Win, E, 0, W.qkv, 3 * E, 0.f, p.in_b)));
-  {
+  if (mha_use_mma<T>(S, hd)) {
+    mha_fwd_mma_kernel<<<dim3(B, heads), MM_THREADS, 0, st>>>((const bf16*)W.qkv, (bf16*)W.attn, (bf16*)W.probs, S, E, heads, 1.0f / sqrtf((float)hd),
+                                                             dr.p, dr.seed, MHA_DROP_SITE);
+    B2C_LAUNCH_CHECK("mha_fwd_mma_kernel");
+  } else {
     const size_t smem = ((size_t)3 * S * mha_pitch(hd) + (size_t)S * mha_pitch(S)) * 4;
     B2C_TRY(set_smem(mha_fwd_kernel<T>, smem));
     mha_fwd_kernel<T><<<dim3(B, heads), MHA_THREADS, smem, st>>>(W.qkv, W.attn, W.probs, S, E, heads, 1.0f / sqrtf((float)hd), dr.p, dr.seed);
@@ -648,7 +683,13 @@ int refinement_backward_impl(const B2CShape& s, const B2CRefineParams& p, const 
   B2C_TRY((ln_bwd<T, T, T>(st, W.dz2, nullptr, 0, 0, W.x, W.proj, W.mean1, W.rstd1, p.n1_w, W.dz1, W.dz1f, W.lnpart, g.n1_w, g.n1_b, g.out_b, R, E)));
   B2C_TRY((gemm<T, float>(st, E, E, (int)R, W.dz1, E, 1, W.attn, E, 1, g.out_w, E)));
   B2C_TRY((gemm<T, T>(st, (int)R, E, E, W.dz1, E, 0, W.Wo, E, 1, W.dattn, E)));
-  {
+  if (mha_use_mma<T>(S, hd)) {
+    const size_t smem = (size_t)(dr.p > 0.f ? 7 : 6) * MM_TILE * sizeof(bf16);
+    B2C_TRY(set_smem(mha_bwd_mma_kernel, smem));
+    mha_bwd_mma_kernel<<<dim3(B, heads), MM_THREADS, smem, st>>>((const bf16*)W.qkv, (const bf16*)W.probs, (const bf16*)W.dattn, (bf16*)W.dqkv, S, E, heads,
+                                                                1.0f / sqrtf((float)hd), dr.p, dr.seed, MHA_DROP_SITE);
+    B2C_LAUNCH_CHECK("mha_bwd_mma_kernel");
+  } else {
     const size_t smem = ((size_t)4 * S * mha_pitch(hd) + (size_t)(dr.p > 0.f ? 3 : 2) * S * mha_pitch(S)) * 4;
     B2C_TRY(set_smem(mha_bwd_kernel<T>, smem));
     mha_bwd_kernel<T><<<dim3(B, heads), MHA_THREADS, smem, st>>>(W.qkv, W.probs, W.dattn, W.dqkv, S, E, heads, 1.0f / sqrtf((float)hd), dr.p, dr.seed);

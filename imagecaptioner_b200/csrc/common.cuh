@@ -45,6 +45,7 @@ template <> struct Math<float> {
   static __device__ __forceinline__ float sigmoid_(float x) { return 1.0f / (1.0f + expf(-x)); }
   static __device__ __forceinline__ float exp_(float x) { return expf(x); }
   static __device__ __forceinline__ float log_(float x) { return logf(x); }
+  static __device__ __forceinline__ float dtanh_(float x) { const float t = tanhf(x); return fmaf(-t, t, 1.0f); }      // 1 - tanh^2
 };
 // bf16 mode: MUFU ex2/rcp based forms (abs error ~1e-7).  tanh.approx (rel 2^-11) is NOT used: the attention score is a sum
 // of E tanh values, and its error goes straight into the softmax weights and from there into ReLU-mask flips downstream.
@@ -57,6 +58,9 @@ template <> struct Math<bf16> {
   static __device__ __forceinline__ float sigmoid_(float x) { return rcp_ftz_(1.0f + ex2_ftz_(-1.4426950408889634f * x)); }
   static __device__ __forceinline__ float exp_(float x) { return ex2_ftz_(1.4426950408889634f * x); }
   static __device__ __forceinline__ float log_(float x) { return __logf(x); }
+  // 1 - tanh^2(x) for the BACKWARD only: one MUFU (tanh.approx, rel. error 2^-11 ~ a quarter of a bf16 ulp).  A relative error in
+  // the derivative only rescales one gradient contribution; the forward (scores -> softmax) keeps the ex2 / rcp form above.
+  static __device__ __forceinline__ float dtanh_(float x) { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x)); return fmaf(-t, t, 1.0f); }
 };
 
 // 2^x, one MUFU (flush-to-zero: no denormal range fix-up code around it)

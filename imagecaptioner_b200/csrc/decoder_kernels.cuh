@@ -112,7 +112,8 @@ attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
     bulk_g2s(Fs, F + (long)b * SE, fb, &bar);
   }
   pdl_wait();
-  for (int e = tid; e < E; e += ATT_THREADS) us[e] = u[(long)b * ldu + e];
+  // u is the only operand produced by the preceding kernel
+  for (int e = tid; e < E; e += ATT_THREADS) us[e] = __ldcg(u + (long)b * ldu + e);
   __syncthreads();
   // scores: warp per token, lanes over E in float4 units
   auto score = [&](const float4 (&pv)[NQR], int l) {
@@ -217,7 +218,7 @@ attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
     bulk_g2s(Fs, F + (long)b * SE, fb, &bar);
   }
   pdl_wait();
-  for (int e = tid; e < E; e += ATT_THREADS) dcs[e] = dctx[(long)b * lddctx + e];
+  for (int e = tid; e < E; e += ATT_THREADS) dcs[e] = __ldcg(dctx + (long)b * lddctx + e);
   __syncthreads();
   mbar_wait(&bar, 0);
   // dw: warp per token, each lane owns 8-element chunks (one 16-byte shared load per token in bf16)
@@ -275,7 +276,7 @@ attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
       }
 #pragma unroll
       for (int i = 0; i < PB; ++i) {
-        if (l0 + i < S) { const float th = Math<T>::tanh_(cur[i] + ue); a = fmaf(dw[l0 + i], 1.0f - th * th, a); }
+        if (l0 + i < S) a = fmaf(dw[l0 + i], Math<T>::dtanh_(cur[i] + ue), a);
       }
 #pragma unroll
       for (int i = 0; i < PB; ++i) cur[i] = nxt[i];
@@ -308,12 +309,68 @@ attn_post_kernel(const float* __restrict__ P, const float* __restrict__ u /*(T,B
     const float p = P[base + idx];
     float aP = 0.f, aF = 0.f;
     for (int t = 0; t < Tn; ++t) {
-      const float th = Math<T>::tanh_(p + us[t * E + e]);
-      aP = fmaf(dss[t * S + l], 1.0f - th * th, aP);
+      aP = fmaf(dss[t * S + l], Math<T>::dtanh_(p + us[t * E + e]), aP);
       aF = fmaf(ws[t * S + l], dcs[t * E + e], aF);
     }
     dP[base + idx] = from_f<T>(aP);
     dF[base + idx] = aF;
+  }
+}
+
+// Register version of the pass above for Tn <= TMAX: a thread owns one column e and keeps u[t,e] and dctx[t,e] of ALL steps in
+// registers (they do not depend on the token), so the inner loop over steps is two broadcast 16-byte shared loads (ds, w,
+// stored [token][step]) per four steps plus the MUFU math: ~10 instructions per (token, column, step) instead of ~24 with
+// the operands in shared memory.  grid (B, token splits): blockIdx.y owns a contiguous range of tokens.
+template <typename T, int TMAX>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_post_reg_kernel(const float* __restrict__ P, const float* __restrict__ u /*(T,B,E)*/, const float* __restrict__ dctx /*(T,B,.) pitch lddctx*/, long lddctx,
+                     const float* __restrict__ attw /*(T,B,S)*/, const float* __restrict__ ds /*(T,B,S)*/,
+                     int Tn, int B, int S, int E, T* __restrict__ dP, float* __restrict__ dF) {
+  extern __shared__ __align__(128) unsigned char att_smem[];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  const int per = (S + gridDim.y - 1) / gridDim.y, l0 = blockIdx.y * per, l1 = min(S, l0 + per), nl = l1 - l0;
+  if (nl <= 0) return;
+  const int TP = (Tn + 3) & ~3;
+  float* dsT = reinterpret_cast<float*>(att_smem);      // [nl][TP]
+  float* wT = dsT + per * TP;                           // [nl][TP]
+  for (int i = tid; i < nl * TP; i += ATT_THREADS) {
+    const int ll = i / TP, t = i - ll * TP;
+    const long g = ((long)t * B + b) * S + l0 + ll;
+    dsT[i] = t < Tn ? ds[g] : 0.f;
+    wT[i] = t < Tn ? attw[g] : 0.f;
+  }
+  __syncthreads();
+  const long base = (long)b * S * E;
+  for (int e = tid; e < E; e += ATT_THREADS) {
+    float ur[TMAX], dcr[TMAX];
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) {
+      ur[t] = t < Tn ? u[((long)t * B + b) * E + e] : 0.f;
+      dcr[t] = t < Tn ? dctx[((long)t * B + b) * lddctx + e] : 0.f;
+    }
+    float p_next = P[base + (long)l0 * E + e];
+#pragma unroll 1
+    for (int l = l0; l < l1; ++l) {
+      const float p = p_next;
+      if (l + 1 < l1) p_next = P[base + (long)(l + 1) * E + e];      // next token's row is in flight under this one's MUFU work
+      const float4* d4p = reinterpret_cast<const float4*>(dsT + (l - l0) * TP);
+      const float4* w4p = reinterpret_cast<const float4*>(wT + (l - l0) * TP);
+      float aP = 0.f, aF = 0.f;
+#pragma unroll
+      for (int t4 = 0; t4 < TMAX; t4 += 4) {
+        if (t4 < TP) {
+          const float4 d4 = d4p[t4 >> 2], w4 = w4p[t4 >> 2];
+          const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            aP = fmaf(dd[j], Math<T>::dtanh_(p + ur[t4 + j]), aP);
+            aF = fmaf(ww[j], dcr[t4 + j], aF);
+          }
+        }
+      }
+      dP[base + (long)l * E + e] = from_f<T>(aP);
+      dF[base + (long)l * E + e] = aF;
+    }
   }
 }
 
@@ -359,6 +416,25 @@ rank1_add_kernel(float* __restrict__ dW, const float* __restrict__ dbx, const fl
 // (The forward cell is the epilogue of the gate GEMM: gemm.cuh LstmEpi.)
 // ======================================================================================
 // dh = [carry] + [dh_b * mask] + [dh_ext] + [dh_hid] + [dh_q]; then the cell adjoint; dc is updated in place.
+// The forward's saves (gates, c), dh_ext and dh_hid are complete before the reverse recurrence starts, so they are loaded (and
+// tanh(c) evaluated) BEFORE griddepcontrol.wait; only the carried gradients (carry, above, dq, dc) wait for the previous kernel.
+template <typename T> struct Gate4;
+template <> struct Gate4<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[4]) {
+    const uint2 a = *reinterpret_cast<const uint2*>(p);
+    v[0] = bf16_lo(a.x); v[1] = bf16_hi(a.x); v[2] = bf16_lo(a.y); v[3] = bf16_hi(a.y);
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[4]) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+  }
+};
+template <> struct Gate4<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 a = *reinterpret_cast<const float4*>(p); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 lstm_pointwise_bwd_kernel(const T* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_cur,
@@ -367,29 +443,35 @@ lstm_pointwise_bwd_kernel(const T* __restrict__ gates, const float* __restrict__
                           const float* __restrict__ dh_ext, const T* __restrict__ dh_hid, const T* __restrict__ dh_q, long ld_q,
                           T* __restrict__ dgates, int B, int H, float drop_p, uint64_t seed, uint32_t site, long row_base) {
   pdl_launch_dependents();
-  pdl_wait();
   const long total = (long)B * H;
   const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+  struct Saved { float gt[4]; float tc, cp, dh_fixed, mask; };
+  auto load_saved = [&](long idx, Saved& sv) {
     const long b = idx / H; const int j = (int)(idx - b * H);
-    float dh = 0.f;
-    if (dh_carry) dh += dh_carry[b * ld_carry + j];
-    if (dh_above) {
-      const float m = drop_p > 0.f ? dropout_scale(seed, site, (uint64_t)((row_base + b) * H + j), drop_p, inv_keep) : 1.0f;
-      dh += dh_above[b * ld_above + j] * m;
-    }
-    if (dh_ext) dh += dh_ext[idx];
-    if (dh_hid) dh += to_f<T>(dh_hid[idx]);
+    Gate4<T>::load(gates + b * 4 * H + 4 * j, sv.gt);
+    sv.tc = Math<T>::tanh_(c_cur[idx]);
+    sv.cp = c_prev[idx];
+    float d = 0.f;
+    if (dh_ext) d += dh_ext[idx];
+    if (dh_hid) d += to_f<T>(dh_hid[idx]);
+    sv.dh_fixed = d;
+    sv.mask = (dh_above && drop_p > 0.f) ? dropout_scale(seed, site, (uint64_t)((row_base + b) * H + j), drop_p, inv_keep) : 1.0f;
+  };
+  const long idx0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  Saved sv;
+  if (idx0 < total) load_saved(idx0, sv);
+  pdl_wait();
+  for (long idx = idx0; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    if (idx != idx0) load_saved(idx, sv);
+    const long b = idx / H; const int j = (int)(idx - b * H);
+    float dh = sv.dh_fixed;
+    if (dh_carry) dh += __ldcg(dh_carry + b * ld_carry + j);
+    if (dh_above) dh += __ldcg(dh_above + b * ld_above + j) * sv.mask;
     if (dh_q) dh += to_f<T>(dh_q[b * ld_q + j]);
-    const T* gt = gates + b * 4 * H + 4 * j;
-    const float i = to_f<T>(gt[0]), f = to_f<T>(gt[1]), g = to_f<T>(gt[2]), o = to_f<T>(gt[3]);
-    const float tc = Math<T>::tanh_(c_cur[idx]);
-    const float dcc = (dc_is_zero ? 0.f : dc[idx]) + dh * o * (1.0f - tc * tc);
-    T* dg = dgates + b * 4 * H + 4 * j;
-    dg[0] = from_f<T>(dcc * g * i * (1.0f - i));
-    dg[1] = from_f<T>(dcc * c_prev[idx] * f * (1.0f - f));
-    dg[2] = from_f<T>(dcc * i * (1.0f - g * g));
-    dg[3] = from_f<T>(dh * tc * o * (1.0f - o));
+    const float i = sv.gt[0], f = sv.gt[1], g = sv.gt[2], o = sv.gt[3], tc = sv.tc;
+    const float dcc = (dc_is_zero ? 0.f : __ldcg(dc + idx)) + dh * o * (1.0f - tc * tc);
+    const float dg[4] = {dcc * g * i * (1.0f - i), dcc * sv.cp * f * (1.0f - f), dcc * i * (1.0f - g * g), dh * tc * o * (1.0f - o)};
+    Gate4<T>::store(dgates + b * 4 * H + 4 * j, dg);
     dc[idx] = dcc * f;
   }
 }

@@ -15,6 +15,7 @@ outside the path: the caller provides encoder features, captions, targets and th
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -47,6 +48,7 @@ class GraphedKDStep:
         self.world = reducer.world_size
         self._side = torch.cuda.Stream()
         self._overlap = False
+        self.high_priority_chain = os.environ.get("B2C_CHAIN_PRIORITY", "1") != "0"
         # every trainable parameter here gets exactly one gradient per step from one native backward call, so the kernels may
         # write it directly into the flat all-reduce buffer (saves ~35 accumulate kernels + the buffer zeroing per step)
         self.direct_grads = direct_grads
@@ -128,12 +130,16 @@ class GraphedKDStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         self._overlap = True
+        # Captured on a HIGH-priority stream: kernel nodes keep the priority of the stream they were captured from, so the
+        # latency-bound main chain (the recurrence) is scheduled ahead of the throughput work forked onto the default-priority
+        # side streams (projector, weight gradients), which then only fills the SMs the chain leaves idle.
+        cap = torch.cuda.Stream(priority=-1) if self.high_priority_chain else torch.cuda.Stream()
         if self.world == 1:
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=cap):
                 self.out5 = self._fwd_bwd()
                 self._clip_and_update()
         else:
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=cap):
                 self.out5 = self._fwd_bwd()
             self.reducer.allreduce()
             self.graph_opt = torch.cuda.CUDAGraph()

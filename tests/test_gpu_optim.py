@@ -147,7 +147,7 @@ def test_graphed_step_with_native_optimizer_matches_torch_optimizer():
     from imagecaptioner_b200.distillation_utils import DistillationLoss
     from imagecaptioner_b200.graph import GraphedKDStep
     from imagecaptioner_b200.optim import FlatAdamW
-    from harness import build_student
+    from tests.harness import build_student
     from oracle import kd_oracle as O
     V, E, H, L, B, T = 200, 64, 128, 2, 8, 6
     params = O.init_student_params(V, E, H, L, True, seed=0)
