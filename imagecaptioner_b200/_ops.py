@@ -89,6 +89,8 @@ SYMBOLS = {
     "b2c_launch_count": (ctypes.c_uint64, []),
     "b2c_workspace_bytes": (_sz, [_SHP, ctypes.c_int, ctypes.c_int]),
     "b2c_decoder_forward": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
+    "b2c_decoder_prepare": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _sz, ctypes.c_int, _vp]),
+    "b2c_decoder_forward_prepared": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_decoder_backward": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _GRD, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_greedy_decode": (ctypes.c_int, [_SHP, _PRM, _vp, _i64, _i64, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_attention_step": (ctypes.c_int, [_SHP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
@@ -220,11 +222,51 @@ def workspace_bytes(shape: B2CShape, code: int, mode: int) -> int:
     return n
 
 
+class PreparedDecoder:
+    """Handle of a b2c_decoder_prepare call in flight on a side stream: its workspace, and what it was prepared for."""
+
+    def __init__(self, ws, cap, key, stream):
+        self.ws, self.cap, self.key, self.stream = ws, cap, key, stream
+
+
+_prepare_streams = {}
+
+
+def decoder_prepare(captions: torch.Tensor, S: int, compute_dtype: torch.dtype, L: int, params: Sequence[torch.Tensor]) -> PreparedDecoder:
+    """Enqueue the feature-independent part of the decoder forward (operand packing, embedding rows, layer-0 embedding gates)
+    on a side stream, so that it runs underneath whatever still produces the image features on the current stream
+    (AttentionRefinement).  Pass the result to DecoderFunction as `prepared`; it joins the side stream before the rest."""
+    lib = load_library()
+    dev = params[0].device
+    if dev.type != "cuda":
+        raise RuntimeError("decoder_prepare: parameters must be CUDA tensors (no CPU fallback)")
+    T, B = captions.shape
+    E = params[1].shape[0]
+    H = params[1].shape[1] - E
+    V = params[0].shape[0]
+    shape = B2CShape(B, T, S, E, H, L, V)
+    code = dtype_code(compute_dtype)
+    cap = captions.detach().to(device=dev, dtype=torch.int64).contiguous()
+    master = _master(params)
+    ws = torch.empty(workspace_bytes(shape, code, B2C_WS_TRAIN), dtype=torch.uint8, device=dev)
+    prm = _fill_struct(B2CParams(), master, L)
+    side = _prepare_streams.get(dev.index)
+    if side is None:
+        side = _prepare_streams[dev.index] = torch.cuda.Stream(device=dev, priority=-1)      # needed right after the features: same rank as the main chain
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        _check(lib.b2c_decoder_prepare(ctypes.byref(shape), ctypes.byref(prm), cap.data_ptr(), ws.data_ptr(), ws.numel(), code, _stream()),
+               "b2c_decoder_prepare")
+    ws.record_stream(side)
+    cap.record_stream(side)
+    return PreparedDecoder(ws, cap, (B, T, S, E, H, L, V, code), side)
+
+
 class DecoderFunction(torch.autograd.Function):
     """LSTMDecoder.forward (reference src/student_model.py:205-256) as one C-ABI call each way."""
 
     @staticmethod
-    def forward(ctx, feats, captions, compute_dtype, dropout_p, seed, L, *params):
+    def forward(ctx, feats, captions, compute_dtype, dropout_p, seed, L, prepared, *params):
         lib = load_library()
         _require_cuda(feats, "image_features")
         B, S, E = feats.shape
@@ -234,16 +276,24 @@ class DecoderFunction(torch.autograd.Function):
         shape = B2CShape(B, T, S, E, H, L, V)
         code = dtype_code(compute_dtype)
         f = feats.detach().to(compute_dtype).contiguous()
-        cap = captions.detach().to(device=feats.device, dtype=torch.int64).contiguous()
         master = _master(params)
-        ws = torch.empty(workspace_bytes(shape, code, B2C_WS_TRAIN), dtype=torch.uint8, device=feats.device)
+        if prepared is not None:
+            if prepared.key != (B, T, S, E, H, L, V, code):
+                raise ValueError(f"decoder was prepared for {prepared.key}, forward called with {(B, T, S, E, H, L, V, code)}")
+            ws, cap = prepared.ws, prepared.cap
+            torch.cuda.current_stream(feats.device).wait_stream(prepared.stream)
+            fwd = lib.b2c_decoder_forward_prepared
+        else:
+            cap = captions.detach().to(device=feats.device, dtype=torch.int64).contiguous()
+            ws = torch.empty(workspace_bytes(shape, code, B2C_WS_TRAIN), dtype=torch.uint8, device=feats.device)
+            fwd = lib.b2c_decoder_forward
         logits = torch.empty(T, B, V, dtype=compute_dtype, device=feats.device)
         hid = torch.empty(T, B, H, dtype=compute_dtype, device=feats.device)
         attw = torch.empty(T, B, S, dtype=torch.float32, device=feats.device)
         prm = _fill_struct(B2CParams(), master, L)
         drop = B2CDropout(float(dropout_p), int(seed))
-        _check(lib.b2c_decoder_forward(ctypes.byref(shape), ctypes.byref(prm), f.data_ptr(), cap.data_ptr(), logits.data_ptr(),
-                                       hid.data_ptr(), attw.data_ptr(), ws.data_ptr(), ws.numel(), code, ctypes.byref(drop), _stream()),
+        _check(fwd(ctypes.byref(shape), ctypes.byref(prm), f.data_ptr(), cap.data_ptr(), logits.data_ptr(),
+                   hid.data_ptr(), attw.data_ptr(), ws.data_ptr(), ws.numel(), code, ctypes.byref(drop), _stream()),
                "b2c_decoder_forward")
         ctx.b2c = (shape, code, drop, L, ws, f, cap, master, hid, attw, feats.dtype, [p.dtype for p in params])
         ctx.b2c_params = params
@@ -270,7 +320,7 @@ class DecoderFunction(torch.autograd.Function):
                "b2c_decoder_backward")
         grads = [g if g.dtype == dt else g.to(dt) for g, dt in zip(grads, pdtypes)]
         dfe = dfeats if feats_dtype == torch.float32 else dfeats.to(feats_dtype)
-        return (dfe, None, None, None, None, None, *grads)
+        return (dfe, None, None, None, None, None, None, *grads)
 
 
 def greedy_decode(feats: torch.Tensor, params: Sequence[torch.Tensor], L: int, max_len: int, start_id: int, end_id: int,

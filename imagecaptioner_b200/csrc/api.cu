@@ -278,16 +278,15 @@ int join_subs(SubPlan& sp) {
 
 // ------------------------------------------------------------------ decoder forward (teacher forced)
 // Per step: u = q W_h^T  ->  attention (ctx lands in layer 0's operand)  ->  L fused gate-GEMM + cell kernels.
+// The feature-independent part of the forward: packed operands (bf16 copies, attention_combine folded into layer 0), embedding
+// rows, the time-batched embedding half of layer 0's gates and the zero initial state, all into the TRAIN workspace.
 template <typename T>
-int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, const int64_t* cap, T* logits, T* hid_top,
-                         float* attw, void* ws, size_t ws_bytes, const B2CDropout& dr, cudaStream_t st) {
+int decoder_prepare_impl(const B2CShape& s, const B2CParams& p, const int64_t* cap, void* ws, size_t ws_bytes, cudaStream_t st) {
   TrainWs<T> W; W.carve(ws, s);
   B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
-  const int B = s.B, Tn = s.T, S = s.S, E = s.E, H = s.H, L = s.L, V = s.V;
+  const int B = s.B, Tn = s.T, E = s.E, H = s.H, L = s.L, V = s.V;
   const long TB = (long)Tn * B;
   B2C_TRY(pack_params<T>(s, p, W.w, st));
-  // time-invariant half of the attention projection: P = F W_f^T + b_a
-  B2C_TRY((gemm<T, float>(st, B * S, E, E, feats, E, 0, W.w.Wf, E, 0, W.P, E, 0.f, p.attn_b)));
   embedding_gather_kernel<T><<<ew_grid(TB * E / 4), 256, 0, st>>>(p.embedding, cap, TB, E, V, W.emb, E);
   B2C_LAUNCH_CHECK("embedding_gather_kernel");
   for (int k = 0; k < L; ++k) {
@@ -296,6 +295,19 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
   }
   // embedding half of layer 0's gate pre-activations for all steps:  G0 = emb (W_ih0 W_ce)^T + b_x
   B2C_TRY((gemm<T, T>(st, (int)TB, 4 * H, E, W.emb, E, 0, W.w.We, E, 0, W.G0, 4 * H, 0.f, W.w.bx)));
+  return 0;
+}
+
+template <typename T>
+int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, const int64_t* cap, T* logits, T* hid_top,
+                         float* attw, void* ws, size_t ws_bytes, const B2CDropout& dr, cudaStream_t st, bool prepared) {
+  TrainWs<T> W; W.carve(ws, s);
+  B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
+  const int B = s.B, Tn = s.T, S = s.S, E = s.E, H = s.H, L = s.L, V = s.V;
+  const long TB = (long)Tn * B;
+  if (!prepared) B2C_TRY(decoder_prepare_impl<T>(s, p, cap, ws, ws_bytes, st));
+  // time-invariant half of the attention projection: P = F W_f^T + b_a
+  B2C_TRY((gemm<T, float>(st, B * S, E, E, feats, E, 0, W.w.Wf, E, 0, W.P, E, 0.f, p.attn_b)));
   const int inL = in_dim(s, L - 1), ldL = inL + H;
   SubPlan sp;
   B2C_TRY(fork_subs(sp, B, st));
@@ -869,16 +881,35 @@ size_t b2c_workspace_bytes(const B2CShape* shape, int dtype, int mode) {
   return 0;
 }
 
-int b2c_decoder_forward(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
-                        void* logits, void* hidden_top, float* attn_w, void* workspace, size_t ws_bytes,
-                        int dtype, const B2CDropout* dropout, void* stream) {
+static int decoder_forward_entry(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
+                                 void* logits, void* hidden_top, float* attn_w, void* workspace, size_t ws_bytes,
+                                 int dtype, const B2CDropout* dropout, void* stream, bool prepared) {
   B2C_TRY(check_shape(shape)); B2C_TRY(check_device());
   B2C_CHECK_ARG(params && feats && captions && logits && hidden_top && attn_w && workspace, "NULL argument");
   const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0};
   B2C_CHECK_ARG(dr.p >= 0.f && dr.p < 1.f, "dropout p=%f outside [0,1)", dr.p);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == B2C_F32) return decoder_forward_impl<float>(*shape, *params, (const float*)feats, captions, (float*)logits, (float*)hidden_top, attn_w, workspace, ws_bytes, dr, st);
-  if (dtype == B2C_BF16) return decoder_forward_impl<bf16>(*shape, *params, (const bf16*)feats, captions, (bf16*)logits, (bf16*)hidden_top, attn_w, workspace, ws_bytes, dr, st);
+  if (dtype == B2C_F32) return decoder_forward_impl<float>(*shape, *params, (const float*)feats, captions, (float*)logits, (float*)hidden_top, attn_w, workspace, ws_bytes, dr, st, prepared);
+  if (dtype == B2C_BF16) return decoder_forward_impl<bf16>(*shape, *params, (const bf16*)feats, captions, (bf16*)logits, (bf16*)hidden_top, attn_w, workspace, ws_bytes, dr, st, prepared);
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+int b2c_decoder_forward(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
+                        void* logits, void* hidden_top, float* attn_w, void* workspace, size_t ws_bytes,
+                        int dtype, const B2CDropout* dropout, void* stream) {
+  return decoder_forward_entry(shape, params, feats, captions, logits, hidden_top, attn_w, workspace, ws_bytes, dtype, dropout, stream, false);
+}
+int b2c_decoder_forward_prepared(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
+                                 void* logits, void* hidden_top, float* attn_w, void* workspace, size_t ws_bytes,
+                                 int dtype, const B2CDropout* dropout, void* stream) {
+  return decoder_forward_entry(shape, params, feats, captions, logits, hidden_top, attn_w, workspace, ws_bytes, dtype, dropout, stream, true);
+}
+int b2c_decoder_prepare(const B2CShape* shape, const B2CParams* params, const int64_t* captions, void* workspace, size_t ws_bytes,
+                        int dtype, void* stream) {
+  B2C_TRY(check_shape(shape)); B2C_TRY(check_device());
+  B2C_CHECK_ARG(params && captions && workspace, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) return decoder_prepare_impl<float>(*shape, *params, captions, workspace, ws_bytes, st);
+  if (dtype == B2C_BF16) return decoder_prepare_impl<bf16>(*shape, *params, captions, workspace, ws_bytes, st);
   return set_err(B2C_EINVAL, "bad dtype %d", dtype);
 }
 

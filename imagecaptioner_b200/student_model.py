@@ -15,6 +15,8 @@ Precision mode of the decoder: bf16 (tcgen05 tensor-core tiles) when called unde
 """
 from __future__ import annotations
 
+import os
+
 from typing import List
 
 import torch
@@ -149,14 +151,19 @@ class LSTMDecoder(nn.Module):
         (inference only; inside forward / greedy the same kernel runs as part of the fused step)."""
         return _ops.attention_step(hidden, image_features, self.attention.weight, self.attention.bias, self._mode())
 
-    def forward(self, image_features, captions, hidden=None):
+    def prepare(self, captions, num_tokens):
+        """Start the part of `forward` that does not need the image features (operand packing, embedding rows, the embedding
+        half of layer 0's gates) on a side stream; pass the handle to forward(..., prepared=handle)."""
+        return _ops.decoder_prepare(captions, num_tokens, self._mode(), self.num_layers, self._param_list())
+
+    def forward(self, image_features, captions, hidden=None, prepared=None):
         """image_features (B,S,E), captions (T,B) -> outputs (T,B,V), hidden_states [T x (B,H)], attention [T x (B,S)]."""
         if hidden is not None:
             raise NotImplementedError("the b2c decoder starts from the zero state (the reference never passes `hidden`)")
         p = self.dropout_p if self.training else 0.0
         self._step += 1
         seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * self._step) & 0xFFFFFFFFFFFFFFFF if p > 0 else 0
-        logits, hid, attw = _ops.DecoderFunction.apply(image_features, captions, self._mode(), p, seed, self.num_layers,
+        logits, hid, attw = _ops.DecoderFunction.apply(image_features, captions, self._mode(), p, seed, self.num_layers, prepared,
                                                        *self._param_list())
         hidden_states = HiddenStateList(hid.unbind(0))
         hidden_states.stacked = hid
@@ -212,6 +219,7 @@ class CaptioningStudent(nn.Module):
         # `encoder` is an extension (default = the reference's ResNet-50 encoder): pass PrecomputedFeatures() to feed features
         self.encoder = CNNEncoder(embed_size=embed_size, fine_tune=True) if encoder is None else encoder
         self.use_attention_refinement = use_attention_refinement
+        self.overlap_decoder_prepare = os.environ.get("B2C_OVERLAP_PREPARE", "1") != "0"
         if use_attention_refinement:
             self.attention_refinement = AttentionRefinement(embed_size=embed_size)
         self.decoder = LSTMDecoder(vocab_size=vocab_size, embed_size=embed_size, hidden_size=hidden_size,
@@ -220,8 +228,12 @@ class CaptioningStudent(nn.Module):
     def forward(self, images, captions):
         """-> (outputs (T,B,V), encoder_features (B,49,E) UN-refined, hidden_states list, attention_weights list)."""
         encoder_features = self.encoder(images)
+        prepared = None
+        if self.use_attention_refinement and encoder_features.is_cuda and self.overlap_decoder_prepare:
+            # the decoder's feature-independent preamble runs on a side stream underneath the refinement block
+            prepared = self.decoder.prepare(captions, encoder_features.shape[1])
         refined = self.attention_refinement(encoder_features) if self.use_attention_refinement else encoder_features
-        outputs, hidden_states, attention_weights = self.decoder(refined, captions)
+        outputs, hidden_states, attention_weights = self.decoder(refined, captions, prepared=prepared)
         return outputs, encoder_features, hidden_states, attention_weights
 
     @torch.no_grad()

@@ -5,6 +5,7 @@
  *
  *   b2c_decoder_forward   <- LSTMDecoder.forward                    src/student_model.py:205-256
  *                            (attention_mechanism :173-203, nn.LSTM step :244, output_projection :247)
+ *   b2c_decoder_prepare / b2c_decoder_forward_prepared <- the same forward split at the point where the image features are first read
  *   b2c_decoder_backward  <- autograd of the above (loss.backward(), src/train_student_kd.py:288)
  *   b2c_greedy_decode     <- CaptioningStudent.caption_image loop   src/student_model.py:339-381 (batched)
  *   b2c_attention_step    <- LSTMDecoder.attention_mechanism          src/student_model.py:173-203 (stand-alone accessor)
@@ -92,6 +93,18 @@ size_t b2c_workspace_bytes(const B2CShape* shape, int dtype, int mode);
  * out: logits (T,B,V) [dtype], hidden_top (T,B,H) [dtype] (top-layer h_t), attn_w (T,B,S) fp32.
  * The workspace keeps what backward needs and must be passed unchanged to b2c_decoder_backward. */
 int b2c_decoder_forward(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
+                        void* logits, void* hidden_top, float* attn_w, void* workspace, size_t ws_bytes,
+                        int dtype, const B2CDropout* dropout, void* stream);
+
+/* The part of b2c_decoder_forward that does not read the image features: operand packing (compute-type copies of the weights,
+ * attention_combine folded into layer 0), the embedding rows of `captions`, the time-batched embedding half of layer 0's
+ * gates and the zero initial state, all written into `workspace` (mode B2C_WS_TRAIN).  It may be enqueued on a different
+ * stream while the features are still being produced (e.g. under AttentionRefinement); b2c_decoder_forward_prepared then
+ * does the rest.  The caller orders the two calls (event / stream wait); shape, params, captions, workspace and dtype must be
+ * identical in both.  b2c_decoder_forward == b2c_decoder_prepare + b2c_decoder_forward_prepared on one stream. */
+int b2c_decoder_prepare(const B2CShape* shape, const B2CParams* params, const int64_t* captions, void* workspace, size_t ws_bytes,
+                        int dtype, void* stream);
+int b2c_decoder_forward_prepared(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
                         void* logits, void* hidden_top, float* attn_w, void* workspace, size_t ws_bytes,
                         int dtype, const B2CDropout* dropout, void* stream);
 

@@ -272,3 +272,33 @@ def test_feature_projector(dims, dtype):
         for k, v in mod.named_parameters():
             lim = tol * (8 if (dtype == torch.bfloat16 and ".0." in k) else 1)      # ReLU-gated Linear, see test_refinement_block
             assert relerr(v.grad.cpu(), P[k].grad) < lim, k
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_decoder_prepare_split_is_bit_identical(dtype):
+    """b2c_decoder_prepare (side stream) + b2c_decoder_forward_prepared == b2c_decoder_forward, forward and backward."""
+    from imagecaptioner_b200 import _ops
+    V, E, H, L, B, T, S = 120, 64, 128, 2, 8, 5, 9
+    params = O.init_student_params(V, E, H, L, False, seed=4)
+    plist = [params["decoder." + k].to(DEV).requires_grad_(True) for k in _ops.param_order(L)]
+    g = torch.Generator().manual_seed(5)
+    feats = torch.randn(B, S, E, generator=g).to(DEV)
+    cap = torch.randint(1, V, (T, B), generator=g).to(DEV)
+    w = torch.randn(T, B, V, generator=g).to(DEV)
+    outs = []
+    for split in (False, True):
+        for p in plist:
+            p.grad = None
+        f = feats.clone().requires_grad_(True)
+        prepared = _ops.decoder_prepare(cap, S, dtype, L, plist) if split else None
+        logits, hid, attw = _ops.DecoderFunction.apply(f, cap, dtype, 0.0, 0, L, prepared, *plist)
+        (logits.float() * w).sum().backward()
+        torch.cuda.synchronize()
+        outs.append([logits.detach().clone(), hid.detach().clone(), attw.clone(), f.grad.clone()] + [p.grad.clone() for p in plist])
+    for i, (a, b) in enumerate(zip(*outs)):
+        if i < 3:
+            assert torch.equal(a, b)                       # forward: the same kernels on the same operands
+        else:
+            assert relerr(a, b) < 1e-6                     # backward: split-K reductions may add in a different order
+    with pytest.raises(ValueError, match="prepared for"):
+        _ops.DecoderFunction.apply(feats[:4], cap[:, :4], dtype, 0.0, 0, L, _ops.decoder_prepare(cap, S, dtype, L, plist), *plist)

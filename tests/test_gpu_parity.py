@@ -126,7 +126,7 @@ def test_training_mode_dropout_is_consistent():
     cap = torch.randint(1, V, (T, B), device=DEV)
 
     def fwd(f, seed=123):
-        return _ops.DecoderFunction.apply(f, cap, torch.float32, 0.3, seed, L, *plist)
+        return _ops.DecoderFunction.apply(f, cap, torch.float32, 0.3, seed, L, None, *plist)
     y1, h1, _ = fwd(feats); y2, _, _ = fwd(feats); y3, _, _ = fwd(feats, seed=124)
     assert torch.equal(y1, y2) and not torch.equal(y1, y3)
     f = feats.clone().requires_grad_(True)
