@@ -425,6 +425,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     constexpr int NCHUNK = BN / CH;                      // 128-byte column chunks per tile row
     constexpr int C_PER = (NCHUNK + 1) / 2;
+    // ---- fast path: a full interior tile written once (no K split, beta = 0, natural rows, 16-byte aligned C).  Straight-line
+    // code without per-element predicates: the generic path below spends most of its issue slots (and instruction-cache
+    // misses: ncu stall_no_inst + branch_resolving = 24 % of the samples of the vocab-head GEMM) on range / mode checks.
+    if (!split && beta == 0.f && vec_ok && row_unperm_h == 0 && m0 + TC_BM <= M && n0 + BN <= N && (((uintptr_t)bias) & 15) == 0) {
+      TC* crow = C + (long)(m0 + q * 32) * ldc + n0;
+#pragma unroll 1
+      for (int ci = half * C_PER; ci < (half + 1) * C_PER && ci < NCHUNK; ++ci) {
+        const int c0 = ci * CH;
+#pragma unroll
+        for (int h = 0; h < CH / 32; ++h) {
+          float v[32];
+          tmem_ld32(tacc + (uint32_t)(c0 + h * 32), v);
+          if (add_bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0 + h * 32);     // n0, c0 multiples of 32: 16-byte aligned when bias is
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = __ldg(b4 + j);
+              v[4 * j] = fmaf(alpha, v[4 * j], bb.x); v[4 * j + 1] = fmaf(alpha, v[4 * j + 1], bb.y);
+              v[4 * j + 2] = fmaf(alpha, v[4 * j + 2], bb.z); v[4 * j + 3] = fmaf(alpha, v[4 * j + 3], bb.w);
+            }
+          } else if (alpha != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= alpha;
+          }
+          if (relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          unsigned char* dst = my + lane * TC_EPI_PITCH + h * 32 * sizeof(TC);
+          if (sizeof(TC) == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              *reinterpret_cast<uint4*>(dst + j * 2) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(dst + j * 4) = make_uint4(__float_as_uint(v[j]), __float_as_uint(v[j + 1]), __float_as_uint(v[j + 2]), __float_as_uint(v[j + 3]));
+          }
+        }
+        __syncwarp();
+        TC* cchunk = crow + c0 + (lane & 7) * PER;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3);
+          *reinterpret_cast<uint4*>(cchunk + (long)r * ldc) = *reinterpret_cast<const uint4*>(my + r * TC_EPI_PITCH + (lane & 7) * 16);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      continue;
+    }
 #pragma unroll 1
     for (int ci = half * C_PER; ci < (half + 1) * C_PER && ci < NCHUNK; ++ci) {
       const int c0 = ci * CH;
