@@ -425,11 +425,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     constexpr int NCHUNK = BN / CH;                      // 128-byte column chunks per tile row
     constexpr int C_PER = (NCHUNK + 1) / 2;
-    // ---- fast path: a full interior tile written once (no K split, beta = 0, natural rows, 16-byte aligned C).  Straight-line
+    // ---- fast path: a full interior tile, written once (beta = 0) or K-split partial sums reduced into fp32 C; 16-byte aligned C.  Straight-line
     // code without per-element predicates: the generic path below spends most of its issue slots (and instruction-cache
     // misses: ncu stall_no_inst + branch_resolving = 24 % of the samples of the vocab-head GEMM) on range / mode checks.
-    if (!split && beta == 0.f && vec_ok && row_unperm_h == 0 && m0 + TC_BM <= M && n0 + BN <= N && (((uintptr_t)bias) & 15) == 0) {
-      TC* crow = C + (long)(m0 + q * 32) * ldc + n0;
+    if ((split ? sizeof(TC) == 4 : beta == 0.f) && vec_ok && m0 + TC_BM <= M && n0 + BN <= N && (((uintptr_t)bias) & 15) == 0) {
 #pragma unroll 1
       for (int ci = half * C_PER; ci < (half + 1) * C_PER && ci < NCHUNK; ++ci) {
         const int c0 = ci * CH;
@@ -465,11 +464,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         __syncwarp();
-        TC* cchunk = crow + c0 + (lane & 7) * PER;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + (lane >> 3);
-          *reinterpret_cast<uint4*>(cchunk + (long)r * ldc) = *reinterpret_cast<const uint4*>(my + r * TC_EPI_PITCH + (lane & 7) * 16);
+          const int r = it * 4 + (lane >> 3), grow = m0 + q * 32 + r;
+          const long orow = row_unperm_h ? (long)(grow & 3) * row_unperm_h + (grow >> 2) : (long)grow;   // interleaved -> gate-major row
+          TC* cp = C + orow * ldc + n0 + c0 + (lane & 7) * PER;
+          const uint4 acc = *reinterpret_cast<const uint4*>(my + r * TC_EPI_PITCH + (lane & 7) * 16);
+          if (split) {                               // K-split partial sums (fp32 C): one 16-byte vector reduction
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(cp), "f"(__uint_as_float(acc.x)), "f"(__uint_as_float(acc.y)),
+                         "f"(__uint_as_float(acc.z)), "f"(__uint_as_float(acc.w)) : "memory");
+          } else {
+            *reinterpret_cast<uint4*>(cp) = acc;
+          }
         }
         __syncwarp();
       }
