@@ -238,7 +238,10 @@ __device__ __forceinline__ uint4 epi_combine_f32(uint4 acc, uint4 old, float bet
 
 // Persistent: grid = min(work items, SMs); work item = (M tile, N tile, K split).  With K splits > 1 (fp32 output only) every split adds its partial tile into C with
 // red.global.add.f32; the host has zeroed C (beta == 0) or C already holds the value to accumulate onto (beta == 1).
-template <int BN, bool A_MN, bool B_MN, typename TC>
+// LSTM = true: the instantiation used by the recurrence (fused cell epilogue only); false: the general epilogues only.  Two
+// kernels instead of one with both keep each one's code small: the recurrence's kernels are short and run back to back with
+// other kernels, so every launch starts with a cold instruction cache.
+template <int BN, bool A_MN, bool B_MN, typename TC, bool LSTM = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, float alpha, float beta, TC* __restrict__ C, long ldc,
@@ -358,7 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(&tfull_bar[as], aph);
     tc_fence_after();
     const uint32_t tacc = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(q * 32) << 16);
-    if (le.enabled) {
+    if constexpr (LSTM) {
       // ---- fused LSTM cell: 32 accumulator columns = 8 hidden units x (i,f,g,o); straight from TMEM to the cell state buffers
       const int H = le.H, N4 = N;                        // N == 4H
       const int grow = m0 + q * 32 + lane;
@@ -422,7 +425,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       continue;
-    }
+    } else {
     constexpr int NCHUNK = BN / CH;                      // 128-byte column chunks per tile row
     constexpr int C_PER = (NCHUNK + 1) / 2;
     // ---- fast path: a full interior tile, written once (beta = 0) or K-split partial sums reduced into fp32 C; 16-byte aligned C.  Straight-line
@@ -512,7 +515,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       __syncwarp();
-#pragma unroll
+#pragma unroll 1                             // edge tiles / beta != 0 only: keep the code small
       for (int it = 0; it < 8; ++it) {
         const int r = it * 4 + (lane >> 3), part = lane & 7;
         const int grow = m0 + q * 32 + r, gcol = n0 + c0 + part * PER;
@@ -554,6 +557,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();                         // order this warp's tcgen05.ld before releasing the accumulator stage
     __syncwarp();
     if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }   // general epilogues
     }
   }
   tc_fence_before();
@@ -649,11 +653,17 @@ int launch_tc(const GemmArgs& g, const TcPlan& plan, cudaStream_t st) {
   CUtensorMap ta, tb;
   if (!A_MN) B2C_TRY(make_tmap_bf16(&ta, g.A, g.K, g.M, g.lda, TC_BM)); else B2C_TRY(make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, 64));
   if (!B_MN) B2C_TRY(make_tmap_bf16(&tb, g.B, g.K, g.N, g.ldb, BN)); else B2C_TRY(make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, 64));
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TC>;
-  static bool attr_set = false;      // per template instantiation
-  if (!attr_set) {
+  constexpr bool CAN_LSTM = !A_MN && !B_MN && sizeof(TC) == 4;
+  void (*kern)(const CUtensorMap, const CUtensorMap, int, int, int, float, float, TC*, long, const float*, int, int, int, int, int, int, const LstmEpi) =
+      gemm_tc_kernel<BN, A_MN, B_MN, TC, false>;
+  if (g.lstm) {
+    if constexpr (CAN_LSTM) kern = gemm_tc_kernel<BN, A_MN, B_MN, TC, true>;
+    else return set_err(B2C_EINVAL, "the fused LSTM epilogue needs K-major operands and fp32 accumulators out");
+  }
+  static bool attr_set[2] = {false, false};      // per template instantiation and epilogue flavour
+  if (!attr_set[g.lstm ? 1 : 0]) {
     B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<BN>::SMEM_BYTES));
-    attr_set = true;
+    attr_set[g.lstm ? 1 : 0] = true;
   }
   const int kb_per_split = plan.kb_per_split, splits = plan.splits;
   if (splits > 1 && g.beta == 0.f)
