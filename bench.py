@@ -375,20 +375,28 @@ def kernel_rooflines(lib, _ops, dev, cfg, peaks):
 
     def kd():
         rc = lib.b2c_kd_token_loss(y.data_ptr(), z.data_ptr(), tgt.data_ptr(), N, V, 4.0, 0.7, 0.0, 1.0, nval.data_ptr(), dy.data_ptr(),
-                                   rows[0].data_ptr(), rows[1].data_ptr(), _ops.B2C_BF16, st)
+                                   rows[0].data_ptr(), rows[1].data_ptr(), _ops.B2C_BF16, torch.cuda.current_stream().cuda_stream)
         assert rc == 0
 
     def timeit(fn, reps=20):
+        """Average device time of one launch: `reps` back-to-back launches captured in a CUDA graph (so the host-side ctypes /
+        tensor-map cost of a launch, ~10 us, is not what is measured), timed with CUDA events around 5 replays."""
         for _ in range(3):
             fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(reps):
-            fn()
+        for _ in range(5):
+            g.replay()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps * 1e-3
+        return e0.elapsed_time(e1) / (5 * reps) * 1e-3
 
     t_kd = timeit(kd)
     kd_bytes = N * V * (2 + 4 + 2) + 8 * N                     # read bf16 student + fp32 teacher, write bf16 dlogits, read targets

@@ -840,7 +840,7 @@ int aux_loss_impl(const TF* fs, const float* ft, int B, int Ss, int St, int E, c
   const long all_rows = hs ? (long)Tn * B : 0;
   const int hid_blocks = (int)((all_rows + 7) / 8);
   if (nfb + hid_blocks == 0) return 0;
-  const size_t smem = fs ? (size_t)(2 * Ss + 2 * St + 2 * E) * 4 : 0;
+  const size_t smem = fs ? (size_t)(2 * Ss + 2 * St + 2 * E + 8 * 2 * E + 8) * 4 : 0;       // + per-warp column partials [8][2][E]
   B2C_TRY(set_smem(aux_loss_kernel<TF, TF>, smem));
   aux_loss_kernel<TF, TF><<<nfb + hid_blocks, 256, smem, st>>>(fs, ft, nfb, B, Ss, St, E, hs, ht, (int)((long)Th * B), (int)all_rows, H, Th, beta, gamma,
                                                                dfs, dft, dhs, feat_part, hid_part);

@@ -342,22 +342,34 @@ aux_loss_kernel(const TF* __restrict__ fs, const float* __restrict__ ft, int n_f
                 int H, int Th, float beta, float gamma,
                 float* __restrict__ dfs, float* __restrict__ dft, TH* __restrict__ dhs,
                 float* __restrict__ feat_part /*B*2*/, float* __restrict__ hid_part /*n_hid_rows*2*/) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   if ((int)blockIdx.x < n_feat_blocks) {
     const int b = blockIdx.x;
     const TF* S = fs + (long)b * Ss * E;
     const float* Tp = ft + (long)b * St * E;
-    float* ps = sm;             // Ss   softmax weights (student)
-    float* pt = ps + Ss;        // St
-    float* dg = pt + St;        // E    delta of global means
-    float* da = dg + E;         // E    delta of attention-pooled
-    float* qs = da + E;         // Ss
-    float* qt = qs + Ss;        // St
+    float* dg = sm;                          // E    delta of global means            (the E-sized arrays first: 16-byte aligned)
+    float* da = dg + E;                      // E    delta of attention-pooled
+    float* part = da + E;                    // [nwarp = 8][2][E] per-warp column partials
+    float* ps = part + (long)8 * 2 * E;      // Ss   softmax weights (student)
+    float* pt = ps + Ss;                     // St
+    float* qs = pt + St;                     // Ss
+    float* qt = qs + Ss;                     // St
     __shared__ float red[16];
+    // Every pass reads the two token matrices with 16-byte accesses, warp per token row, lanes over 8-column chunks (E % 8 == 0).
+    // Pass 1 comes from HBM, the later ones from L2 (75 KB per sample).
+    const int nch = E >> 3;
     // 1. token row sums
-    for (int l = warp; l < Ss; l += nwarp) { float a = 0.f; for (int e = lane; e < E; e += 32) a += to_f<TF>(S[(long)l * E + e]); a = warp_sum(a); if (lane == 0) ps[l] = a; }
-    for (int l = warp; l < St; l += nwarp) { float a = 0.f; for (int e = lane; e < E; e += 32) a += Tp[(long)l * E + e]; a = warp_sum(a); if (lane == 0) pt[l] = a; }
+    for (int l = warp; l < Ss; l += nwarp) {
+      float a = 0.f;
+      for (int c = lane; c < nch; c += 32) { float v[8]; Vec8<TF>::load(S + (long)l * E + c * 8, v); a += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])); }
+      a = warp_sum(a); if (lane == 0) ps[l] = a;
+    }
+    for (int l = warp; l < St; l += nwarp) {
+      float a = 0.f;
+      for (int c = lane; c < nch; c += 32) { float v[8]; Vec8<float>::load(Tp + (long)l * E + c * 8, v); a += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])); }
+      a = warp_sum(a); if (lane == 0) pt[l] = a;
+    }
     __syncthreads();
     // 2. softmax over tokens (warp 0: student, warp 1: teacher)
     if (warp < 2) {
@@ -367,13 +379,33 @@ aux_loss_kernel(const TF* __restrict__ fs, const float* __restrict__ ft, int n_f
       const float inv = 1.0f / s; for (int l = lane; l < n; l += 32) p[l] *= inv;
     }
     __syncthreads();
-    // 3. pooled vectors and their deltas
+    // 3. pooled vectors: each warp sums its rows into per-column partials (global mean and attention-pooled, student minus teacher),
+    //    the partials of the 8 warps are combined through shared memory
+    for (int c = lane; c < nch; c += 32) {
+      float g8[8], a8[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { g8[k] = 0.f; a8[k] = 0.f; }
+      const float is = 1.0f / (float)Ss, it = 1.0f / (float)St;
+      for (int l = warp; l < Ss; l += nwarp) {
+        float v[8]; Vec8<TF>::load(S + (long)l * E + c * 8, v);
+        const float w = ps[l];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { g8[k] = fmaf(v[k], is, g8[k]); a8[k] = fmaf(w, v[k], a8[k]); }
+      }
+      for (int l = warp; l < St; l += nwarp) {
+        float v[8]; Vec8<float>::load(Tp + (long)l * E + c * 8, v);
+        const float w = pt[l];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { g8[k] = fmaf(-v[k], it, g8[k]); a8[k] = fmaf(-w, v[k], a8[k]); }
+      }
+      Vec8<float>::store(part + ((long)warp * 2 + 0) * E + c * 8, g8);
+      Vec8<float>::store(part + ((long)warp * 2 + 1) * E + c * 8, a8);
+    }
+    __syncthreads();
     float acc_g = 0.f, acc_a = 0.f;
     for (int e = tid; e < E; e += blockDim.x) {
-      float gs = 0.f, as = 0.f, gt = 0.f, at = 0.f;
-      for (int l = 0; l < Ss; ++l) { const float v = to_f<TF>(S[(long)l * E + e]); gs += v; as += ps[l] * v; }
-      for (int l = 0; l < St; ++l) { const float v = Tp[(long)l * E + e]; gt += v; at += pt[l] * v; }
-      const float d_g = gs / (float)Ss - gt / (float)St, d_a = as - at;
+      float d_g = 0.f, d_a = 0.f;
+      for (int w = 0; w < nwarp; ++w) { d_g += part[((long)w * 2 + 0) * E + e]; d_a += part[((long)w * 2 + 1) * E + e]; }
       dg[e] = d_g; da[e] = d_a; acc_g += d_g * d_g; acc_a += d_a * d_a;
     }
     acc_g = warp_sum(acc_g); acc_a = warp_sum(acc_a);
@@ -383,24 +415,45 @@ aux_loss_kernel(const TF* __restrict__ fs, const float* __restrict__ ft, int n_f
     // 4. gradients
     const float inv_be = 1.0f / ((float)B * (float)E);
     const float ca = 0.4f * 2.0f * inv_be, cg = 0.6f * 2.0f * inv_be;
-    for (int l = warp; l < Ss; l += nwarp) { float a = 0.f; for (int e = lane; e < E; e += 32) a += da[e] * to_f<TF>(S[(long)l * E + e]); a = warp_sum(a); if (lane == 0) qs[l] = ca * a; }
-    for (int l = warp; l < St; l += nwarp) { float a = 0.f; for (int e = lane; e < E; e += 32) a += da[e] * Tp[(long)l * E + e]; a = warp_sum(a); if (lane == 0) qt[l] = ca * a; }
+    for (int l = warp; l < Ss; l += nwarp) {
+      float a = 0.f;
+      for (int c = lane; c < nch; c += 32) {
+        float v[8], d8[8]; Vec8<TF>::load(S + (long)l * E + c * 8, v); Vec8<float>::load(da + c * 8, d8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a = fmaf(d8[k], v[k], a);
+      }
+      a = warp_sum(a); if (lane == 0) qs[l] = ca * a;
+    }
+    for (int l = warp; l < St; l += nwarp) {
+      float a = 0.f;
+      for (int c = lane; c < nch; c += 32) {
+        float v[8], d8[8]; Vec8<float>::load(Tp + (long)l * E + c * 8, v); Vec8<float>::load(da + c * 8, d8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a = fmaf(d8[k], v[k], a);
+      }
+      a = warp_sum(a); if (lane == 0) qt[l] = ca * a;
+    }
     __syncthreads();
     float qsbar = 0.f, qtbar = 0.f;
     for (int l = 0; l < Ss; ++l) qsbar += ps[l] * qs[l];
     for (int l = 0; l < St; ++l) qtbar += pt[l] * qt[l];
+    const int E4 = E >> 2;
     if (dfs != nullptr) {
-      float* D = dfs + (long)b * Ss * E;
-      for (int i = tid; i < Ss * E; i += blockDim.x) {
-        const int l = i / E, e = i - l * E;
-        D[i] = beta * (cg / (float)Ss * dg[e] + ca * da[e] * ps[l] + ps[l] * (qs[l] - qsbar));
+      float4* D = reinterpret_cast<float4*>(dfs + (long)b * Ss * E);
+      for (int i = tid; i < Ss * E4; i += blockDim.x) {
+        const int l = i / E4, e = (i - l * E4) * 4;
+        const float4 g4 = *reinterpret_cast<const float4*>(dg + e), a4 = *reinterpret_cast<const float4*>(da + e);
+        const float k1 = cg / (float)Ss, k2 = ca * ps[l], k3 = ps[l] * (qs[l] - qsbar);
+        D[i] = make_float4(beta * (k1 * g4.x + k2 * a4.x + k3), beta * (k1 * g4.y + k2 * a4.y + k3), beta * (k1 * g4.z + k2 * a4.z + k3), beta * (k1 * g4.w + k2 * a4.w + k3));
       }
     }
     if (dft != nullptr) {
-      float* D = dft + (long)b * St * E;
-      for (int i = tid; i < St * E; i += blockDim.x) {
-        const int l = i / E, e = i - l * E;
-        D[i] = -beta * (cg / (float)St * dg[e] + ca * da[e] * pt[l] + pt[l] * (qt[l] - qtbar));
+      float4* D = reinterpret_cast<float4*>(dft + (long)b * St * E);
+      for (int i = tid; i < St * E4; i += blockDim.x) {
+        const int l = i / E4, e = (i - l * E4) * 4;
+        const float4 g4 = *reinterpret_cast<const float4*>(dg + e), a4 = *reinterpret_cast<const float4*>(da + e);
+        const float k1 = cg / (float)St, k2 = ca * pt[l], k3 = pt[l] * (qt[l] - qtbar);
+        D[i] = make_float4(-beta * (k1 * g4.x + k2 * a4.x + k3), -beta * (k1 * g4.y + k2 * a4.y + k3), -beta * (k1 * g4.z + k2 * a4.z + k3), -beta * (k1 * g4.w + k2 * a4.w + k3));
       }
     }
   } else {
@@ -415,7 +468,22 @@ aux_loss_kernel(const TF* __restrict__ fs, const float* __restrict__ ft, int n_f
     }
     const float* t = ht + row * H;
     float sq = 0.f, dot = 0.f, ns = 0.f, nt = 0.f;
-    for (int h = lane; h < H; h += 32) { const float a = to_f<TH>(s[h]), c = t[h]; const float df = a - c; sq += df * df; dot += a * c; ns += a * a; nt += c * c; }
+    constexpr int HC = 2;                                   // H <= 512: the row stays in registers between the two passes
+    const bool in_regs = (H & 7) == 0 && H <= HC * 256;
+    float sa[HC][8], tc[HC][8];
+    if (in_regs) {
+#pragma unroll
+      for (int c = 0; c < HC; ++c) {
+        const int ch = lane + 32 * c;
+        if (ch * 8 < H) {
+          Vec8<TH>::load(s + ch * 8, sa[c]); Vec8<float>::load(t + ch * 8, tc[c]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { const float a = sa[c][k], cc = tc[c][k], df = a - cc; sq += df * df; dot += a * cc; ns += a * a; nt += cc * cc; }
+        }
+      }
+    } else {
+      for (int h = lane; h < H; h += 32) { const float a = to_f<TH>(s[h]), c = t[h]; const float df = a - c; sq += df * df; dot += a * c; ns += a * a; nt += c * c; }
+    }
     sq = warp_sum(sq); dot = warp_sum(dot); ns = warp_sum(ns); nt = warp_sum(nt);
     const float eps = 1e-12f;
     const float nse = ns + eps, nte = nt + eps;
@@ -425,9 +493,23 @@ aux_loss_kernel(const TF* __restrict__ fs, const float* __restrict__ ft, int n_f
     if (d) {
       const float c_mse = gamma / (float)Th * 0.7f * 2.0f / ((float)B * (float)H);
       const float c_cos = gamma / (float)Th * 0.3f / (float)B;
-      for (int h = lane; h < H; h += 32) {
-        const float a = to_f<TH>(s[h]), c = t[h];
-        d[h] = from_f<TH>(c_mse * (a - c) - c_cos * (c * inv_norm - cosv * a / nse));
+      if (in_regs) {
+        const float k_a = cosv / nse;
+#pragma unroll
+        for (int c = 0; c < HC; ++c) {
+          const int ch = lane + 32 * c;
+          if (ch * 8 < H) {
+            float o8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o8[k] = c_mse * (sa[c][k] - tc[c][k]) - c_cos * (tc[c][k] * inv_norm - k_a * sa[c][k]);
+            Vec8<TH>::store(d + ch * 8, o8);
+          }
+        }
+      } else {
+        for (int h = lane; h < H; h += 32) {
+          const float a = to_f<TH>(s[h]), c = t[h];
+          d[h] = from_f<TH>(c_mse * (a - c) - c_cos * (c * inv_norm - cosv * a / nse));
+        }
       }
     }
   }

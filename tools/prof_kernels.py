@@ -17,7 +17,17 @@ dy = torch.empty_like(y); rows = torch.empty(2, N, device=dev)
 A = torch.randn(N, E, device=dev).bfloat16(); W = torch.randn(V, E, device=dev).bfloat16(); C = torch.empty(N, V, device=dev, dtype=torch.bfloat16)
 A2 = torch.randn(B, E + H, device=dev).bfloat16(); W2 = torch.randn(4 * H, E + H, device=dev).bfloat16(); C2 = torch.empty(B, 4 * H, device=dev)
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+# AttentionRefinement at the bench shape (tensor-core MHA forward / backward) and the native optimizer step on 7.3 M parameters
+from imagecaptioner_b200.student_model import AttentionRefinement
+from imagecaptioner_b200.optim import FlatAdamW
+ref = AttentionRefinement(E, 4).to(dev).eval(); ref.compute_dtype = torch.bfloat16
+xr = torch.randn(B, 49, E, device=dev, requires_grad=True)
+big = [torch.nn.Parameter(torch.randn(7_330_000 // 2, device=dev)), torch.nn.Parameter(torch.randn(7_330_000 // 2, device=dev))]
+opt = FlatAdamW([{"params": [big[0]], "clip_group": 0}, {"params": [big[1]], "clip_group": 1}], lr=1e-4)
+opt.reducer.flat.normal_()
 for _ in range(reps):
+    out = ref(xr); out.float().sum().backward()
+    opt.step()
     assert lib.b2c_kd_token_loss(y.data_ptr(), z.data_ptr(), tgt.data_ptr(), N, V, 4.0, 0.7, 0.0, 1.0, nval.data_ptr(), dy.data_ptr(),
                                  rows[0].data_ptr(), rows[1].data_ptr(), _ops.B2C_BF16, st) == 0
     _ops.gemm(A, W, N, V, E, C=C)
