@@ -76,7 +76,7 @@ class B2COptSegment(ctypes.Structure):
 
 
 class B2COptHyper(ctypes.Structure):
-    _fields_ = [("beta1", ctypes.c_double), ("beta2", ctypes.c_double), ("eps", ctypes.c_double), ("max_norm", ctypes.c_float),
+    _fields_ = [("beta1", ctypes.c_double), ("beta2", ctypes.c_double), ("eps", ctypes.c_double), ("max_norm", ctypes.c_float), ("grad_scale", ctypes.c_float),
                 ("growth_factor", ctypes.c_float), ("backoff_factor", ctypes.c_float), ("growth_interval", ctypes.c_int32)]
 
 
@@ -222,6 +222,11 @@ def workspace_bytes(shape: B2CShape, code: int, mode: int) -> int:
     return n
 
 
+# Optional callable run right after b2c_decoder_backward is enqueued (same stream): graph.GraphedKDStep records an event there
+# so the gradient all-reduce of the decoder's parameters can start while the refinement backward still runs.
+after_decoder_backward = None
+
+
 class PreparedDecoder:
     """Handle of a b2c_decoder_prepare call in flight on a side stream: its workspace, and what it was prepared for."""
 
@@ -318,6 +323,8 @@ class DecoderFunction(torch.autograd.Function):
                                         dlogits.data_ptr(), _ptr(dhid), ctypes.byref(grd), dfeats.data_ptr(), ws.data_ptr(), ws.numel(),
                                         code, ctypes.byref(drop), _stream()),
                "b2c_decoder_backward")
+        if after_decoder_backward is not None:          # GraphedKDStep: the decoder's gradients are final from here on this stream
+            after_decoder_backward()
         grads = [g if g.dtype == dt else g.to(dt) for g, dt in zip(grads, pdtypes)]
         dfe = dfeats if feats_dtype == torch.float32 else dfeats.to(feats_dtype)
         return (dfe, None, None, None, None, None, None, *grads)

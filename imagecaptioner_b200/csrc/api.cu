@@ -1062,6 +1062,7 @@ int b2c_optimizer_step(float* param, const float* grad, float* exp_avg, float* e
   B2C_CHECK_ARG(((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0, "flat buffers must be 16-byte aligned");
   B2C_CHECK_ARG(hyper_host->beta1 >= 0. && hyper_host->beta1 < 1. && hyper_host->beta2 >= 0. && hyper_host->beta2 < 1. && hyper_host->eps >= 0.,
                 "bad AdamW hyper-parameters");
+  B2C_CHECK_ARG(hyper_host->grad_scale > 0.f, "grad_scale must be positive (1 when unused)");
   OptSegs segs; memset(&segs, 0, sizeof(segs));
   segs.nseg = n_segments;
   for (int i = 0; i < n_segments; ++i) {
@@ -1073,7 +1074,7 @@ int b2c_optimizer_step(float* param, const float* grad, float* exp_avg, float* e
     segs.weight_decay[i] = s.weight_decay;
   }
   OptHyper hp{hyper_host->beta1, hyper_host->beta2, (float)hyper_host->beta2, (float)(1.0 - hyper_host->beta1), (float)(1.0 - hyper_host->beta2),
-              (float)hyper_host->eps, hyper_host->max_norm, hyper_host->growth_factor, hyper_host->backoff_factor, hyper_host->growth_interval};
+              (float)hyper_host->eps, hyper_host->max_norm, hyper_host->grad_scale, hyper_host->growth_factor, hyper_host->backoff_factor, hyper_host->growth_interval};
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = 4 * sm_count();
   static_assert(16 + 4 * 160 * 4 * OPT_NPART <= B2C_OPT_SCRATCH_BYTES, "scratch too small for the partials");

@@ -63,6 +63,7 @@ grad_sqnorm_kernel(const float* __restrict__ g, OptSegs segs, float* __restrict_
 struct OptHyper {
   double beta1d, beta2d;                      // for the bias corrections 1 - beta^t (fp64, one thread per block)
   float beta2, omb1, omb2, eps, max_norm;     // omb = (float)(1 - beta) formed in fp64 on the host, as torch does
+  float grad_scale;                           // applied to every gradient before anything else (1/world after a SUM all-reduce)
   float growth_factor, backoff_factor;
   int growth_interval;
 };
@@ -92,7 +93,7 @@ clip_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
   }
   __syncthreads();
   const float scale = loss_scale ? *loss_scale : 1.0f;
-  const float inv_scale = 1.0f / scale;
+  const float inv_scale = hp.grad_scale / scale;
   const int t = *step + 1;
   if (threadIdx.x == 0) {
     float tot[OPT_NPART];

@@ -38,6 +38,10 @@ class GraphedKDStep:
             if reducer is not optimizer.reducer:
                 raise ValueError("a FlatAdamW optimizer brings its own gradient buffer: pass reducer=None or optimizer.reducer")
         self.optimizer, self.reducer = optimizer, reducer
+        # native optimizer: the 1/world of the gradient average is applied inside the update kernel instead of a pass of its own
+        self._fold_avg = self._native_opt and reducer.world_size > 1
+        if self._fold_avg:
+            optimizer.fold_average(reducer.world_size)
         self.max_grad_norm = max_grad_norm
         self.autocast_dtype = autocast_dtype
         self.static = {k: example[k].clone() for k in self.INPUT_KEYS if example.get(k) is not None}
@@ -48,6 +52,7 @@ class GraphedKDStep:
         self.world = reducer.world_size
         self._side = torch.cuda.Stream()
         self._overlap = False
+        self._capturing = False
         self.high_priority_chain = os.environ.get("B2C_CHAIN_PRIORITY", "1") != "0"
         # every trainable parameter here gets exactly one gradient per step from one native backward call, so the kernels may
         # write it directly into the flat all-reduce buffer (saves ~35 accumulate kernels + the buffer zeroing per step)
@@ -57,15 +62,46 @@ class GraphedKDStep:
             _ops.set_grad_destinations(reducer.grad_views())
         # Data parallel: NCCL stays OUTSIDE the graphs.  The non-PAD count is all-reduced before graph 1 (targets are an
         # input, so it does not depend on the step) and the flat gradient buffer between graph 1 and graph 2.
-        self.nval = torch.zeros(1, dtype=torch.int32, device=self.static["targets"].device) if self.world > 1 else None
+        # B2C_FAKE_DP=1: exercise the multi-rank control flow (two graphs, overlapped exchanges) on ONE GPU with an identity in
+        # place of each collective -- used by the tests, which cannot run NCCL.
+        self._fake_dp = self.world == 1 and os.environ.get("B2C_FAKE_DP", "0") == "1"
+        self._multi = self.world > 1 or self._fake_dp
+        self.nval = torch.zeros(1, dtype=torch.int32, device=self.static["targets"].device) if self._multi else None
+        # Overlapped exchanges (graph mode, multi-rank): the collectives run on a communication stream, tied to the graph by
+        # EXTERNAL events -- the non-PAD count is all-reduced under the forward (graph 1 waits for it just before the loss) and
+        # the decoder's gradient segment (90 % of the bytes) is all-reduced under the refinement backward (graph 1 records an
+        # event right after b2c_decoder_backward).
+        self.overlap_comm = use_graph and self._multi and os.environ.get("B2C_OVERLAP_COMM", "1") != "0"
+        self._early = self._early_segment() if self.overlap_comm else None
+        if self.overlap_comm:
+            self._comm = torch.cuda.Stream()
+            self._ev_count = torch.cuda.Event(external=True)
+            self._ev_dec = torch.cuda.Event(external=True)
         if use_graph:
             self._capture(warmup_steps)
 
+    # ---- collectives (identity in the single-GPU fake mode)
+    def _all_reduce(self, t):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, group=self.loss_module.process_group)
+        else:
+            t.add_(0)
+
+    def _early_segment(self):
+        """[a, b) of the flat gradient buffer that holds exactly the decoder's parameters, or None if they are not contiguous."""
+        dec = {id(p) for p in self.model.decoder.parameters() if p.requires_grad}
+        spans = [(o, o + p.numel()) for p, o in zip(self.reducer.params, self.reducer.offsets) if id(p) in dec]
+        if not spans or len(spans) != len(dec):
+            return None
+        a, b = min(s[0] for s in spans), max(s[1] for s in spans)
+        inside = [p for p, o in zip(self.reducer.params, self.reducer.offsets) if a <= o < b and id(p) not in dec]
+        return None if inside else (a, b)
+
     # ---- the step body (eager or under capture)
     def _pre(self):
-        if self.world > 1:
+        if self._multi:
             _ops.count_valid(self.static["targets"], self.loss_module.vocab_size or 2 ** 31 - 1, out=self.nval)
-            torch.distributed.all_reduce(self.nval, group=self.loss_module.process_group)
+            self._all_reduce(self.nval)
             self.loss_module.n_valid_global = self.nval
 
     def _fwd_bwd(self):
@@ -89,6 +125,8 @@ class GraphedKDStep:
             with ctx:
                 outputs, enc, hids, _ = self.model(feats, inp["captions_input"])
                 tproj = self.projector(inp["teacher_features"])
+        if self._capturing and self.overlap_comm:
+            torch.cuda.current_stream().wait_event(self._ev_count)      # external event: the count all-reduce of THIS step
         loss, out5 = self.loss_module.forward_device(
             {"logits": outputs, "encoder_features": enc, "hidden_states": hids},
             {"logits": inp["teacher_logits"], "encoder_features": tproj, "hidden_states": inp.get("teacher_hiddens")},
@@ -97,7 +135,12 @@ class GraphedKDStep:
             self.reducer.detach_grads()          # backward kernels write every parameter gradient straight into the flat buffer
         else:
             self.reducer.zero_grad()
-        loss.backward()
+        if self._capturing and self.overlap_comm and self._early is not None:
+            _ops.after_decoder_backward = self._ev_dec.record            # event-record node right behind b2c_decoder_backward
+        try:
+            loss.backward()
+        finally:
+            _ops.after_decoder_backward = None
         if self.direct_grads:
             self.reducer.attach_views()          # the flat buffer is authoritative (the kernels wrote into it), whatever autograd kept
         return out5
@@ -111,10 +154,19 @@ class GraphedKDStep:
             self.reducer.flat.mul_(torch.clamp(self.max_grad_norm / (gn + 1e-6), max=1.0))
         self.optimizer.step()
 
+    def _exchange_grads(self):
+        if self.world > 1:
+            if self._fold_avg:
+                self._all_reduce(self.reducer.flat)
+            else:
+                self.reducer.allreduce()
+        elif self._fake_dp:
+            self._all_reduce(self.reducer.flat)
+
     def _body(self):
         self._pre()
         out5 = self._fwd_bwd()
-        self.reducer.allreduce()
+        self._exchange_grads()
         self._clip_and_update()
         return out5
 
@@ -128,24 +180,28 @@ class GraphedKDStep:
         torch.cuda.synchronize()
         self._pre()
         torch.cuda.synchronize()
+        if self.overlap_comm:
+            self._ev_count.record()                                      # the wait node needs a recorded event at capture time
         self.graph = torch.cuda.CUDAGraph()
         self._overlap = True
+        self._capturing = True
         # Captured on a HIGH-priority stream: kernel nodes keep the priority of the stream they were captured from, so the
         # latency-bound main chain (the recurrence) is scheduled ahead of the throughput work forked onto the default-priority
         # side streams (projector, weight gradients), which then only fills the SMs the chain leaves idle.
         cap = torch.cuda.Stream(priority=-1) if self.high_priority_chain else torch.cuda.Stream()
-        if self.world == 1:
+        if not self._multi:
             with torch.cuda.graph(self.graph, stream=cap):
                 self.out5 = self._fwd_bwd()
                 self._clip_and_update()
         else:
             with torch.cuda.graph(self.graph, stream=cap):
                 self.out5 = self._fwd_bwd()
-            self.reducer.allreduce()
+            self._exchange_grads()
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
                 self._clip_and_update()
         self._overlap = False
+        self._capturing = False
 
     def load(self, batch: Dict[str, torch.Tensor], non_blocking: bool = True) -> int:
         """Copy one step's inputs (host or device tensors) into the static buffers; returns the bytes copied."""
@@ -162,11 +218,34 @@ class GraphedKDStep:
         [total, ce, token_kd, feature_kd, hidden_kd] (no host sync)."""
         if self.graph is None:
             self.out5 = self._body()
-        elif self.world == 1:
+        elif not self._multi:
             self.graph.replay()
-        else:
+        elif not self.overlap_comm:
             self._pre()
             self.graph.replay()
-            self.reducer.allreduce()
+            self._exchange_grads()
+            self.graph_opt.replay()
+        else:
+            main, comm = torch.cuda.current_stream(), self._comm
+            comm.wait_stream(main)                   # the previous step has consumed nval and the gradient buffer
+            with torch.cuda.stream(comm):
+                self._pre()                          # count + all-reduce under the forward
+                self._ev_count.record()
+            self.graph.replay()                      # waits for _ev_count before the loss; records _ev_dec after the decoder backward
+            flat = self.reducer.flat
+            if self._early is not None:
+                a, b = self._early
+                with torch.cuda.stream(comm):
+                    comm.wait_event(self._ev_dec)
+                    self._all_reduce(flat[a:b])      # decoder gradients, under the refinement backward
+                if a > 0:
+                    self._all_reduce(flat[:a])
+                if b < flat.numel():
+                    self._all_reduce(flat[b:])
+                main.wait_stream(comm)
+            else:
+                self._all_reduce(flat)
+            if self.world > 1 and not self._fold_avg:
+                self.reducer.finish()
             self.graph_opt.replay()
         return self.out5

@@ -101,7 +101,9 @@ class FlatAdamW:
         self.exp_avg = torch.zeros_like(self.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
         self.reducer = FlatGradAllReducer(self.params, group=process_group, offsets=self.offsets, numel=off)
-        self.hyper = _ops.B2COptHyper(betas[0], betas[1], eps, float(max_grad_norm) if max_grad_norm else 0.0,
+        # grad_scale: the data-parallel average (1/world after the SUM all-reduce) is folded into the update kernel when the
+        # caller asks for it (GraphedKDStep does); FlatGradAllReducer.finish() then must not be called.
+        self.hyper = _ops.B2COptHyper(betas[0], betas[1], eps, float(max_grad_norm) if max_grad_norm else 0.0, 1.0,
                                       growth_factor, backoff_factor, growth_interval)
         self.lr = torch.zeros(len(lr_slots), dtype=torch.float32, device=dev)
         self._lr_host = torch.zeros(len(lr_slots), dtype=torch.float32).pin_memory()
@@ -125,6 +127,10 @@ class FlatAdamW:
 
     def get_lrs(self) -> List[float]:
         return self._lr_host.tolist()
+
+    def fold_average(self, world_size: int) -> None:
+        """Gradients arrive as a SUM over `world_size` ranks: apply the 1/world inside the update kernel (no separate pass)."""
+        self.hyper.grad_scale = 1.0 / float(world_size)
 
     # ---- the step
     def step(self) -> None:

@@ -203,12 +203,13 @@ typedef struct {
 typedef struct {
   double beta1, beta2, eps; /* torch.optim.AdamW defaults 0.9, 0.999, 1e-8 (doubles, as in torch: 1 - beta is formed in fp64) */
   float max_norm;          /* clip_grad_norm_ threshold per clip group; <= 0 disables clipping */
+  float grad_scale;        /* every gradient is multiplied by this first (1/world after a SUM all-reduce; 1 otherwise) */
   float growth_factor, backoff_factor;   /* torch.amp.GradScaler defaults 2.0, 0.5 */
   int32_t growth_interval;               /* default 2000; only read when loss_scale != NULL */
 } B2COptHyper;
 
 /* One optimizer step, two kernel launches, no host synchronisation:
- *   g' = grad / *loss_scale (unscale_);  if any g' is non-finite the parameters, the moments and *step are left untouched
+ *   g' = grad * grad_scale / *loss_scale (data-parallel average + unscale_);  if any g' is non-finite the parameters, the moments and *step are left untouched
  *   (scaler.step skips) and *loss_scale is multiplied by backoff_factor;  otherwise each clip group is scaled by
  *   min(1, max_norm / (||g'||_2 + 1e-6)) and AdamW is applied with bias correction for step *step + 1, *step is
  *   incremented, and *loss_scale grows by growth_factor after growth_interval consecutive clean steps (scaler.update).

@@ -121,6 +121,23 @@ def test_loss_scale_skip_backoff_growth_and_lr_schedule():
             assert torch.allclose(p.detach().cpu().double(), q, rtol=3e-6, atol=3e-7)
 
 
+def test_folded_data_parallel_average():
+    """fold_average(world): gradients that are SUMS over `world` ranks give the same update (and norms) as the averaged ones."""
+    vals = _groups(3)
+    lrs, clips = [1e-4, 1e-3, 1e-3, 1e-3], [0, 0, 0, 1]
+    params_a, opt_a = _build(vals, lrs, clips, max_grad_norm=1.0)
+    params_b, opt_b = _build(vals, lrs, clips, max_grad_norm=1.0)
+    opt_b.fold_average(4)
+    for it in range(3):
+        grads = _grads(vals, 80 + it, 1.5)
+        _set_grads(opt_a, params_a, grads)
+        _set_grads(opt_b, params_b, [[g * 4.0 for g in gg] for gg in grads])
+        opt_a.step(); opt_b.step()
+        na, nb = opt_a.grad_norms(), opt_b.grad_norms()
+        assert abs(na[0] - nb[0]) <= 1e-6 * na[0] and abs(na[1] - nb[1]) <= 1e-6 * na[1]
+    assert torch.allclose(opt_a.flat_param, opt_b.flat_param, rtol=1e-6, atol=1e-8)
+
+
 def test_optimizer_step_rejects_bad_segments():
     import ctypes
     from imagecaptioner_b200 import _ops
@@ -128,7 +145,7 @@ def test_optimizer_step_rejects_bad_segments():
     buf = torch.zeros(64, device=DEV)
     st = torch.zeros(_ops.B2C_OPT_NSTATS, device=DEV); scratch = torch.zeros(_ops.B2C_OPT_SCRATCH_BYTES, dtype=torch.uint8, device=DEV)
     step = torch.zeros(1, dtype=torch.int32, device=DEV); lr = torch.ones(1, device=DEV)
-    hp = _ops.B2COptHyper(0.9, 0.999, 1e-8, 1.0, 2.0, 0.5, 2000)
+    hp = _ops.B2COptHyper(0.9, 0.999, 1e-8, 1.0, 1.0, 2.0, 0.5, 2000)
     def call(seg):
         segs = (_ops.B2COptSegment * 1)(seg)
         return lib.b2c_optimizer_step(buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), segs, 1, ctypes.byref(hp), lr.data_ptr(), 1,

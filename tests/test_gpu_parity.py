@@ -194,8 +194,13 @@ def test_full_size_properties_config2():
     assert relerr(got_b["grads"]["decoder.lstm.weight_hh_l0"], got32["grads"]["decoder.lstm.weight_hh_l0"]) < 1e-5
 
 
-def test_graphed_step_equals_eager_step():
-    """GraphedKDStep (one CUDA graph per KD step) reproduces the eagerly issued step: same loss parts, same updated weights."""
+@pytest.mark.parametrize("fake_dp", [False, True])
+def test_graphed_step_equals_eager_step(fake_dp, monkeypatch):
+    """GraphedKDStep (one CUDA graph per KD step) reproduces the eagerly issued step: same loss parts, same updated weights.
+    fake_dp: the multi-rank control flow on one GPU (two graphs; the count exchange under the forward and the decoder-gradient
+    exchange under the refinement backward, tied to the graph by external events) with identities in place of the collectives."""
+    if fake_dp:
+        monkeypatch.setenv("B2C_FAKE_DP", "1")
     from imagecaptioner_b200.ddp import FlatGradAllReducer
     from imagecaptioner_b200.distillation_utils import DistillationLoss
     from imagecaptioner_b200.graph import GraphedKDStep
@@ -222,6 +227,8 @@ def test_graphed_step_equals_eager_step():
     (l0, w0), (l1, w1) = results
     assert relerr(l1[0], l0[0]) < 1e-5                       # first step: identical weights, identical loss parts
     assert float(l0[2, 0]) < float(l0[0, 0])                 # and the loss goes down over the three steps
+    if fake_dp:
+        assert kd.overlap_comm and kd._early is not None     # the overlapped path really ran, on the decoder's gradient segment
 
 
 @pytest.mark.parametrize("B", [128, 256])
