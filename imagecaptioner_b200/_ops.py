@@ -100,6 +100,8 @@ SYMBOLS = {
     "b2c_projector_backward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CProjParams), _vp, ctypes.POINTER(B2CProjGrads), _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_count_valid": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "b2c_kd_token_loss": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _f, _f, _f, _f, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
+    "b2c_kd_token_eval": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _f, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
+    "b2c_bleu1": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "b2c_aux_loss": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _f, _f, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
     "b2c_loss_finalize": (ctypes.c_int, [_vp, _vp, _i64, _vp, _f, _vp, _i32, _i32, _vp, _i32, _i32, _f, _f, _f, _f, _f, _vp, _vp]),
     "b2c_scale_inplace": (ctypes.c_int, [_vp, _i64, ctypes.c_int, _vp, _vp]),
@@ -461,6 +463,62 @@ class KDLossFunction(torch.autograd.Function):
             return None if t is None else (t if t.dtype == dt else t.to(dt))
 
         return cast(sv["dlogits"], dt_l), None, None, cast(sv["dfs"], dt_fs), cast(sv["dft"], dt_ft), cast(sv["dhs"], dt_hs), None, None
+
+
+@torch.no_grad()
+def kd_eval(logits, teacher_logits, targets, feats_s, feats_t, hid_s, hid_t, alpha, beta, gamma, temperature, w_ce, nval_global=None,
+            ce_mult=1.0):
+    """DistillationLoss without gradients (validate_student_model): -> (out5 device tensor [total, ce, token_kd, feature_kd,
+    hidden_kd], predicted tokens (T,B) int32 = logits.argmax(-1), taken in the same pass over the logits)."""
+    lib = load_library()
+    _require_cuda(logits, "student logits")
+    T, B, V = logits.shape
+    N, dev = T * B, logits.device
+    cdt = logits.dtype if logits.dtype in (torch.float32, torch.bfloat16) else torch.float32
+    code = dtype_code(cdt)
+    y = logits.detach().to(cdt).contiguous()
+    z = teacher_logits.detach().to(device=dev, dtype=torch.float32).contiguous()
+    tg = targets.detach().to(device=dev, dtype=torch.int64).contiguous()
+    st = _stream()
+    nval = nval_global if nval_global is not None else count_valid(tg, V)
+    rows = torch.empty(2, N, dtype=torch.float32, device=dev)
+    pred = torch.empty(T, B, dtype=torch.int32, device=dev)
+    _check(lib.b2c_kd_token_eval(y.data_ptr(), z.data_ptr(), tg.data_ptr(), N, V, float(temperature), nval.data_ptr(), rows[0].data_ptr(),
+                                 rows[1].data_ptr(), pred.data_ptr(), code, st), "b2c_kd_token_eval")
+    fs = ft = hs = ht = feat_part = hid_part = None
+    Ss = St = E = H = Th = 0
+    if feats_s is not None and feats_t is not None:
+        fs = feats_s.detach().to(cdt).contiguous()
+        ft = feats_t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        _, Ss, E = fs.shape
+        St = ft.shape[1]
+        feat_part = torch.empty(B, 2, dtype=torch.float32, device=dev)
+    if hid_s is not None and hid_t is not None:
+        hs = hid_s.detach().to(cdt).contiguous()
+        ht = hid_t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        Th, H = ht.shape[0], ht.shape[2]
+        hid_part = torch.empty(Th * B, 2, dtype=torch.float32, device=dev)
+    if fs is not None or hs is not None:
+        _check(lib.b2c_aux_loss(_ptr(fs), _ptr(ft), B, Ss, St, E, _ptr(hs), _ptr(ht), hs.shape[0] if hs is not None else 0, Th, H,
+                                float(beta), float(gamma), None, None, None, _ptr(feat_part), _ptr(hid_part), code, st), "b2c_aux_loss")
+    out5 = torch.empty(5, dtype=torch.float32, device=dev)
+    _check(lib.b2c_loss_finalize(rows[0].data_ptr(), rows[1].data_ptr(), N, nval.data_ptr(), float(ce_mult), _ptr(feat_part), B, E,
+                                 _ptr(hid_part), Th, H, float(temperature), float(alpha), float(beta), float(gamma), float(w_ce),
+                                 out5.data_ptr(), st), "b2c_loss_finalize")
+    return out5, pred
+
+
+@torch.no_grad()
+def bleu1(predicted: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    """compute_bleu_score for every sample: predicted (T,B) int32/int64, targets (T,B) -> (B) fp32 on the device."""
+    lib = load_library()
+    _require_cuda(predicted, "predicted tokens")
+    T, B = predicted.shape
+    p = predicted.detach().to(torch.int32).contiguous()
+    t = targets.detach().to(device=p.device, dtype=torch.int64).contiguous()
+    out = torch.empty(B, dtype=torch.float32, device=p.device)
+    _check(lib.b2c_bleu1(p.data_ptr(), t.data_ptr(), T, B, out.data_ptr(), _stream()), "b2c_bleu1")
+    return out
 
 
 REFINE_PARAM_ORDER = ["attention.in_proj_weight", "attention.in_proj_bias", "attention.out_proj.weight", "attention.out_proj.bias",

@@ -793,13 +793,14 @@ int projector_backward_impl(const B2CShape& s, const B2CProjParams& p, const flo
 
 template <typename TS>
 int kd_token_loss_impl(const TS* y, const float* z, const int64_t* tgt, long N, int V, float temperature, float alpha,
-                       float w_ce_eff, const int* n_valid, TS* dy, float* row_kl, float* row_ce, cudaStream_t st) {
+                       float w_ce_eff, const int* n_valid, TS* dy, float* row_kl, float* row_ce, cudaStream_t st, int* argmax_out = nullptr) {
+  const bool eval = (dy == nullptr) || (argmax_out != nullptr);      // losses only (+ predictions): the row-in-smem kernel
   const bool vec = (V % 8 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)z % 16 == 0) && ((uintptr_t)dy % 16 == 0);
   const bool t4 = (temperature == 4.0f);
   const size_t smem = align_up((size_t)V * 4, 16) + align_up((size_t)V * sizeof(TS), 16);
   const float inv_temp = 1.0f / temperature, kd_coef = alpha * temperature / (float)N;
   // default: persistent CTAs, TMA double-buffered row prefetch, register-resident math (V % 8 == 0, V <= 16384)
-  if (vec && V <= 8 * KDR_THREADS * 8) {
+  if (vec && V <= 8 * KDR_THREADS * 8 && !eval) {
     const int need = cdiv(V / 8, KDR_THREADS);
     const size_t psmem = 2 * ((size_t)V * 4 + (size_t)V * sizeof(TS));
     int per_sm = (int)((200 * 1024) / (psmem + 1024)); if (per_sm < 1) per_sm = 1;
@@ -824,7 +825,7 @@ int kd_token_loss_impl(const TS* y, const float* z, const int64_t* tgt, long N, 
 #define B2C_KD_LAUNCH(G, T4)                                                                                             \
   do {                                                                                                                   \
     B2C_TRY(set_smem(kd_token_loss_kernel<TS, G, T4>, smem));                                                            \
-    kd_token_loss_kernel<TS, G, T4><<<(unsigned)N, KD_THREADS, smem, st>>>(y, z, tgt, V, inv_temp, kd_coef, w_ce_eff, n_valid, dy, row_kl, row_ce); \
+    kd_token_loss_kernel<TS, G, T4><<<(unsigned)N, KD_THREADS, smem, st>>>(y, z, tgt, V, inv_temp, kd_coef, w_ce_eff, n_valid, dy, row_kl, row_ce, argmax_out); \
   } while (0)
   if (vec && t4) B2C_KD_LAUNCH(8, true);
   else if (vec) B2C_KD_LAUNCH(8, false);
@@ -1012,6 +1013,25 @@ int b2c_kd_token_loss(const void* student_logits, const float* teacher_logits, c
   if (dtype == B2C_F32) return kd_token_loss_impl<float>((const float*)student_logits, teacher_logits, targets, (long)N, V, temperature, alpha, w_ce * ce_mult, n_valid, (float*)dlogits, row_kl, row_ce, st);
   if (dtype == B2C_BF16) return kd_token_loss_impl<bf16>((const bf16*)student_logits, teacher_logits, targets, (long)N, V, temperature, alpha, w_ce * ce_mult, n_valid, (bf16*)dlogits, row_kl, row_ce, st);
   return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_kd_token_eval(const void* student_logits, const float* teacher_logits, const int64_t* targets, int64_t N, int32_t V,
+                      float temperature, const int32_t* n_valid, float* row_kl, float* row_ce, int32_t* argmax_out, int dtype, void* stream) {
+  B2C_TRY(check_device());
+  B2C_CHECK_ARG(student_logits && teacher_logits && targets && n_valid && row_kl && row_ce, "NULL argument");
+  B2C_CHECK_ARG(N > 0 && N < 2147483647L && V > 1 && temperature > 0.f, "bad N=%ld V=%d temperature=%f", (long)N, V, temperature);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) return kd_token_loss_impl<float>((const float*)student_logits, teacher_logits, targets, (long)N, V, temperature, 0.f, 0.f, n_valid, (float*)nullptr, row_kl, row_ce, st, argmax_out);
+  if (dtype == B2C_BF16) return kd_token_loss_impl<bf16>((const bf16*)student_logits, teacher_logits, targets, (long)N, V, temperature, 0.f, 0.f, n_valid, (bf16*)nullptr, row_kl, row_ce, st, argmax_out);
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_bleu1(const int32_t* predicted, const int64_t* targets, int32_t T, int32_t B, float* bleu_out, void* stream) {
+  B2C_TRY(check_device());
+  B2C_CHECK_ARG(predicted && targets && bleu_out && T > 0 && B > 0, "bad argument");
+  bleu1_kernel<<<cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(predicted, targets, T, B, bleu_out);
+  B2C_LAUNCH_CHECK("bleu1_kernel");
+  return 0;
 }
 
 int b2c_aux_loss(const void* feats_s, const float* feats_t, int32_t B, int32_t Ss, int32_t St, int32_t E,

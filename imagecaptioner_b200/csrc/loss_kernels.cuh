@@ -67,7 +67,8 @@ template <typename TS, int G, bool TEMP4>
 __global__ void __launch_bounds__(KD_THREADS)
 kd_token_loss_kernel(const TS* __restrict__ y, const float* __restrict__ z, const int64_t* __restrict__ tgt,
                      int V, float inv_temp, float kd_coef, float w_ce, const int* __restrict__ n_valid_ptr,
-                     TS* __restrict__ dy, float* __restrict__ row_kl, float* __restrict__ row_ce) {
+                     TS* __restrict__ dy /* NULL: losses only (evaluation) */, float* __restrict__ row_kl, float* __restrict__ row_ce,
+                     int* __restrict__ argmax_out /* NULL, or (N): argmax_v y[r, v], lowest index on ties like torch.argmax */) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* zs = reinterpret_cast<float*>(smem_raw);                             // V floats
   TS* ys = reinterpret_cast<TS*>(smem_raw + align_up((size_t)V * 4, 16)); // V TS
@@ -118,6 +119,16 @@ kd_token_loss_kernel(const TS* __restrict__ y, const float* __restrict__ z, cons
     for (int i = 1; i < KD_THREADS / 32; ++i) { my = fmaxf(my, scratch[i * 2]); mz = fmaxf(mz, scratch[i * 2 + 1]); }
   }
 
+  if (argmax_out != nullptr) {                 // teacher-forced prediction of this row (validate_student_model's logits.argmax(-1))
+    int best = V;
+    for (int v = tid; v < V; v += KD_THREADS) if (to_f<TS>(ys[v]) == my) best = min(best, v);
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    __shared__ int best_s[KD_THREADS / 32];
+    if ((tid & 31) == 0) best_s[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) { int bb = best_s[0]; for (int i = 1; i < KD_THREADS / 32; ++i) bb = min(bb, best_s[i]); argmax_out[r] = bb; }
+  }
+
   // pass 2: partition sums; e^{z'} is written back over z (and e^{y'} over y when y is fp32)
   float sT = 0.f, sZ = 0.f, sA = 0.f, s1 = 0.f;
   for (int g = tid; g < groups; g += KD_THREADS) {
@@ -147,6 +158,7 @@ kd_token_loss_kernel(const TS* __restrict__ y, const float* __restrict__ z, cons
   }
 
   // pass 3: gradient
+  if (dy == nullptr) return;
   TS* dyg = dy + r * (long)V;
   const float a_s = kd_coef * inv_sT, a_t = kd_coef * inv_sZ, a_c = ce_coef * inv_s1;
   for (int g = tid; g < groups; g += KD_THREADS) {
@@ -322,6 +334,27 @@ kd_token_loss_pipe_kernel(const TS* __restrict__ y, const float* __restrict__ z,
       }
     }
   }
+}
+
+// validate_student_model's monitoring metric (reference src/distillation_utils.py:398-409, compute_bleu_score): per sample,
+//   |set(pred \ {PAD,START,END}) ∩ set(target \ {PAD,START,END})| / |set(target \ {PAD,START,END})|   (0 if the target set is empty).
+// Token ids stand for words (vocab.itos is injective).  One warp per sample, O(T^2) comparisons (T = caption length).
+__global__ void __launch_bounds__(128)
+bleu1_kernel(const int* __restrict__ pred /*(T,B)*/, const int64_t* __restrict__ tgt /*(T,B)*/, int T, int B, float* __restrict__ out /*(B)*/) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  int n_set = 0, n_hit = 0;
+  for (int i = lane; i < T; i += 32) {
+    const long tok = tgt[(long)i * B + b];
+    if (tok == 0 || tok == 1 || tok == 2) continue;
+    bool first = true;
+    for (int j = 0; j < i; ++j) if (tgt[(long)j * B + b] == tok) { first = false; break; }
+    if (!first) continue;
+    ++n_set;
+    for (int j = 0; j < T; ++j) if ((long)pred[(long)j * B + b] == tok) { ++n_hit; break; }
+  }
+  for (int o = 16; o > 0; o >>= 1) { n_set += __shfl_xor_sync(0xffffffffu, n_set, o); n_hit += __shfl_xor_sync(0xffffffffu, n_hit, o); }
+  if (lane == 0) out[b] = n_set > 0 ? (float)n_hit / (float)n_set : 0.f;
 }
 
 __global__ void count_valid_kernel(const int64_t* __restrict__ tgt, long n, int V, int* __restrict__ out) {

@@ -87,6 +87,32 @@ class DistillationLoss(nn.Module):
                      "feature_kd_loss": vals[3], "hidden_kd_loss": vals[4]}
         return loss, loss_dict
 
+    @torch.no_grad()
+    def evaluate(self, student_outputs, teacher_outputs, targets):
+        """Validation form (reference src/train_student_kd.py:56-75): the same loss WITHOUT gradients, and the teacher-forced
+        predictions ``student_logits.argmax(dim=-1)`` from the same pass over the logits.
+        -> (total_loss 0-dim tensor, loss_dict of 5 floats, predicted_tokens (T,B) int32 on the device)."""
+        feats_s = feats_t = hid_s = hid_t = None
+        if "encoder_features" in student_outputs and "encoder_features" in teacher_outputs:
+            feats_s, feats_t = student_outputs["encoder_features"], teacher_outputs["encoder_features"]
+            if feats_s is not None and feats_t is not None and feats_s.shape[-1] != feats_t.shape[-1]:
+                raise ValueError(f"Feature dimensions don't match: student {feats_s.shape[-1]}, teacher {feats_t.shape[-1]}")
+        if "hidden_states" in student_outputs and "hidden_states" in teacher_outputs:
+            hid_s, hid_t = _stack_hidden(student_outputs["hidden_states"]), _stack_hidden(teacher_outputs["hidden_states"])
+            if hid_s is not None and hid_t is not None:
+                if hid_s.shape[-1] != hid_t.shape[-1]:
+                    raise ValueError(f"Hidden dimensions don't match: student {hid_s.shape[-1]}, teacher {hid_t.shape[-1]}")
+                hid_t = hid_t[:min(hid_s.shape[0], hid_t.shape[0])]
+            else:
+                hid_s = hid_t = None
+        w_ce = 1 - self.alpha - self.beta - self.gamma
+        out5, pred = _ops.kd_eval(student_outputs["logits"], teacher_outputs["logits"], targets, feats_s, feats_t, hid_s, hid_t,
+                                  self.alpha, self.beta, self.gamma, self.temperature, w_ce, self.n_valid_global, float(self.world_size))
+        vals = out5.tolist()
+        loss_dict = {"total_loss": vals[0], "ce_loss": vals[1], "token_kd_loss": vals[2],
+                     "feature_kd_loss": vals[3], "hidden_kd_loss": vals[4]}
+        return out5[0], loss_dict, pred
+
     # ---- the reference's individual terms, each through the same kernels --------------------------
     def _dummy_targets(self, logits):
         # any non-PAD id: the CE term is weighted by exactly 0 in the single-term entry points below

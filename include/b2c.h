@@ -13,6 +13,8 @@
  *   b2c_projector_forward/backward  <- FeatureProjector.forward (+ autograd)      src/distillation_utils.py:203-252
  *   b2c_count_valid       <- CrossEntropyLoss(ignore_index=0) normaliser  src/distillation_utils.py:22
  *   b2c_kd_token_loss     <- token_level_distillation :30-54 + CE term :154 (+ their gradient)
+ *   b2c_kd_token_eval     <- validate_student_model: loss without gradients + logits.argmax(-1)   src/train_student_kd.py:29-86
+ *   b2c_bleu1             <- compute_bleu_score (per sample, on the device)                       src/distillation_utils.py:398-409
  *   b2c_aux_loss          <- encoder_feature_distillation :56-94 + decoder_hidden_state_distillation :96-136
  *   b2c_loss_finalize     <- the alpha/beta/gamma weighting and loss_dict  :184-198
  *   b2c_scale_inplace     <- the scalar grad_output of loss.backward() (GradScaler / accumulation, train_student_kd.py:285-288)
@@ -165,6 +167,17 @@ int b2c_count_valid(const int64_t* targets, int64_t n, int32_t V, int32_t* n_val
 int b2c_kd_token_loss(const void* student_logits, const float* teacher_logits, const int64_t* targets,
                       int64_t N, int32_t V, float temperature, float alpha, float w_ce, float ce_mult,
                       const int32_t* n_valid, void* dlogits, float* row_kl, float* row_ce, int dtype, void* stream);
+
+/* Evaluation form of the token pass (validate_student_model, src/train_student_kd.py:29-86): the same per-row KL and CE partials,
+ * NO gradient, plus (argmax_out != NULL) the teacher-forced prediction argmax_v student_logits[r, v] of every row (lowest index on
+ * ties, like torch.argmax) from the same read of the logits -- `student_logits.argmax(dim=-1)` (:74) without a second pass. */
+int b2c_kd_token_eval(const void* student_logits, const float* teacher_logits, const int64_t* targets, int64_t N, int32_t V,
+                      float temperature, const int32_t* n_valid, float* row_kl, float* row_ce, int32_t* argmax_out, int dtype, void* stream);
+
+/* compute_bleu_score (src/distillation_utils.py:398-409) for every sample of a batch on the device: predicted (T,B) int32,
+ * targets (T,B) int64 -> bleu_out (B) = |set(pred) & set(target)| / |set(target)| over token ids outside {PAD=0, START=1, END=2}
+ * (0 when the target set is empty).  Token ids stand for the words (vocab.itos is one-to-one). */
+int b2c_bleu1(const int32_t* predicted, const int64_t* targets, int32_t T, int32_t B, float* bleu_out, void* stream);
 
 /* Fused feature-KD + hidden-KD reduction and gradients.
  *   feats_s (B,Ss,E) [dtype] or NULL, feats_t (B,St,E) fp32 (the projected teacher features);

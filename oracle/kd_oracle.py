@@ -411,6 +411,25 @@ def init_projector_params(Et: int, Es: int, seed: int = 1) -> Dict[str, Tensor]:
     }
 
 
+def bleu1(predicted: Tensor, targets: Tensor) -> Tensor:
+    """compute_bleu_score (src/distillation_utils.py:398-409) for every column of (T,B) token matrices, on token ids:
+    |set(pred) & set(target)| / |set(target)| with PAD / START / END (0, 1, 2) removed; 0 when the target set is empty."""
+    out = []
+    for b in range(predicted.shape[1]):
+        ps = {int(t) for t in predicted[:, b].tolist() if int(t) not in (PAD, START, END)}
+        ts = {int(t) for t in targets[:, b].tolist() if int(t) not in (PAD, START, END)}
+        out.append(len(ps & ts) / len(ts) if ts else 0.0)
+    return torch.tensor(out, dtype=torch.float32)
+
+
+def eval_step(params: Dict[str, Tensor], proj_params: Dict[str, Tensor], batch: dict, alpha=0.7, beta=0.2, gamma=0.1, temperature=4.0) -> dict:
+    """One batch of validate_student_model (src/train_student_kd.py:43-80): forward, the distillation loss without gradients,
+    teacher-forced predictions logits.argmax(-1) (:74) and the BLEU-1 of EVERY sample (the reference scores the first two)."""
+    got = kd_step(params, proj_params, batch, alpha, beta, gamma, temperature)      # the gradients it also returns are ignored here
+    pred = got["logits"].argmax(dim=-1)
+    return {"loss": got["loss"], "predicted_tokens": pred, "bleu": bleu1(pred, batch["targets"])}
+
+
 def synthetic_batch(B: int, T: int, V: int, E: int = 256, H: int = 512, S: int = 49,
                     St: int = 197, Et: int = 384, seed: int = 1234, teacher_hiddens: bool = True) -> dict:
     """Synthetic KD batch of SURVEY.md §8d: N(0,1) encoder features, START-first captions,

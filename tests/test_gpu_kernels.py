@@ -302,3 +302,35 @@ def test_decoder_prepare_split_is_bit_identical(dtype):
             assert relerr(a, b) < 1e-6                     # backward: split-K reductions may add in a different order
     with pytest.raises(ValueError, match="prepared for"):
         _ops.DecoderFunction.apply(feats[:4], cap[:, :4], dtype, 0.0, 0, L, _ops.decoder_prepare(cap, S, dtype, L, plist), *plist)
+
+
+def test_bleu1_kernel_matches_reference_fixture():
+    import os
+    from imagecaptioner_b200 import _ops
+    from tests.harness import GOLDEN
+    fx = torch.load(os.path.join(GOLDEN, "validation_case.pt"), weights_only=False)["bleu"]
+    got = _ops.bleu1(fx["pred"].to(DEV), fx["targets"].to(DEV)).cpu()
+    assert torch.allclose(got, fx["reference"], atol=1e-6)
+    g = torch.Generator().manual_seed(2)                       # longer captions than a warp, many samples
+    pred = torch.randint(0, 30, (70, 37), generator=g); tgt = torch.randint(0, 30, (70, 37), generator=g)
+    assert torch.allclose(_ops.bleu1(pred.to(DEV), tgt.to(DEV)).cpu(), O.bleu1(pred, tgt), atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("V", [5000, 203])
+def test_kd_token_eval_matches_training_kernel_and_argmax(V, dtype):
+    """b2c_kd_token_eval: the same loss parts as the training pass (no gradient written) and logits.argmax(-1), lowest index on ties."""
+    from imagecaptioner_b200 import _ops
+    T, B = 3, 7
+    g = torch.Generator().manual_seed(V)
+    y = (torch.randn(T, B, V, generator=g) * 2).to(dtype)
+    y[0, 0, 17] = y[0, 0].max() + 1; y[0, 0, 5] = y[0, 0, 17]            # a tie: the lower index wins
+    z = torch.randn(T, B, V, generator=g) * 2
+    tgt = torch.randint(0, V, (T, B), generator=g); tgt[1, :3] = 0
+    yd, zd, td = y.to(DEV), z.to(DEV), tgt.to(DEV)
+    out5, pred = _ops.kd_eval(yd, zd, td, None, None, None, None, 0.7, 0.0, 0.0, 4.0, 0.3)
+    cfg = (0.7, 0.0, 0.0, 4.0, 0.3, 1.0, None, None, False)
+    loss, ref5 = _ops.KDLossFunction.apply(yd.clone().requires_grad_(True), zd, td, None, None, None, None, cfg)
+    assert torch.allclose(out5.cpu(), ref5.cpu(), rtol=2e-5, atol=1e-6)
+    assert torch.equal(pred.cpu().long(), y.float().argmax(dim=-1))
+    assert int(pred[0, 0]) == 5

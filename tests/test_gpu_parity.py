@@ -261,3 +261,46 @@ def test_large_variant_real_dims_fp32_and_bf16():
     compare_step(got16, ref, 3 * BF16_TOL, verbose=False, loosen={k: 4.0 for k in GATED})   # 196 rows: one flipped ReLU is ~1/14 of a column
     toks, lens = model.decoder.greedy(model.attention_refinement(batch["encoder_features"].to(DEV)).float(), 6)
     assert tuple(toks.shape) == (6, B) and int(lens.max()) <= 6
+
+
+def test_validation_path_matches_reference_fixture():
+    """validate_student_model on the native path (eval loss without gradients, argmax in the loss pass, device BLEU-1) against the
+    reference's loss, `logits.argmax(-1)` and compute_bleu_score on the golden KD case (tests/golden/validation_case.pt)."""
+    from imagecaptioner_b200.distillation_utils import DistillationLoss, TeacherWrapper
+    from imagecaptioner_b200.validation import validate_student_model
+    g = torch.load(os.path.join(GOLDEN, "kd_small_default.pt"), weights_only=False)
+    fx = torch.load(os.path.join(GOLDEN, "validation_case.pt"), weights_only=False)["kd_small_default"]
+    m, batch = g["meta"], g["batch"]
+    Et = batch["teacher_features"].shape[-1]
+    model, projector = build_student(g["params"], g["proj_params"], m["V"], m["E"], m["H"], m["L"], m["refinement"], Et, DEV)
+    model.decoder.compute_dtype = torch.float32
+    model.attention_refinement.compute_dtype = torch.float32
+    projector.compute_dtype = torch.float32
+    loss_mod = DistillationLoss(m["alpha"], m["beta"], m["gamma"], m["temperature"], vocab_size=m["V"])
+    with torch.no_grad():
+        logits, enc, hids, _ = model(batch["encoder_features"].to(DEV), batch["captions_input"].to(DEV))
+        th = batch["teacher_hiddens"]
+        t_out = {"logits": batch["teacher_logits"].to(DEV), "encoder_features": projector(batch["teacher_features"].to(DEV)),
+                 "hidden_states": [th[t].to(DEV) for t in range(th.shape[0])]}
+        loss, loss_dict, pred = loss_mod.evaluate({"logits": logits, "encoder_features": enc, "hidden_states": hids}, t_out,
+                                                  batch["targets"].to(DEV))
+    for k, v in g["reference"]["loss"].items():
+        assert abs(loss_dict[k] - v) <= 1e-4 * max(1.0, abs(v)), k
+    assert torch.equal(pred.cpu().long(), fx["predicted_tokens"])
+    from imagecaptioner_b200 import _ops
+    assert torch.allclose(_ops.bleu1(pred, batch["targets"].to(DEV)).cpu(), fx["bleu"], atol=1e-6)
+
+    # the whole function, with a stub teacher that replays the fixture's teacher outputs (hidden_states None like TeacherWrapper)
+    class StubTeacher(TeacherWrapper):
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+        def forward(self, images, captions):
+            return {"logits": batch["teacher_logits"].to(DEV), "encoder_features": batch["teacher_features"].to(DEV), "hidden_states": None}
+    captions = torch.cat([batch["captions_input"][:1], batch["targets"]], dim=0)          # (T+1, B): input = [:-1], target = [1:]
+    captions[:-1] = batch["captions_input"]
+    loader = [(batch["encoder_features"], captions)] * 3
+    avg_loss, avg_bleu = validate_student_model(model, StubTeacher(), loader, loss_mod, {"encoder": projector}, DEV, vocab=None, max_batches=2)
+    ref = O.kd_step(g["params"], g["proj_params"], dict(batch, teacher_hiddens=None), m["alpha"], m["beta"], m["gamma"], m["temperature"])
+    assert abs(avg_loss - ref["loss"]["total_loss"]) <= 1e-4 * max(1.0, abs(ref["loss"]["total_loss"]))
+    assert abs(avg_bleu - float(fx["bleu"][:2].mean())) < 1e-6
+    assert not model.training

@@ -134,3 +134,18 @@ def test_loss_edge_cases():
     # list truncation to the shorter side
     s = [torch.randn(2, 8) for _ in range(5)]
     assert abs(float(O.hidden_kd(s, s[:3])) - float(O.hidden_kd(s[:3], s[:3]))) < 1e-7
+
+
+def test_validation_oracle_matches_reference_fixture():
+    """oracle bleu1 / eval_step vs tests/golden/validation_case.pt (written by oracle/pin_validation.py from the reference's
+    compute_bleu_score and logits.argmax)."""
+    import os
+    from tests.harness import GOLDEN
+    fx = torch.load(os.path.join(GOLDEN, "validation_case.pt"), weights_only=False)
+    got = O.bleu1(fx["bleu"]["pred"], fx["bleu"]["targets"])
+    assert torch.allclose(got, fx["bleu"]["reference"], atol=1e-6)
+    assert float(got[0]) == 0.0 and abs(float(got[1]) - 1.0) < 1e-6        # empty target set; {5} vs {5, 9}
+    case = torch.load(os.path.join(GOLDEN, "kd_small_default.pt"), weights_only=False)
+    ev = O.eval_step(case["params"], case["proj_params"], case["batch"])
+    assert torch.equal(ev["predicted_tokens"], fx["kd_small_default"]["predicted_tokens"])
+    assert torch.allclose(ev["bleu"], fx["kd_small_default"]["bleu"], atol=1e-6)
