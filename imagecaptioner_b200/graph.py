@@ -60,8 +60,8 @@ class GraphedKDStep:
         loss_module.assume_unit_grad = True      # _fwd_bwd calls loss.backward() with the implicit grad_output of exactly 1
         if direct_grads:
             _ops.set_grad_destinations(reducer.grad_views())
-        # Data parallel: NCCL stays OUTSIDE the graphs.  The non-PAD count is all-reduced before graph 1 (targets are an
-        # input, so it does not depend on the step) and the flat gradient buffer between graph 1 and graph 2.
+        # Data parallel: NCCL stays OUTSIDE the graphs (graph 1 = forward + loss + backward, graph 2 = clip + AdamW); the two
+        # exchanges (non-PAD count, flat gradient buffer) are issued eagerly around / alongside graph 1, see overlap_comm below.
         # B2C_FAKE_DP=1: exercise the multi-rank control flow (two graphs, overlapped exchanges) on ONE GPU with an identity in
         # place of each collective -- used by the tests, which cannot run NCCL.
         self._fake_dp = self.world == 1 and os.environ.get("B2C_FAKE_DP", "0") == "1"
