@@ -358,6 +358,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int m0 = (rem / tiles_n) * TC_BM, n0 = (rem % tiles_n) * BN;
     const int as = t & 1; const uint32_t aph = (t >> 1) & 1;
     const bool add_bias = (bias != nullptr) && (sp == 0);
+    // LSTM epilogue: the operands that do not come from the MMA (bias, the time-batched addend, c_{t-1}) of this warp's first 32
+    // columns are fetched BEFORE waiting for the accumulator, so their L2 latency runs under the main loop.
+    [[maybe_unused]] float4 pre_b[8]; [[maybe_unused]] uint4 pre_a[4]; [[maybe_unused]] float4 pre_c0, pre_c1;
+    [[maybe_unused]] int pre_ci = -1;
+    if constexpr (LSTM) {
+      constexpr int NC32 = BN / 32, C32_PER = (NC32 + 1) / 2;
+      const int ci = half * C32_PER, col0 = n0 + ci * 32, grow = m0 + q * 32 + lane;
+      if (ci < NC32 && col0 < N && grow < M) {
+        pre_ci = ci;
+        if (le.bias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pre_b[j] = *reinterpret_cast<const float4*>(le.bias + col0 + 4 * j);
+        }
+        if (le.addend) {
+          const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(le.addend) + (long)grow * N + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pre_a[j] = ap[j];
+        }
+        pre_c0 = *reinterpret_cast<const float4*>(le.c_prev + (long)grow * le.H + (col0 >> 2));
+        pre_c1 = *reinterpret_cast<const float4*>(le.c_prev + (long)grow * le.H + (col0 >> 2) + 4);
+      }
+    }
     mbar_wait(&tfull_bar[as], aph);
     tc_fence_after();
     const uint32_t tacc = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(q * 32) << 16);
@@ -374,22 +396,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float v[32];
         tmem_ld32(tacc + (uint32_t)(ci * 32), v);
         if (grow < M) {
+          const bool pre = (ci == pre_ci);
           if (le.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) { const float4 b4 = *reinterpret_cast<const float4*>(le.bias + col0 + j); v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w; }
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = pre ? pre_b[j >> 2] : *reinterpret_cast<const float4*>(le.bias + col0 + j);
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
           }
           if (le.addend) {
             const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(le.addend) + (long)grow * N4 + col0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 a = ap[j];
+              const uint4 a = pre ? pre_a[j] : ap[j];
               v[j * 8 + 0] += bf16_lo(a.x); v[j * 8 + 1] += bf16_hi(a.x); v[j * 8 + 2] += bf16_lo(a.y); v[j * 8 + 3] += bf16_hi(a.y);
               v[j * 8 + 4] += bf16_lo(a.z); v[j * 8 + 5] += bf16_hi(a.z); v[j * 8 + 6] += bf16_lo(a.w); v[j * 8 + 7] += bf16_hi(a.w);
             }
           }
           const int u0 = col0 >> 2;
-          const float4 cp0 = *reinterpret_cast<const float4*>(le.c_prev + (long)grow * H + u0);
-          const float4 cp1 = *reinterpret_cast<const float4*>(le.c_prev + (long)grow * H + u0 + 4);
+          const float4 cp0 = pre ? pre_c0 : *reinterpret_cast<const float4*>(le.c_prev + (long)grow * H + u0);
+          const float4 cp1 = pre ? pre_c1 : *reinterpret_cast<const float4*>(le.c_prev + (long)grow * H + u0 + 4);
           const float cp[8] = {cp0.x, cp0.y, cp0.z, cp0.w, cp1.x, cp1.y, cp1.z, cp1.w};
           float cn[8], hn[8];
 #pragma unroll
