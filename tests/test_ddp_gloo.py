@@ -94,3 +94,41 @@ def test_flat_buffer_and_sharding_single_process():
     assert shard_batch(4096, 3, 8) == slice(1536, 2048)
     with pytest.raises(ValueError):
         shard_batch(10, 0, 4)
+
+
+def test_early_allreduce_segment_and_reference_param_groups():
+    """Host logic of the overlapped gradient exchange: the decoder's parameters must form ONE contiguous range of the flat buffer
+    (that range is all-reduced under the refinement backward); and the reference's LR / clip grouping."""
+    import torch.nn as nn
+    from imagecaptioner_b200.ddp import FlatGradAllReducer
+    from imagecaptioner_b200.graph import GraphedKDStep
+    from imagecaptioner_b200.optim import reference_param_groups
+
+    class Tiny(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encoder = nn.Linear(3, 3)
+            self.attention_refinement = nn.Linear(4, 4)
+            self.decoder = nn.Sequential(nn.Linear(5, 5), nn.Linear(5, 2))
+            self.use_attention_refinement = True
+
+    model, projector = Tiny(), nn.Linear(6, 6)
+    for p in model.encoder.parameters():
+        p.requires_grad = False                                   # frozen encoder, as in the bench (features are fed directly)
+    groups = reference_param_groups(model, {"encoder": projector}, 1e-3)
+    assert [len(g["params"]) for g in groups] == [2, 4, 2, 2]
+    assert [g["lr"] for g in groups] == [1e-4, 1e-3, 1e-3, 1e-3] and [g["clip_group"] for g in groups] == [0, 0, 0, 1]
+    assert groups[3]["lr_group"] == 2                             # projector shares the "other" learning-rate group
+
+    def early(order):
+        kd = GraphedKDStep.__new__(GraphedKDStep)
+        kd.model = model
+        kd.reducer = FlatGradAllReducer(order)
+        return kd._early_segment()
+
+    dec, ref, prj = list(model.decoder.parameters()), list(model.attention_refinement.parameters()), list(projector.parameters())
+    n_dec = sum(p.numel() for p in dec)
+    assert early(dec + ref + prj) == (0, n_dec)
+    n_ref = sum(p.numel() for p in ref)
+    assert early(ref + dec + prj) == (n_ref, n_ref + n_dec)
+    assert early(dec[:2] + ref + dec[2:] + prj) is None           # a foreign parameter inside the decoder's range: no early exchange
