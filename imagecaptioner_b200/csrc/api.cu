@@ -133,7 +133,7 @@ template <typename T> struct TrainWs {
 
 template <typename T> struct DecodeWs {
   Weights<T> w;
-  float *P, *u; T *emb, *G0, *o1; T* xh[MAXL]; float* c[MAXL]; float* logits; int64_t* cur; int32_t* done;
+  float *P, *u; T *emb, *G0, *o1; T* xh[MAXL]; float* c[MAXL]; float* logits; int64_t* cur; int32_t* done; float* amax_v; int* amax_i;
   size_t bytes;
   void carve(void* base, const B2CShape& s) {
     Carver c{reinterpret_cast<unsigned char*>(base), 0};
@@ -142,6 +142,7 @@ template <typename T> struct DecodeWs {
     P = c.take<float>(B * S * E); emb = c.take<T>(B * E); u = c.take<float>(B * E); G0 = c.take<T>(B * 4 * H); o1 = c.take<T>(B * E);
     for (int k = 0; k < s.L; ++k) { xh[k] = c.take<T>(2 * B * (in_dim(s, k) + H)); this->c[k] = c.take<float>(B * H); }   // two [input;h] slots (ping-pong)
     logits = c.take<float>(B * (size_t)s.V); cur = c.take<int64_t>(B); done = c.take<int32_t>(B);
+    amax_v = c.take<float>(B * (size_t)cdiv(s.V, 32)); amax_i = c.take<int>(B * (size_t)cdiv(s.V, 32));      // argmax partials (<= one per 32 columns)
     bytes = align_up(c.off, 256);
   }
 };
@@ -481,6 +482,8 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
 }
 
 
+inline bool fuse_argmax_off() { static const bool off = getenv("B2C_DECODE_LOGITS") != nullptr; return off; }     // A/B + debugging
+
 // ------------------------------------------------------------------ greedy decode (eval, argmax fed back on device)
 template <typename T>
 int greedy_decode_impl(const B2CShape& s, const B2CParams& p, const T* feats, int64_t start_id, int64_t end_id,
@@ -514,9 +517,20 @@ int greedy_decode_impl(const B2CShape& s, const B2CParams& p, const T* feats, in
                                 k + 1 < L ? slot(k + 1, pcur) : nullptr, (T*)nullptr, nodrop, 0));
     }
     B2C_TRY((gemm<T, T>(st, B, E, H, slot(L - 1, pnxt) + inL, ldL, 0, W.w.W1, H, 0, W.o1, E, 0.f, p.out0_b, 1)));
-    B2C_TRY((gemm<T, float>(st, B, V, E, W.o1, E, 0, W.w.W2, E, 0, W.logits, V, 0.f, p.out3_b)));
-    argmax_feedback_kernel<<<B, 256, 0, st>>>(W.logits, V, V, end_id, t, W.cur, tokens + (long)t * B, lengths, W.done);
-    B2C_LAUNCH_CHECK("argmax_feedback_kernel");
+    // vocabulary head.  bf16 mode on the tcgen05 path: the GEMM's epilogue reduces every tile to per-row partial (max, index)
+    // pairs, the logits are never written; otherwise (fp32 parity mode, or a pitch TMA cannot describe): logits + argmax kernel.
+    GemmArgs gv{B, V, E, 1.f, 0.f, W.o1, (long)E, 0, W.w.W2, (long)E, 0, W.logits, (long)V, p.out3_b, 0};
+    if (sizeof(T) == 2 && tc_eligible(gv) && !fuse_argmax_off()) {
+      ArgmaxEpi ae{W.amax_v, W.amax_i, 0, 0};
+      gv.amax = &ae;
+      B2C_TRY((Gemm<T, float>::run(gv, st)));
+      argmax_parts_feedback_kernel<<<cdiv(B, 8), 256, 0, st>>>(W.amax_v, W.amax_i, ae.nparts, B, end_id, t, W.cur, tokens + (long)t * B, lengths, W.done);
+      B2C_LAUNCH_CHECK("argmax_parts_feedback_kernel");
+    } else {
+      B2C_TRY((Gemm<T, float>::run(gv, st)));
+      argmax_feedback_kernel<<<B, 256, 0, st>>>(W.logits, V, V, end_id, t, W.cur, tokens + (long)t * B, lengths, W.done);
+      B2C_LAUNCH_CHECK("argmax_feedback_kernel");
+    }
   }
   finish_lengths_kernel<<<cdiv(B, 256), 256, 0, st>>>(lengths, B, Tn);
   B2C_LAUNCH_CHECK("finish_lengths_kernel");

@@ -548,6 +548,30 @@ argmax_feedback_kernel(const float* __restrict__ logits, int V, long ld, int64_t
     if (besti == end_id && !done[b]) { done[b] = 1; lengths[b] = t; }
   }
 }
+// Same feedback from the per-row partial (max, index) pairs the vocabulary-head GEMM's argmax epilogue leaves (gemm.cuh ArgmaxEpi):
+// one warp per sample reduces its `nparts` partials with the same ordering (larger value, then lower index).
+__global__ void __launch_bounds__(256)
+argmax_parts_feedback_kernel(const float* __restrict__ pmax, const int* __restrict__ pidx, int nparts, int B, int64_t end_id, int t,
+                             int64_t* __restrict__ cur_tok, int64_t* __restrict__ tokens_t, int32_t* __restrict__ lengths, int32_t* __restrict__ done) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float best = -INFINITY; int besti = 0x7fffffff;
+  for (int p = lane; p < nparts; p += 32) {
+    const float x = pmax[(long)b * nparts + p]; const int i = pidx[(long)b * nparts + p];
+    if (x > best || (x == best && i < besti)) { best = x; besti = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  if (lane == 0) {
+    if (besti == 0x7fffffff) besti = 0;      // all-NaN row
+    cur_tok[b] = besti; tokens_t[b] = besti;
+    if (t == 0) { done[b] = 0; lengths[b] = -1; }
+    if (besti == end_id && !done[b]) { done[b] = 1; lengths[b] = t; }
+  }
+}
 __global__ void fill_i64_kernel(int64_t* p, long n, int64_t v) { for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = v; }
 __global__ void finish_lengths_kernel(int32_t* lengths, int B, int T) { const int b = blockIdx.x * blockDim.x + threadIdx.x; if (b < B && lengths[b] < 0) lengths[b] = T; }
 

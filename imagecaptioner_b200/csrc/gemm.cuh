@@ -36,6 +36,17 @@ struct LstmEpi {
   float drop_p; unsigned long long seed; unsigned int site; long row_base;
 };
 
+// Greedy decoding needs argmax_n C[m, n] only: the vocabulary-head GEMM can reduce every accumulator tile to per-row partial
+// (max, index) pairs in its epilogue instead of writing the logits (41 MB per step at B = 2048, V = 5000, read again by the argmax
+// kernel).  One partial per (row, part): a part is the run of `cols_per_part` columns one epilogue warp drains of one tile.
+// The descriptor travels in the (otherwise unused) LstmEpi slot of the general instantiation: enabled == 2.
+struct ArgmaxEpi { float* pmax; int* pidx; int nparts; int cols_per_part; };
+inline LstmEpi pack_argmax(const ArgmaxEpi& a) {
+  LstmEpi le{};
+  le.enabled = 2; le.H = a.nparts; le.c_out = a.pmax; le.gates_out = a.pidx; le.ld_rec = a.cols_per_part;
+  return le;
+}
+
 // one hidden unit: pre[4] = i,f,g,o pre-activations (bias/addend already added) -> act[4], c, h
 template <typename TL>
 __device__ __forceinline__ void lstm_cell_unit(const float (&pre)[4], float c_prev, float (&act)[4], float& c, float& h) {
@@ -454,6 +465,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
     constexpr int NCHUNK = BN / CH;                      // 128-byte column chunks per tile row
     constexpr int C_PER = (NCHUNK + 1) / 2;
+    if (le.enabled == 2) {
+      // ---- argmax epilogue (ArgmaxEpi): this thread owns one row and C_PER * CH columns of it: running (max, lowest index)
+      float* pmax = le.c_out; int* pidx = reinterpret_cast<int*>(le.gates_out);
+      const int nparts = le.H, grow = m0 + q * 32 + lane;
+      float best = -INFINITY; int bidx = 0x7fffffff;
+#pragma unroll 1
+      for (int ci = half * C_PER; ci < (half + 1) * C_PER && ci < NCHUNK; ++ci) {
+#pragma unroll 1
+        for (int h = 0; h < CH / 32; ++h) {
+          const int colb = n0 + ci * CH + h * 32;
+          if (colb >= N) break;                             // warp-uniform
+          float v[32];
+          tmem_ld32(tacc + (uint32_t)(ci * CH + h * 32), v);
+          if (colb + 32 <= N && bias != nullptr && (((uintptr_t)bias) & 15) == 0) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + colb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = __ldg(b4 + j);
+              v[4 * j] = fmaf(alpha, v[4 * j], bb.x); v[4 * j + 1] = fmaf(alpha, v[4 * j + 1], bb.y);
+              v[4 * j + 2] = fmaf(alpha, v[4 * j + 2], bb.z); v[4 * j + 3] = fmaf(alpha, v[4 * j + 3], bb.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(alpha, v[j], (bias != nullptr && colb + j < N) ? bias[colb + j] : 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (colb + j < N && v[j] > best) { best = v[j]; bidx = colb + j; }     // ascending: ties keep the lowest index
+        }
+      }
+      if (grow < M) {
+        const int part = (n0 + half * C_PER * CH) / (C_PER * CH);
+        if (part < nparts) { pmax[(long)grow * nparts + part] = best; pidx[(long)grow * nparts + part] = bidx; }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      continue;
+    }
     // ---- fast path: a full interior tile, written once (beta = 0) or K-split partial sums reduced into fp32 C; 16-byte aligned C.  Straight-line
     // code without per-element predicates: the generic path below spends most of its issue slots (and instruction-cache
     // misses: ncu stall_no_inst + branch_resolving = 24 % of the samples of the vocab-head GEMM) on range / mode checks.
@@ -635,6 +684,7 @@ struct GemmArgs {
   const float* bias; int relu;
   int row_unperm_h = 0;              // != 0: output row m is written to row (m & 3) * H + (m >> 2) (gate-interleaved -> gate-major)
   const LstmEpi* lstm = nullptr;     // fused LSTM-cell epilogue instead of writing C
+  ArgmaxEpi* amax = nullptr;         // per-row partial argmax instead of writing C (tcgen05 path only; nparts / cols_per_part are filled in)
 };
 
 inline bool tc_eligible(const GemmArgs& g) {
@@ -647,7 +697,7 @@ inline bool tc_eligible(const GemmArgs& g) {
 struct TcPlan { int bn, splits, kb_per_split; };
 inline TcPlan plan_tc(const GemmArgs& g, int elem_c, int sms) {
   const int num_kb = cdiv(g.K, TC_BK);
-  const bool can_split = (elem_c == 4) && !g.relu && (g.beta == 0.f || g.beta == 1.f) && (g.lstm == nullptr);
+  const bool can_split = (elem_c == 4) && !g.relu && (g.beta == 0.f || g.beta == 1.f) && (g.lstm == nullptr) && (g.amax == nullptr);
   TcPlan best{64, 1, num_kb}; double best_cost = 1e30;
   const int cand[3] = {256, 128, 64};
   for (int ci = 0; ci < 3; ++ci) {
@@ -697,8 +747,16 @@ int launch_tc(const GemmArgs& g, const TcPlan& plan, cudaStream_t st) {
   const int tiles_m = cdiv(g.M, TC_BM), tiles_n = cdiv(g.N, BN);
   const long total = (long)tiles_m * tiles_n * splits;
   const int grid = (int)(total < sm_count() ? total : sm_count());
+  LstmEpi epi = g.lstm ? *g.lstm : LstmEpi{};
+  if (g.amax) {
+    B2C_CHECK_ARG(!g.lstm && splits == 1 && g.amax->pmax && g.amax->pidx, "argmax epilogue: no K split, no LSTM epilogue, partial buffers required");
+    constexpr int CHc = 128 / (int)sizeof(TC), CPER = (BN / CHc + 1) / 2;
+    g.amax->cols_per_part = CPER * CHc;
+    g.amax->nparts = cdiv(g.N, g.amax->cols_per_part);
+    epi = pack_argmax(*g.amax);
+  }
   B2C_CUDA(launch_pdl(kern, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES, st, ta, tb, g.M, g.N, g.K, g.alpha, g.beta, (TC*)g.C, g.ldc,
-                      g.bias, g.relu, kb_per_split, tiles_m, tiles_n, splits, g.row_unperm_h, g.lstm ? *g.lstm : LstmEpi{}));
+                      g.bias, g.relu, kb_per_split, tiles_m, tiles_n, splits, g.row_unperm_h, epi));
   B2C_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }

@@ -304,3 +304,26 @@ def test_validation_path_matches_reference_fixture():
     assert abs(avg_loss - ref["loss"]["total_loss"]) <= 1e-4 * max(1.0, abs(ref["loss"]["total_loss"]))
     assert abs(avg_bleu - float(fx["bleu"][:2].mean())) < 1e-6
     assert not model.training
+
+
+def test_fused_argmax_decode_equals_logits_path(tmp_path):
+    """bf16 greedy decode with the argmax reduced inside the vocabulary-head GEMM epilogue (no logits written) gives exactly the
+    tokens and lengths of the logits + argmax-kernel path (B2C_DECODE_LOGITS=1), including an edge N tile (V = 5000) and a batch
+    that is not a multiple of the 128-row tile."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for mode in ("fused", "logits"):
+        env = dict(os.environ)
+        env.pop("B2C_DECODE_LOGITS", None)
+        if mode == "logits":
+            env["B2C_DECODE_LOGITS"] = "1"
+        out = str(tmp_path / f"tok_{mode}.pt")
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_decode_argmax.py"), out], env=env, cwd=root,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.load(out))
+    assert torch.equal(outs[0]["tokens"], outs[1]["tokens"])
+    assert torch.equal(outs[0]["lengths"], outs[1]["lengths"])
+    assert outs[0]["tokens"].unique().numel() > 8              # not a degenerate caption (19 distinct ids over columns 171..4393)
