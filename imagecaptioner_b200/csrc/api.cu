@@ -463,7 +463,9 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
     // one CTA per sample: the 2 x Tn register loads of a thread are amortised over all S tokens (measured: 1 split 2.76 ms / step,
     // 2 -> 2.79, 4 -> 2.79, 7 -> 2.81)
     const int splits = 1, per = cdiv(S, splits), TP = (Tn + 3) & ~3;
-    attn_post_reg_kernel<T, 24><<<dim3(B, splits), ATT_THREADS, (size_t)2 * per * TP * 4, st>>>(W.P, W.u, W.dxh0, (long)(E + H), attw, W.ds, Tn, B, S, E, W.dP, dfeats);
+    const size_t psmem = (size_t)2 * per * TP * 4;
+    B2C_TRY(set_smem(attn_post_reg_kernel<T, 24>, psmem));          // > 48 KB only for very long token lists
+    attn_post_reg_kernel<T, 24><<<dim3(B, splits), ATT_THREADS, psmem, st>>>(W.P, W.u, W.dxh0, (long)(E + H), attw, W.ds, Tn, B, S, E, W.dP, dfeats);
     B2C_LAUNCH_CHECK("attn_post_reg_kernel");
   } else {
     const size_t smem = (size_t)Tn * (2 * E + 2 * S) * 4;
