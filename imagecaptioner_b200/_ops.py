@@ -92,6 +92,8 @@ SYMBOLS = {
     "b2c_decoder_prepare": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_decoder_forward_prepared": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_decoder_backward": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _GRD, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
+    "b2c_set_defer_side_join": (ctypes.c_int, [ctypes.c_int]),
+    "b2c_join_side_work": (ctypes.c_int, [_vp]),
     "b2c_greedy_decode": (ctypes.c_int, [_SHP, _PRM, _vp, _i64, _i64, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_attention_step": (ctypes.c_int, [_SHP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_refinement_forward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CRefineParams), _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),

@@ -345,6 +345,10 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
 }
 
 
+// Deferred join of the weight-gradient branch (b2c_set_defer_side_join / b2c_join_side_work, include/b2c.h)
+// process-wide, not thread_local: PyTorch runs backward functions on its autograd worker thread, not on the thread that set the flag
+inline volatile bool& defer_side_join() { static volatile bool on = false; return on; }
+
 // ------------------------------------------------------------------ decoder backward (BPTT), oracle/manual_backward.py v2
 template <typename T>
 int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats, const int64_t* cap, const T* hid_top,
@@ -479,6 +483,7 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
   B2C_TRY((gemm<T, float>(side, E, E, B * S, W.dP, E, 1, feats, E, 1, g.attn_w + H, H + E)));                      // dW_a[:, H:]
   B2C_TRY(colsum<T>(side, W.dP, (long)B * S, E, E, W.partial_side, g.attn_b));
   B2C_CUDA(cudaEventRecord(hs->join[MAX_SUB - 1], side));
+  if (defer_side_join()) return 0;                                  // the caller joins with b2c_join_side_work (b2c_set_defer_side_join)
   B2C_CUDA(cudaStreamWaitEvent(st, hs->join[MAX_SUB - 1], 0));      // every weight gradient is complete when the call's work on `stream` is
   return 0;
 }
@@ -943,6 +948,16 @@ int b2c_decoder_backward(const B2CShape* shape, const B2CParams* params, const v
   if (dtype == B2C_F32) return decoder_backward_impl<float>(*shape, *params, (const float*)feats, captions, (const float*)hidden_top, attn_w, (const float*)dlogits, (const float*)dhidden_top, *grads, dfeats, workspace, ws_bytes, dr, st);
   if (dtype == B2C_BF16) return decoder_backward_impl<bf16>(*shape, *params, (const bf16*)feats, captions, (const bf16*)hidden_top, attn_w, (const bf16*)dlogits, (const bf16*)dhidden_top, *grads, dfeats, workspace, ws_bytes, dr, st);
   return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_set_defer_side_join(int on) { defer_side_join() = (on != 0); return 0; }
+
+int b2c_join_side_work(void* stream) {
+  B2C_TRY(check_device());
+  SubStreams* hs = nullptr;
+  B2C_TRY(get_substreams(&hs));
+  B2C_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, hs->join[MAX_SUB - 1], 0));
+  return 0;
 }
 
 int b2c_greedy_decode(const B2CShape* shape, const B2CParams* params, const void* feats, int64_t start_id, int64_t end_id,

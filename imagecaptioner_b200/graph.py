@@ -54,6 +54,7 @@ class GraphedKDStep:
         self._overlap = False
         self._capturing = False
         self.high_priority_chain = os.environ.get("B2C_CHAIN_PRIORITY", "1") != "0"
+        self.defer_weight_grad_join = os.environ.get("B2C_DEFER_JOIN", "1") != "0"
         # every trainable parameter here gets exactly one gradient per step from one native backward call, so the kernels may
         # write it directly into the flat all-reduce buffer (saves ~35 accumulate kernels + the buffer zeroing per step)
         self.direct_grads = direct_grads
@@ -137,10 +138,20 @@ class GraphedKDStep:
             self.reducer.zero_grad()
         if self._capturing and self.overlap_comm and self._early is not None:
             _ops.after_decoder_backward = self._ev_dec.record            # event-record node right behind b2c_decoder_backward
+        # Single rank: the weight-gradient branch of b2c_decoder_backward (side stream) is joined AFTER the whole backward, so the
+        # refinement backward overlaps it instead of waiting 0.26 ms for it (the parameters' gradients are first read by the
+        # optimizer).  Multi-rank keeps the join inside the call: the early all-reduce reads the decoder's gradients right after it.
+        defer = self.defer_weight_grad_join and not self._multi
+        lib = _ops.load_library()
+        if defer:
+            lib.b2c_set_defer_side_join(1)
         try:
             loss.backward()
         finally:
             _ops.after_decoder_backward = None
+            if defer:
+                lib.b2c_set_defer_side_join(0)
+                _ops._check(lib.b2c_join_side_work(_ops._stream()), "b2c_join_side_work")
         if self.direct_grads:
             self.reducer.attach_views()          # the flat buffer is authoritative (the kernels wrote into it), whatever autograd kept
         return out5

@@ -117,6 +117,16 @@ int b2c_decoder_backward(const B2CShape* shape, const B2CParams* params, const v
                          const B2CGrads* grads, float* dfeats, void* workspace, size_t ws_bytes,
                          int dtype, const B2CDropout* dropout, void* stream);
 
+/* b2c_decoder_backward contracts every weight gradient on an internal side stream next to the chain that produces dfeats, and by
+ * default makes `stream` wait for that branch before it returns ("all work is enqueued on stream").  A caller that does not read
+ * parameter gradients until later (an optimizer step after the rest of the backward) may defer the wait so that whatever it
+ * enqueues next (the refinement backward) overlaps the weight-gradient contractions:
+ *   b2c_set_defer_side_join(1);  b2c_decoder_backward(...);  ... more work on stream ...;  b2c_join_side_work(stream);
+ * The flag is process-wide (autograd engines call the backward from worker threads).  With the flag set, parameter gradients are
+ * defined only after b2c_join_side_work. */
+int b2c_set_defer_side_join(int on);
+int b2c_join_side_work(void* stream);
+
 /* Batched greedy decode: every sample starts at start_id and steps shape->T (= max_len) times with its own
  * argmax fed back on the device (no host sync per token).  out: tokens (T,B) int64; lengths (B) int32 =
  * number of tokens emitted before the first end_id (T if none) == len(caption_image(...)). */
