@@ -18,7 +18,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libb2c.so")
 B2C_MAX_LAYERS = 4
 B2C_F32, B2C_BF16 = 0, 1
 B2C_WS_TRAIN, B2C_WS_DECODE, B2C_WS_ATTN, B2C_WS_REFINE, B2C_WS_PROJ = 0, 1, 2, 3, 4
-ABI_VERSION = 1
+ABI_VERSION = 2
+B2C_BWD_DEFER_JOIN = 1
 
 c_f32p = ctypes.c_void_p
 
@@ -63,7 +64,7 @@ class B2CProjGrads(ctypes.Structure):
 
 
 class B2CDropout(ctypes.Structure):
-    _fields_ = [("p", ctypes.c_float), ("seed", ctypes.c_uint64)]
+    _fields_ = [("p", ctypes.c_float), ("seed", ctypes.c_uint64), ("seed_dev", ctypes.c_void_p)]
 
 
 B2C_OPT_MAX_SEG, B2C_OPT_MAX_CLIP, B2C_OPT_SCRATCH_BYTES = 8, 4, 16384
@@ -91,8 +92,8 @@ SYMBOLS = {
     "b2c_decoder_forward": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_decoder_prepare": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_decoder_forward_prepared": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
-    "b2c_decoder_backward": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _GRD, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
-    "b2c_set_defer_side_join": (ctypes.c_int, [ctypes.c_int]),
+    "b2c_decoder_backward": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _GRD, _vp, _vp, _sz, ctypes.c_int, _DRP, ctypes.c_int, _vp]),
+    "b2c_bump_counter": (ctypes.c_int, [_vp, _vp]),
     "b2c_join_side_work": (ctypes.c_int, [_vp]),
     "b2c_greedy_decode": (ctypes.c_int, [_SHP, _PRM, _vp, _i64, _i64, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_attention_step": (ctypes.c_int, [_SHP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
@@ -193,29 +194,61 @@ def _master(params: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     return out
 
 
-# Optional gradient destinations: parameter data_ptr -> fp32 tensor (a view into the flat all-reduce buffer of
-# imagecaptioner_b200.ddp).  When registered (GraphedKDStep does, for one-micro-batch-per-step training), the backward
-# kernels write a parameter's gradient straight into its slot and return that view; with `.grad = None` autograd adopts it
-# without a copy or an add kernel.  The kernels OVERWRITE, so this must stay off when gradients are accumulated over
-# several backward passes (the default).
-_GRAD_DEST = {}
+class CallOptions:
+    """Per-call options of the native autograd Functions.  A module reads them from its `b2c_options` attribute at FORWARD time and
+    the Function keeps them in its ctx for the backward, so nothing here is process-global: two models (or two devices, or an
+    eager loop next to a GraphedKDStep) do not see each other's settings.
+
+    grad_dest       parameter data_ptr -> fp32 tensor (a view into the flat gradient buffer of imagecaptioner_b200.ddp).  The
+                    backward kernels then write that parameter's gradient straight into its slot and return the view; with
+                    `.grad = None` autograd adopts it without a copy or an add kernel.  The kernels OVERWRITE, so this is only
+                    for one-backward-per-step training (GraphedKDStep); leave it None when gradients are accumulated.
+    defer_join      b2c_decoder_backward returns without joining its weight-gradient side branch (B2C_BWD_DEFER_JOIN); the owner
+                    calls join_side_work() before the gradients are read.  Honoured only when every decoder gradient goes to a
+                    grad_dest slot (a fresh tensor would be consumed by autograd's accumulation before it is written).
+    after_backward  callable run right after b2c_decoder_backward is enqueued (same stream): GraphedKDStep records an event there
+                    so the all-reduce of the decoder's gradient segment can start while the refinement backward still runs.
+    seed_dev        int64 device tensor (1 element): the per-step dropout counter the kernels mix into the seed (B2CDropout.seed_dev),
+                    so CUDA-graph replays draw fresh masks."""
+
+    def __init__(self, grad_dest=None, defer_join=False, after_backward=None, seed_dev=None):
+        self.grad_dest, self.defer_join, self.after_backward, self.seed_dev = grad_dest, defer_join, after_backward, seed_dev
+        self.join_pending = False      # set by DecoderFunction.backward when it deferred the join
 
 
-def set_grad_destinations(mapping) -> None:
-    _GRAD_DEST.clear()
-    if mapping:
-        _GRAD_DEST.update(mapping)
+_NO_OPTIONS = CallOptions()
 
 
-def _grad_buffers(params, master):
-    out = []
+def _options(opts) -> CallOptions:
+    return opts if opts is not None else _NO_OPTIONS
+
+
+def _dropout(p, seed, opts) -> B2CDropout:
+    sd = opts.seed_dev
+    return B2CDropout(float(p), int(seed), sd.data_ptr() if (sd is not None and float(p) > 0) else None)
+
+
+def bump_counter(counter: torch.Tensor) -> None:
+    """counter[0] += 1 on the current stream (the dropout step counter; one tiny native launch, capturable)."""
+    _check(load_library().b2c_bump_counter(counter.data_ptr(), _stream()), "b2c_bump_counter")
+
+
+def join_side_work() -> None:
+    _check(load_library().b2c_join_side_work(_stream()), "b2c_join_side_work")
+
+
+def _grad_buffers(params, master, opts=None):
+    """-> (gradient tensors, all_direct): all_direct is True when every one is a registered destination slot."""
+    dest = _options(opts).grad_dest
+    out, all_direct = [], bool(dest)
     for p, m in zip(params, master):
-        dst = _GRAD_DEST.get(p.data_ptr()) if _GRAD_DEST else None
+        dst = dest.get(p.data_ptr()) if dest else None
         if dst is not None and dst.dtype == torch.float32 and dst.shape == m.shape and dst.is_contiguous():
             out.append(dst.view(dst.shape))      # a fresh view object: autograd adopts it as .grad only if nothing else holds it
         else:
             out.append(torch.empty_like(m))
-    return out
+            all_direct = False
+    return out, all_direct
 
 
 def workspace_bytes(shape: B2CShape, code: int, mode: int) -> int:
@@ -224,11 +257,6 @@ def workspace_bytes(shape: B2CShape, code: int, mode: int) -> int:
     if n == 0:
         _check(-1, "b2c_workspace_bytes")
     return n
-
-
-# Optional callable run right after b2c_decoder_backward is enqueued (same stream): graph.GraphedKDStep records an event there
-# so the gradient all-reduce of the decoder's parameters can start while the refinement backward still runs.
-after_decoder_backward = None
 
 
 class PreparedDecoder:
@@ -275,8 +303,9 @@ class DecoderFunction(torch.autograd.Function):
     """LSTMDecoder.forward (reference src/student_model.py:205-256) as one C-ABI call each way."""
 
     @staticmethod
-    def forward(ctx, feats, captions, compute_dtype, dropout_p, seed, L, prepared, *params):
+    def forward(ctx, feats, captions, compute_dtype, dropout_p, seed, L, prepared, opts, *params):
         lib = load_library()
+        opts = _options(opts)
         _require_cuda(feats, "image_features")
         B, S, E = feats.shape
         T = captions.shape[0]
@@ -300,11 +329,11 @@ class DecoderFunction(torch.autograd.Function):
         hid = torch.empty(T, B, H, dtype=compute_dtype, device=feats.device)
         attw = torch.empty(T, B, S, dtype=torch.float32, device=feats.device)
         prm = _fill_struct(B2CParams(), master, L)
-        drop = B2CDropout(float(dropout_p), int(seed))
+        drop = _dropout(dropout_p, seed, opts)
         _check(fwd(ctypes.byref(shape), ctypes.byref(prm), f.data_ptr(), cap.data_ptr(), logits.data_ptr(),
                    hid.data_ptr(), attw.data_ptr(), ws.data_ptr(), ws.numel(), code, ctypes.byref(drop), _stream()),
                "b2c_decoder_forward")
-        ctx.b2c = (shape, code, drop, L, ws, f, cap, master, hid, attw, feats.dtype, [p.dtype for p in params])
+        ctx.b2c = (shape, code, drop, L, ws, f, cap, master, hid, attw, feats.dtype, [p.dtype for p in params], opts)
         ctx.b2c_params = params
         ctx.mark_non_differentiable(attw)
         return logits, hid, attw
@@ -312,26 +341,31 @@ class DecoderFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits, dhid, _dattw):
         lib = load_library()
-        shape, code, drop, L, ws, f, cap, master, hid, attw, feats_dtype, pdtypes = ctx.b2c
+        shape, code, drop, L, ws, f, cap, master, hid, attw, feats_dtype, pdtypes, opts = ctx.b2c
         cdt = f.dtype
         if dlogits is None:
             dlogits = torch.zeros(shape.T, shape.B, shape.V, dtype=cdt, device=f.device)
         dlogits = dlogits.to(cdt).contiguous()
         if dhid is not None:
             dhid = dhid.to(cdt).contiguous()
-        grads = _grad_buffers(ctx.b2c_params, master)
+        grads, all_direct = _grad_buffers(ctx.b2c_params, master, opts)
+        # the weight gradients are written on the library's side stream: the join may only be deferred when none of them is a
+        # fresh tensor that autograd accumulates / casts on this stream right after the call returns
+        defer = opts.defer_join and all_direct and all(dt == torch.float32 for dt in pdtypes)
         dfeats = torch.empty(shape.B, shape.S, shape.E, dtype=torch.float32, device=f.device)
         prm = _fill_struct(B2CParams(), master, L)
         grd = _fill_struct(B2CGrads(), grads, L)
         _check(lib.b2c_decoder_backward(ctypes.byref(shape), ctypes.byref(prm), f.data_ptr(), cap.data_ptr(), hid.data_ptr(), attw.data_ptr(),
                                         dlogits.data_ptr(), _ptr(dhid), ctypes.byref(grd), dfeats.data_ptr(), ws.data_ptr(), ws.numel(),
-                                        code, ctypes.byref(drop), _stream()),
+                                        code, ctypes.byref(drop), B2C_BWD_DEFER_JOIN if defer else 0, _stream()),
                "b2c_decoder_backward")
-        if after_decoder_backward is not None:          # GraphedKDStep: the decoder's gradients are final from here on this stream
-            after_decoder_backward()
+        if defer:
+            opts.join_pending = True                     # the owner of `opts` calls join_side_work() and clears this
+        if opts.after_backward is not None:              # GraphedKDStep: the decoder's gradients are enqueued from here on
+            opts.after_backward()
         grads = [g if g.dtype == dt else g.to(dt) for g, dt in zip(grads, pdtypes)]
         dfe = dfeats if feats_dtype == torch.float32 else dfeats.to(feats_dtype)
-        return (dfe, None, None, None, None, None, None, *grads)
+        return (dfe, None, None, None, None, None, None, None, *grads)
 
 
 def greedy_decode(feats: torch.Tensor, params: Sequence[torch.Tensor], L: int, max_len: int, start_id: int, end_id: int,
@@ -539,8 +573,9 @@ class RefinementFunction(torch.autograd.Function):
     GEMM, the 49x49 4-head attention core, residual LayerNorms and every gradient in native kernels."""
 
     @staticmethod
-    def forward(ctx, x, compute_dtype, dropout_p, seed, heads, *params):
+    def forward(ctx, x, compute_dtype, dropout_p, seed, heads, opts, *params):
         lib = load_library()
+        opts = _options(opts)
         _require_cuda(x, "features")
         B, S, E = x.shape
         shape = B2CShape(B, 1, S, E, heads, 1, 2)
@@ -550,26 +585,26 @@ class RefinementFunction(torch.autograd.Function):
         ws = torch.empty(workspace_bytes(shape, code, B2C_WS_REFINE), dtype=torch.uint8, device=x.device)
         out = torch.empty(B, S, E, dtype=compute_dtype, device=x.device)
         prm = _fill_flat(B2CRefineParams(), master)
-        drop = B2CDropout(float(dropout_p), int(seed))
+        drop = _dropout(dropout_p, seed, opts)
         _check(lib.b2c_refinement_forward(ctypes.byref(shape), ctypes.byref(prm), xf.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
                                           code, ctypes.byref(drop), _stream()), "b2c_refinement_forward")
-        ctx.b2c = (shape, code, drop, ws, master, x.dtype, [p.dtype for p in params], compute_dtype)
+        ctx.b2c = (shape, code, drop, ws, master, x.dtype, [p.dtype for p in params], compute_dtype, opts)
         ctx.b2c_params = params
         return out
 
     @staticmethod
     def backward(ctx, dout):
         lib = load_library()
-        shape, code, drop, ws, master, x_dtype, pdtypes, cdt = ctx.b2c
+        shape, code, drop, ws, master, x_dtype, pdtypes, cdt, opts = ctx.b2c
         dout = dout.to(cdt).contiguous()
-        grads = _grad_buffers(ctx.b2c_params, master)
+        grads, _ = _grad_buffers(ctx.b2c_params, master, opts)
         dx = torch.empty(shape.B, shape.S, shape.E, dtype=torch.float32, device=dout.device)
         prm = _fill_flat(B2CRefineParams(), master)
         grd = _fill_flat(B2CRefineGrads(), grads)
         _check(lib.b2c_refinement_backward(ctypes.byref(shape), ctypes.byref(prm), dout.data_ptr(), ctypes.byref(grd), dx.data_ptr(),
                                            ws.data_ptr(), ws.numel(), code, ctypes.byref(drop), _stream()), "b2c_refinement_backward")
         grads = [g if g.dtype == dt else g.to(dt) for g, dt in zip(grads, pdtypes)]
-        return (dx if x_dtype == torch.float32 else dx.to(x_dtype), None, None, None, None, *grads)
+        return (dx if x_dtype == torch.float32 else dx.to(x_dtype), None, None, None, None, None, *grads)
 
 
 class ProjectorFunction(torch.autograd.Function):
@@ -577,8 +612,9 @@ class ProjectorFunction(torch.autograd.Function):
     token pooling, and the parameter gradients, in native kernels.  `params` is empty for the identity channel projection."""
 
     @staticmethod
-    def forward(ctx, x, compute_dtype, dropout_p, seed, out_tokens, student_dim, *params):
+    def forward(ctx, x, compute_dtype, dropout_p, seed, out_tokens, student_dim, opts, *params):
         lib = load_library()
+        opts = _options(opts)
         _require_cuda(x, "teacher features")
         B, St, Et = x.shape
         shape = B2CShape(B, out_tokens, St, Et, student_dim, 1, 2)
@@ -589,27 +625,27 @@ class ProjectorFunction(torch.autograd.Function):
         nbytes = workspace_bytes(shape, code, B2C_WS_PROJ) if master else 256
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         out = torch.empty(B, out_tokens, student_dim, dtype=torch.float32, device=x.device)
-        drop = B2CDropout(float(dropout_p), int(seed))
+        drop = _dropout(dropout_p, seed, opts)
         _check(lib.b2c_projector_forward(ctypes.byref(shape), ctypes.byref(prm), xf.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
                                          code, ctypes.byref(drop), _stream()), "b2c_projector_forward")
-        ctx.b2c = (shape, code, drop, ws, master, [p.dtype for p in params])
+        ctx.b2c = (shape, code, drop, ws, master, [p.dtype for p in params], opts)
         ctx.b2c_params = params
         return out
 
     @staticmethod
     def backward(ctx, dout):
         lib = load_library()
-        shape, code, drop, ws, master, pdtypes = ctx.b2c
+        shape, code, drop, ws, master, pdtypes, opts = ctx.b2c
         if not master:
-            return (None,) * 6
+            return (None,) * 7
         dout = dout.to(torch.float32).contiguous()
-        grads = _grad_buffers(ctx.b2c_params, master)
+        grads, _ = _grad_buffers(ctx.b2c_params, master, opts)
         prm = _fill_flat(B2CProjParams(), master)
         grd = _fill_flat(B2CProjGrads(), grads)
         _check(lib.b2c_projector_backward(ctypes.byref(shape), ctypes.byref(prm), dout.data_ptr(), ctypes.byref(grd), ws.data_ptr(), ws.numel(),
                                           code, ctypes.byref(drop), _stream()), "b2c_projector_backward")
         grads = [g if g.dtype == dt else g.to(dt) for g, dt in zip(grads, pdtypes)]
-        return (None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, None, *grads)
 
 
 def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,

@@ -221,7 +221,7 @@ int lstm_layer_fwd(cudaStream_t st, const B2CShape& s, const Weights<T>& w, int 
   le.enabled = 1; le.H = s.H; le.addend = addend; le.bias = (k == 0) ? nullptr : w.bcat[k];     // layer 0: b_x is inside the addend
   le.c_prev = c_prev; le.c_out = c_out; le.gates_out = gates_out;
   le.h_rec = h_rec; le.ld_rec = ld; le.h_next = h_next; le.ld_next = 2 * s.H; le.h_top = h_top; le.ld_top = s.H;
-  le.drop_p = dr.p; le.seed = dr.seed; le.site = (unsigned)k; le.row_base = row_base;
+  le.drop_p = dr.p; le.seed = dr.seed; le.site = (unsigned)k; le.row_base = row_base; le.seed_dev = (const unsigned long long*)dr.seed_dev;
   return gemm_lstm<T>(st, s.B, s.H, ld, xh_t, ld, w.Wcat[k], ld, le);
 }
 
@@ -233,8 +233,14 @@ int lstm_layer_fwd(cudaStream_t st, const B2CShape& s, const Weights<T>& w, int 
 // still see whole tensors.  Fork / join use events, which CUDA graph capture records as parallel branches.
 constexpr int MAX_SUB = 5;          // 4 sub-batch branches (B2C_SUB_BATCHES) + 1 side stream for work hidden under the recurrence
 struct SubStreams { cudaStream_t s[MAX_SUB]; cudaEvent_t fork; cudaEvent_t join[MAX_SUB]; cudaEvent_t ev[4]; };
+constexpr int MAX_DEVICES = 64;
 int get_substreams(SubStreams** out) {
-  static SubStreams ss; static bool ready = false;
+  // one stream / event set per device (created on first use with that device current): a process may drive several GPUs
+  static SubStreams all[MAX_DEVICES]; static bool all_ready[MAX_DEVICES] = {false};
+  int dev = 0;
+  B2C_CUDA(cudaGetDevice(&dev));
+  B2C_CHECK_ARG(dev >= 0 && dev < MAX_DEVICES, "device index %d outside [0,%d)", dev, MAX_DEVICES);
+  SubStreams& ss = all[dev]; bool& ready = all_ready[dev];
   if (!ready) {
     for (int i = 0; i < MAX_SUB; ++i) {
       B2C_CUDA(cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking));
@@ -337,7 +343,7 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
   // output head, time-batched: y = W2 Drop(ReLU(W1 h + b1)) + b2
   B2C_TRY((gemm<T, T>(st, (int)TB, E, H, hid_top, H, 0, W.w.W1, H, 0, W.o1, E, 0.f, p.out0_b, 1)));
   if (dr.p > 0.f) {
-    dropout_inplace_kernel<T><<<ew_grid(TB * E), 256, 0, st>>>(W.o1, TB * E, dr.p, dr.seed, 100u);
+    dropout_inplace_kernel<T><<<ew_grid(TB * E), 256, 0, st>>>(W.o1, TB * E, dr.p, dr.seed, 100u, (const unsigned long long*)dr.seed_dev);
     B2C_LAUNCH_CHECK("dropout_inplace_kernel");
   }
   B2C_TRY((gemm<T, T>(st, (int)TB, V, E, W.o1, E, 0, W.w.W2, E, 0, logits, V, 0.f, p.out3_b)));
@@ -345,15 +351,12 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
 }
 
 
-// Deferred join of the weight-gradient branch (b2c_set_defer_side_join / b2c_join_side_work, include/b2c.h)
-// process-wide, not thread_local: PyTorch runs backward functions on its autograd worker thread, not on the thread that set the flag
-inline volatile bool& defer_side_join() { static volatile bool on = false; return on; }
 
 // ------------------------------------------------------------------ decoder backward (BPTT), oracle/manual_backward.py v2
 template <typename T>
 int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats, const int64_t* cap, const T* hid_top,
                           const float* attw, const T* dlogits, const T* dhid, const B2CGrads& g, float* dfeats,
-                          void* ws, size_t ws_bytes, const B2CDropout& dr, cudaStream_t st) {
+                          void* ws, size_t ws_bytes, const B2CDropout& dr, cudaStream_t st, int flags) {
   TrainWs<T> W; W.carve(ws, s);
   B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
   B2C_CHECK_ARG(g.embedding && g.attn_w && g.attn_b && g.comb_w && g.comb_b && g.out0_w && g.out0_b && g.out3_w && g.out3_b && dfeats, "NULL gradient pointer");
@@ -420,7 +423,7 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
         B2C_CUDA(launch_pdl(lstm_pointwise_bwd_kernel<T>, dim3(ew_grid((long)Bh * H)), dim3(256), 0, ss,
             (const T*)(W.gates[k] + row * 4 * H), (const float*)(W.c[k] + row * H), (const float*)(W.c[k] + (row + B) * H), W.dc[k] + b0 * H, last ? 1 : 0,
             carry, (long)ld, above, (long)(2 * H), (const float*)(top ? W.dHext + row * H : nullptr), (const T*)((top && dhid) ? dhid + row * H : nullptr),
-            (const T*)((top && !last) ? W.dq + b0 * H : nullptr), (long)H, W.dgates[k] + row * 4 * H, Bh, H, dr.p, dr.seed, (uint32_t)k, row));
+            (const T*)((top && !last) ? W.dq + b0 * H : nullptr), (long)H, W.dgates[k] + row * 4 * H, Bh, H, dr.p, dr.seed, (uint32_t)k, row, (const unsigned long long*)dr.seed_dev));
         B2C_LAUNCH_CHECK("lstm_pointwise_bwd_kernel");
         float* out = (k == 0) ? W.dxh0 + row * (E + H) : W.dxh[k] + row * 2 * H;
         B2C_TRY((gemm<T, float>(ss, Bh, ld, 4 * H, W.dgates[k] + row * 4 * H, 4 * H, 0, W.w.Wcat[k], ld, 1, out, ld, 1.f)));
@@ -483,7 +486,7 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
   B2C_TRY((gemm<T, float>(side, E, E, B * S, W.dP, E, 1, feats, E, 1, g.attn_w + H, H + E)));                      // dW_a[:, H:]
   B2C_TRY(colsum<T>(side, W.dP, (long)B * S, E, E, W.partial_side, g.attn_b));
   B2C_CUDA(cudaEventRecord(hs->join[MAX_SUB - 1], side));
-  if (defer_side_join()) return 0;                                  // the caller joins with b2c_join_side_work (b2c_set_defer_side_join)
+  if (flags & B2C_BWD_DEFER_JOIN) return 0;                         // the caller joins with b2c_join_side_work
   B2C_CUDA(cudaStreamWaitEvent(st, hs->join[MAX_SUB - 1], 0));      // every weight gradient is complete when the call's work on `stream` is
   return 0;
 }
@@ -498,7 +501,7 @@ int greedy_decode_impl(const B2CShape& s, const B2CParams& p, const T* feats, in
   DecodeWs<T> W; W.carve(ws, s);
   B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
   const int B = s.B, Tn = s.T, S = s.S, E = s.E, H = s.H, L = s.L, V = s.V;
-  const B2CDropout nodrop{0.f, 0};
+  const B2CDropout nodrop{0.f, 0, nullptr};
   B2C_TRY(pack_params<T>(s, p, W.w, st));
   B2C_TRY((gemm<T, float>(st, B * S, E, E, feats, E, 0, W.w.Wf, E, 0, W.P, E, 0.f, p.attn_b)));
   for (int k = 0; k < L; ++k) {
@@ -677,19 +680,19 @@ int refinement_forward_impl(const B2CShape& s, const B2CRefineParams& p, const f
   B2C_TRY((gemm<T, T>(st, (int)R, 3 * E, E, W.x, E, 0, W.Win, E, 0, W.qkv, 3 * E, 0.f, p.in_b)));
   if (mha_use_mma<T>(S, hd)) {
     mha_fwd_mma_kernel<<<dim3(B, heads), MM_THREADS, 0, st>>>((const bf16*)W.qkv, (bf16*)W.attn, (bf16*)W.probs, S, E, heads, 1.0f / sqrtf((float)hd),
-                                                             dr.p, dr.seed, MHA_DROP_SITE);
+                                                             dr.p, dr.seed, MHA_DROP_SITE, (const unsigned long long*)dr.seed_dev);
     B2C_LAUNCH_CHECK("mha_fwd_mma_kernel");
   } else {
     const size_t smem = ((size_t)3 * S * mha_pitch(hd) + (size_t)S * mha_pitch(S)) * 4;
     B2C_TRY(set_smem(mha_fwd_kernel<T>, smem));
-    mha_fwd_kernel<T><<<dim3(B, heads), MHA_THREADS, smem, st>>>(W.qkv, W.attn, W.probs, S, E, heads, 1.0f / sqrtf((float)hd), dr.p, dr.seed);
+    mha_fwd_kernel<T><<<dim3(B, heads), MHA_THREADS, smem, st>>>(W.qkv, W.attn, W.probs, S, E, heads, 1.0f / sqrtf((float)hd), dr.p, dr.seed, (const unsigned long long*)dr.seed_dev);
     B2C_LAUNCH_CHECK("mha_fwd_kernel");
   }
   B2C_TRY((gemm<T, T>(st, (int)R, E, E, W.attn, E, 0, W.Wo, E, 0, W.proj, E, 0.f, p.out_b)));
   B2C_TRY((ln_fwd<T, T>(st, W.x, W.proj, p.n1_w, p.n1_b, W.x1, W.mean1, W.rstd1, R, E)));
   B2C_TRY((gemm<T, T>(st, (int)R, 2 * E, E, W.x1, E, 0, W.W1, E, 0, W.f1, 2 * E, 0.f, p.ffn0_b, 1)));
   if (dr.p > 0.f) {
-    dropout_inplace_kernel<T><<<ew_grid(R * 2 * E), 256, 0, st>>>(W.f1, R * 2 * E, dr.p, dr.seed, 201u);
+    dropout_inplace_kernel<T><<<ew_grid(R * 2 * E), 256, 0, st>>>(W.f1, R * 2 * E, dr.p, dr.seed, 201u, (const unsigned long long*)dr.seed_dev);
     B2C_LAUNCH_CHECK("dropout_inplace_kernel");
   }
   B2C_TRY((gemm<T, T>(st, (int)R, E, 2 * E, W.f1, 2 * E, 0, W.W2, 2 * E, 0, W.f2, E, 0.f, p.ffn3_b)));
@@ -722,12 +725,12 @@ int refinement_backward_impl(const B2CShape& s, const B2CRefineParams& p, const 
     const size_t smem = (size_t)(dr.p > 0.f ? 7 : 6) * MM_TILE * sizeof(bf16);
     B2C_TRY(set_smem(mha_bwd_mma_kernel, smem));
     mha_bwd_mma_kernel<<<dim3(B, heads), MM_THREADS, smem, st>>>((const bf16*)W.qkv, (const bf16*)W.probs, (const bf16*)W.dattn, (bf16*)W.dqkv, S, E, heads,
-                                                                1.0f / sqrtf((float)hd), dr.p, dr.seed, MHA_DROP_SITE);
+                                                                1.0f / sqrtf((float)hd), dr.p, dr.seed, MHA_DROP_SITE, (const unsigned long long*)dr.seed_dev);
     B2C_LAUNCH_CHECK("mha_bwd_mma_kernel");
   } else {
     const size_t smem = ((size_t)4 * S * mha_pitch(hd) + (size_t)(dr.p > 0.f ? 3 : 2) * S * mha_pitch(S)) * 4;
     B2C_TRY(set_smem(mha_bwd_kernel<T>, smem));
-    mha_bwd_kernel<T><<<dim3(B, heads), MHA_THREADS, smem, st>>>(W.qkv, W.probs, W.dattn, W.dqkv, S, E, heads, 1.0f / sqrtf((float)hd), dr.p, dr.seed);
+    mha_bwd_kernel<T><<<dim3(B, heads), MHA_THREADS, smem, st>>>(W.qkv, W.probs, W.dattn, W.dqkv, S, E, heads, 1.0f / sqrtf((float)hd), dr.p, dr.seed, (const unsigned long long*)dr.seed_dev);
     B2C_LAUNCH_CHECK("mha_bwd_kernel");
   }
   // qkv = x Win^T + b
@@ -782,7 +785,7 @@ int projector_forward_impl(const B2CShape& s, const B2CProjParams& p, const floa
   B2C_LAUNCH_CHECK("cast_f32_kernel");
   B2C_TRY((gemm<T, T>(st, (int)R, Es, Et, W.xb, Et, 0, W.Wp, Et, 0, W.h, Es, 0.f, p.b, 1)));
   if (dr.p > 0.f) {
-    dropout_inplace_kernel<T><<<ew_grid(R * Es), 256, 0, st>>>(W.h, R * Es, dr.p, dr.seed, 210u);
+    dropout_inplace_kernel<T><<<ew_grid(R * Es), 256, 0, st>>>(W.h, R * Es, dr.p, dr.seed, 210u, (const unsigned long long*)dr.seed_dev);
     B2C_LAUNCH_CHECK("dropout_inplace_kernel");
   }
   {
@@ -821,9 +824,9 @@ int kd_token_loss_impl(const TS* y, const float* z, const int64_t* tgt, long N, 
   const size_t smem = align_up((size_t)V * 4, 16) + align_up((size_t)V * sizeof(TS), 16);
   const float inv_temp = 1.0f / temperature, kd_coef = alpha * temperature / (float)N;
   // default: persistent CTAs, TMA double-buffered row prefetch, register-resident math (V % 8 == 0, V <= 16384)
-  if (vec && V <= 8 * KDR_THREADS * 8 && !eval) {
+  const size_t psmem = 2 * ((size_t)V * 4 + (size_t)V * sizeof(TS));     // double-buffered row pair; larger rows take the row-in-smem kernel
+  if (vec && V <= 8 * KDR_THREADS * 8 && !eval && psmem <= 200 * 1024) {
     const int need = cdiv(V / 8, KDR_THREADS);
-    const size_t psmem = 2 * ((size_t)V * 4 + (size_t)V * sizeof(TS));
     int per_sm = (int)((200 * 1024) / (psmem + 1024)); if (per_sm < 1) per_sm = 1;
     const int reg_cap = need <= 3 ? 3 : (need <= 5 ? 2 : 1);      // matches the kernel's __launch_bounds__ min-blocks
     if (per_sm > reg_cap) per_sm = reg_cap;
@@ -910,7 +913,7 @@ static int decoder_forward_entry(const B2CShape* shape, const B2CParams* params,
                                  int dtype, const B2CDropout* dropout, void* stream, bool prepared) {
   B2C_TRY(check_shape(shape)); B2C_TRY(check_device());
   B2C_CHECK_ARG(params && feats && captions && logits && hidden_top && attn_w && workspace, "NULL argument");
-  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0};
+  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0, nullptr};
   B2C_CHECK_ARG(dr.p >= 0.f && dr.p < 1.f, "dropout p=%f outside [0,1)", dr.p);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2C_F32) return decoder_forward_impl<float>(*shape, *params, (const float*)feats, captions, (float*)logits, (float*)hidden_top, attn_w, workspace, ws_bytes, dr, st, prepared);
@@ -940,17 +943,23 @@ int b2c_decoder_prepare(const B2CShape* shape, const B2CParams* params, const in
 int b2c_decoder_backward(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
                          const void* hidden_top, const float* attn_w, const void* dlogits, const void* dhidden_top,
                          const B2CGrads* grads, float* dfeats, void* workspace, size_t ws_bytes,
-                         int dtype, const B2CDropout* dropout, void* stream) {
+                         int dtype, const B2CDropout* dropout, int flags, void* stream) {
   B2C_TRY(check_shape(shape)); B2C_TRY(check_device());
   B2C_CHECK_ARG(params && feats && captions && hidden_top && attn_w && dlogits && grads && workspace, "NULL argument");
-  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0};
+  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0, nullptr};
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == B2C_F32) return decoder_backward_impl<float>(*shape, *params, (const float*)feats, captions, (const float*)hidden_top, attn_w, (const float*)dlogits, (const float*)dhidden_top, *grads, dfeats, workspace, ws_bytes, dr, st);
-  if (dtype == B2C_BF16) return decoder_backward_impl<bf16>(*shape, *params, (const bf16*)feats, captions, (const bf16*)hidden_top, attn_w, (const bf16*)dlogits, (const bf16*)dhidden_top, *grads, dfeats, workspace, ws_bytes, dr, st);
+  if (dtype == B2C_F32) return decoder_backward_impl<float>(*shape, *params, (const float*)feats, captions, (const float*)hidden_top, attn_w, (const float*)dlogits, (const float*)dhidden_top, *grads, dfeats, workspace, ws_bytes, dr, st, flags);
+  if (dtype == B2C_BF16) return decoder_backward_impl<bf16>(*shape, *params, (const bf16*)feats, captions, (const bf16*)hidden_top, attn_w, (const bf16*)dlogits, (const bf16*)dhidden_top, *grads, dfeats, workspace, ws_bytes, dr, st, flags);
   return set_err(B2C_EINVAL, "bad dtype %d", dtype);
 }
 
-int b2c_set_defer_side_join(int on) { defer_side_join() = (on != 0); return 0; }
+int b2c_bump_counter(uint64_t* counter, void* stream) {
+  B2C_TRY(check_device());
+  B2C_CHECK_ARG(counter != nullptr, "NULL counter");
+  bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(counter));
+  B2C_LAUNCH_CHECK("bump_counter_kernel");
+  return 0;
+}
 
 int b2c_join_side_work(void* stream) {
   B2C_TRY(check_device());
@@ -984,7 +993,7 @@ int b2c_refinement_forward(const B2CShape* shape, const B2CRefineParams* params,
                            void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream) {
   B2C_TRY(check_refine_shape(shape)); B2C_TRY(check_device());
   B2C_CHECK_ARG(params && x && out && workspace, "NULL argument");
-  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0};
+  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0, nullptr};
   B2C_CHECK_ARG(dr.p >= 0.f && dr.p < 1.f, "dropout p=%f outside [0,1)", dr.p);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2C_F32) return refinement_forward_impl<float>(*shape, *params, x, (float*)out, workspace, ws_bytes, dr, st);
@@ -996,7 +1005,7 @@ int b2c_refinement_backward(const B2CShape* shape, const B2CRefineParams* params
                             float* dx, void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream) {
   B2C_TRY(check_refine_shape(shape)); B2C_TRY(check_device());
   B2C_CHECK_ARG(params && dout && grads && dx && workspace, "NULL argument");
-  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0};
+  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0, nullptr};
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2C_F32) return refinement_backward_impl<float>(*shape, *params, (const float*)dout, *grads, dx, workspace, ws_bytes, dr, st);
   if (dtype == B2C_BF16) return refinement_backward_impl<bf16>(*shape, *params, (const bf16*)dout, *grads, dx, workspace, ws_bytes, dr, st);
@@ -1007,7 +1016,7 @@ int b2c_projector_forward(const B2CShape* shape, const B2CProjParams* params, co
                           void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream) {
   B2C_TRY(check_proj_shape(shape)); B2C_TRY(check_device());
   B2C_CHECK_ARG(params && x && out && workspace, "NULL argument");
-  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0};
+  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0, nullptr};
   B2C_CHECK_ARG(dr.p >= 0.f && dr.p < 1.f, "dropout p=%f outside [0,1)", dr.p);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2C_F32) return projector_forward_impl<float>(*shape, *params, x, out, workspace, ws_bytes, dr, st);
@@ -1019,7 +1028,7 @@ int b2c_projector_backward(const B2CShape* shape, const B2CProjParams* params, c
                            void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream) {
   B2C_TRY(check_proj_shape(shape)); B2C_TRY(check_device());
   B2C_CHECK_ARG(params && dout && grads && workspace, "NULL argument");
-  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0};
+  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0, nullptr};
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2C_F32) return projector_backward_impl<float>(*shape, *params, dout, *grads, workspace, ws_bytes, dr, st);
   if (dtype == B2C_BF16) return projector_backward_impl<bf16>(*shape, *params, dout, *grads, workspace, ws_bytes, dr, st);
@@ -1071,8 +1080,8 @@ int b2c_aux_loss(const void* feats_s, const float* feats_t, int32_t B, int32_t S
                  float* feat_part, float* hid_part, int dtype, void* stream) {
   B2C_TRY(check_device());
   B2C_CHECK_ARG(B > 0, "B=%d", B);
-  if (feats_s) B2C_CHECK_ARG(feats_t && feat_part && Ss > 0 && St > 0 && E > 0, "feature KD needs feats_t, feat_part and positive Ss/St/E");
-  if (hid_s) B2C_CHECK_ARG(hid_t && hid_part && T > 0 && Th > 0 && Th <= T && H > 0, "hidden KD needs hid_t, hid_part and 0 < Th <= T");
+  if (feats_s) B2C_CHECK_ARG(feats_t && feat_part && Ss > 0 && St > 0 && E > 0 && E % 8 == 0, "feature KD needs feats_t, feat_part, positive Ss/St and E a positive multiple of 8 (E=%d)", E);
+  if (hid_s) B2C_CHECK_ARG(hid_t && hid_part && T > 0 && Th > 0 && Th <= T && H > 0 && H % 8 == 0, "hidden KD needs hid_t, hid_part, 0 < Th <= T and H a positive multiple of 8 (H=%d)", H);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2C_F32) return aux_loss_impl<float>((const float*)feats_s, feats_t, B, Ss, St, E, (const float*)hid_s, hid_t, T, Th, H, beta, gamma, dfeats_s, dfeats_t, (float*)dhid_s, feat_part, hid_part, st);
   if (dtype == B2C_BF16) return aux_loss_impl<bf16>((const bf16*)feats_s, feats_t, B, Ss, St, E, (const bf16*)hid_s, hid_t, T, Th, H, beta, gamma, dfeats_s, dfeats_t, (bf16*)dhid_s, feat_part, hid_part, st);

@@ -86,6 +86,10 @@ __device__ __forceinline__ uint32_t mix32(uint64_t seed, uint32_t stream, uint64
   z = z ^ (z >> 31);
   return (uint32_t)(z >> 32);
 }
+// effective seed: the by-value seed (frozen inside a captured CUDA graph) mixed with an optional device-side step counter
+__device__ __forceinline__ uint64_t drop_seed(uint64_t seed, const unsigned long long* seed_dev) {
+  return seed_dev ? seed + 0xD6E8FEB86659FD93ull * __ldg(seed_dev) : seed;
+}
 // returns 0 (dropped) or 1/(1-p) (kept)
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t stream, uint64_t idx, float p, float inv_keep) {
   const uint32_t thr = (uint32_t)(p * 4294967296.0f);

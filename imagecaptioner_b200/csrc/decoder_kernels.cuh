@@ -441,8 +441,10 @@ lstm_pointwise_bwd_kernel(const T* __restrict__ gates, const float* __restrict__
                           float* __restrict__ dc, int dc_is_zero,
                           const float* __restrict__ dh_carry, long ld_carry, const float* __restrict__ dh_above, long ld_above,
                           const float* __restrict__ dh_ext, const T* __restrict__ dh_hid, const T* __restrict__ dh_q, long ld_q,
-                          T* __restrict__ dgates, int B, int H, float drop_p, uint64_t seed, uint32_t site, long row_base) {
+                          T* __restrict__ dgates, int B, int H, float drop_p, uint64_t seed, uint32_t site, long row_base,
+                          const unsigned long long* __restrict__ seed_dev) {
   pdl_launch_dependents();
+  if (drop_p > 0.f) seed = drop_seed(seed, seed_dev);
   const long total = (long)B * H;
   const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   struct Saved { float gt[4]; float tc, cp, dh_fixed, mask; };
@@ -481,7 +483,9 @@ lstm_pointwise_bwd_kernel(const T* __restrict__ gates, const float* __restrict__
 // ======================================================================================
 // output_projection dropout (training only): o1 *= keep-mask/(1-p)
 template <typename T>
-__global__ void __launch_bounds__(256) dropout_inplace_kernel(T* __restrict__ x, long n, float p, uint64_t seed, uint32_t site) {
+__global__ void __launch_bounds__(256) dropout_inplace_kernel(T* __restrict__ x, long n, float p, uint64_t seed, uint32_t site,
+                                                              const unsigned long long* __restrict__ seed_dev) {
+  seed = drop_seed(seed, seed_dev);
   const float inv_keep = 1.0f / (1.0f - p);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     x[i] = from_f<T>(to_f<T>(x[i]) * dropout_scale(seed, site, (uint64_t)i, p, inv_keep));
@@ -572,6 +576,7 @@ argmax_parts_feedback_kernel(const float* __restrict__ pmax, const int* __restri
     if (besti == end_id && !done[b]) { done[b] = 1; lengths[b] = t; }
   }
 }
+__global__ void bump_counter_kernel(unsigned long long* c) { *c += 1ull; }
 __global__ void fill_i64_kernel(int64_t* p, long n, int64_t v) { for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = v; }
 __global__ void finish_lengths_kernel(int32_t* lengths, int B, int T) { const int b = blockIdx.x * blockDim.x + threadIdx.x; if (b < B && lengths[b] < 0) lengths[b] = T; }
 

@@ -34,6 +34,7 @@ struct LstmEpi {
   void* gates_out;             // (rows, 4H) post-activation gates, interleaved (null in decode)
   void* h_rec; long ld_rec; void* h_next; long ld_next; void* h_top; long ld_top;
   float drop_p; unsigned long long seed; unsigned int site; long row_base;
+  const unsigned long long* seed_dev;   // optional device step counter mixed into the seed (CUDA-graph replays)
 };
 
 // Greedy decoding needs argmax_n C[m, n] only: the vocabulary-head GEMM can reduce every accumulator tile to per-row partial
@@ -119,6 +120,7 @@ gemm_simt_kernel(int M, int N, int K, float alpha, const TA* __restrict__ A, lon
     const int gn = n0 + tx * 4, unit = gn >> 2, H = le.H;
     if (gn >= N) return;
     const float inv_keep = le.drop_p > 0.f ? 1.0f / (1.0f - le.drop_p) : 1.0f;
+    const uint64_t dseed = le.drop_p > 0.f ? drop_seed(le.seed, le.seed_dev) : 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int gm = m0 + ty * 4 + i;
@@ -138,7 +140,7 @@ gemm_simt_kernel(int M, int N, int K, float alpha, const TA* __restrict__ A, lon
       }
       if (le.h_rec) reinterpret_cast<TA*>(le.h_rec)[(long)gm * le.ld_rec + unit] = from_f<TA>(h);
       if (le.h_next) {
-        const float m = le.drop_p > 0.f ? dropout_scale(le.seed, le.site, (uint64_t)((le.row_base + gm) * H + unit), le.drop_p, inv_keep) : 1.0f;
+        const float m = le.drop_p > 0.f ? dropout_scale(dseed, le.site, (uint64_t)((le.row_base + gm) * H + unit), le.drop_p, inv_keep) : 1.0f;
         reinterpret_cast<TA*>(le.h_next)[(long)gm * le.ld_next + unit] = from_f<TA>(h * m);
       }
       if (le.h_top) reinterpret_cast<TA*>(le.h_top)[(long)gm * le.ld_top + unit] = from_f<TA>(h);
@@ -399,6 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int H = le.H, N4 = N;                        // N == 4H
       const int grow = m0 + q * 32 + lane;
       const float inv_keep = le.drop_p > 0.f ? 1.0f / (1.0f - le.drop_p) : 1.0f;
+      const uint64_t dseed = le.drop_p > 0.f ? drop_seed(le.seed, le.seed_dev) : 0;
       constexpr int NC32 = BN / 32, C32_PER = (NC32 + 1) / 2;
 #pragma unroll 1
       for (int ci = half * C32_PER; ci < (half + 1) * C32_PER && ci < NC32; ++ci) {
@@ -451,7 +454,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (le.drop_p > 0.f) {
               float hm[8];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) hm[u] = hn[u] * dropout_scale(le.seed, le.site, (uint64_t)((le.row_base + grow) * H + u0 + u), le.drop_p, inv_keep);
+              for (int u = 0; u < 8; ++u) hm[u] = hn[u] * dropout_scale(dseed, le.site, (uint64_t)((le.row_base + grow) * H + u0 + u), le.drop_p, inv_keep);
               hd = make_uint4(pack_bf16(hm[0], hm[1]), pack_bf16(hm[2], hm[3]), pack_bf16(hm[4], hm[5]), pack_bf16(hm[6], hm[7]));
             }
             *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(le.h_next) + (long)grow * le.ld_next + u0) = hd;

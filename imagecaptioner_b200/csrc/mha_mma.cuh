@@ -112,8 +112,9 @@ __device__ __forceinline__ void mm_store_rows(const float (&acc)[8][4], bf16* ds
 // both sides use 16-byte accesses; the FFMA kernels keep (B, heads, S, S)).  grid (B, heads), 128 threads.
 __global__ void __launch_bounds__(MM_THREADS)
 mha_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, bf16* __restrict__ probs, int S, int E, int heads, float scale,
-                   float drop_p, uint64_t seed, uint32_t drop_site) {
+                   float drop_p, uint64_t seed, uint32_t drop_site, const unsigned long long* __restrict__ seed_dev) {
   __shared__ __align__(16) bf16 Qs[MM_TILE], Ks[MM_TILE], Vs[MM_TILE];
+  if (drop_p > 0.f) seed = drop_seed(seed, seed_dev);
   const int b = blockIdx.x, h = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bf16* base = qkv + (long)b * S * 3 * E + h * MM_R;
   {
@@ -193,8 +194,9 @@ mha_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, bf16* _
 //   dV = Pd^T dO;  dPd = dO V^T;  dP = dPd * mask;  dS = P (dP - rowsum(dP P)) scale;  dQ = dS K;  dK = dS^T Q
 __global__ void __launch_bounds__(MM_THREADS)
 mha_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ probs, const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
-                   int S, int E, int heads, float scale, float drop_p, uint64_t seed, uint32_t drop_site) {
+                   int S, int E, int heads, float scale, float drop_p, uint64_t seed, uint32_t drop_site, const unsigned long long* __restrict__ seed_dev) {
   extern __shared__ __align__(16) unsigned char mm_smem[];
+  if (drop_p > 0.f) seed = drop_seed(seed, seed_dev);
   bf16* Qs = reinterpret_cast<bf16*>(mm_smem);
   bf16* Ks = Qs + MM_TILE; bf16* Vs = Ks + MM_TILE; bf16* dOs = Vs + MM_TILE; bf16* Ps = dOs + MM_TILE; bf16* dSs = Ps + MM_TILE;
   bf16* Pds = drop_p > 0.f ? dSs + MM_TILE : Ps;

@@ -369,8 +369,9 @@ __device__ __forceinline__ void mha_load_heads(const T* qkv, int b, int h, int S
 template <typename T>
 __global__ void __launch_bounds__(MHA_THREADS)
 mha_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, T* __restrict__ probs, int S, int E, int heads, float scale,
-               float drop_p, uint64_t seed) {
+               float drop_p, uint64_t seed, const unsigned long long* __restrict__ seed_dev) {
   extern __shared__ __align__(16) float mh_sm[];
+  if (drop_p > 0.f) seed = drop_seed(seed, seed_dev);
   const int hd = E / heads, ph = mha_pitch(hd), ps = mha_pitch(S);
   float* Qs = mh_sm; float* Ks = Qs + S * ph; float* Vs = Ks + S * ph; float* sc = Vs + S * ph;    // sc: S x ps
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -401,8 +402,9 @@ mha_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, T* __restrict__ p
 template <typename T>
 __global__ void __launch_bounds__(MHA_THREADS)
 mha_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ probs, const T* __restrict__ dout, T* __restrict__ dqkv,
-               int S, int E, int heads, float scale, float drop_p, uint64_t seed) {
+               int S, int E, int heads, float scale, float drop_p, uint64_t seed, const unsigned long long* __restrict__ seed_dev) {
   extern __shared__ __align__(16) float mh_sm[];
+  if (drop_p > 0.f) seed = drop_seed(seed, seed_dev);
   const int hd = E / heads, ph = mha_pitch(hd), ps = mha_pitch(S);
   float* Qs = mh_sm; float* Ks = Qs + S * ph; float* Vs = Ks + S * ph; float* dOs = Vs + S * ph;
   float* Ps = dOs + S * ph; float* dS = Ps + S * ps; float* Pd = drop_p > 0.f ? dS + S * ps : Ps;     // S x ps each; Pd aliases Ps without dropout

@@ -4,7 +4,8 @@ Same public names, constructor arguments, dict keys and error behaviour as
 ``/root/reference/src/distillation_utils.py``; ``DistillationLoss.forward`` is two fused sm_100a
 kernels (the streaming token KD + CE pass producing loss and dlogits, and the feature/hidden KD
 reduction) plus a fixed-order finalize, instead of ~40 eager launches and 5 host syncs.
-``FeatureProjector`` keeps the reference's stock modules (SURVEY.md §8f lists it as a later row);
+``FeatureProjector`` keeps its parameters in the reference's stock submodules and computes through
+``b2c_projector_forward`` / ``_backward`` (SURVEY.md §8f row 2);
 ``TeacherWrapper`` / ``create_feature_projectors`` / ``validate_distillation_setup`` /
 ``compute_bleu_score`` / ``log_training_progress`` are host-side glue with the reference's behaviour.
 """
@@ -171,7 +172,8 @@ class FeatureProjector(nn.Module):
         dt = torch.bfloat16 if torch.is_autocast_enabled() else getattr(self, "compute_dtype", torch.float32)
         named = dict(self.named_parameters())
         params = [named[k] for k in _ops.PROJ_PARAM_ORDER] if self.teacher_dim != self.student_dim else []
-        return _ops.ProjectorFunction.apply(features, dt, p, seed, self.student_seq_len, self.student_dim, *params)
+        return _ops.ProjectorFunction.apply(features, dt, p, seed, self.student_seq_len, self.student_dim,
+                                            getattr(self, "b2c_options", None), *params)
 
 
 class TeacherWrapper(nn.Module):

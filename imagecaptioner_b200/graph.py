@@ -51,6 +51,8 @@ class GraphedKDStep:
         self.graph_opt = None      # clip + AdamW, a second graph when a gradient all-reduce sits in between
         self.world = reducer.world_size
         self._side = torch.cuda.Stream()
+        self._aux = torch.cuda.Stream()
+        self._aux_used = False
         self._overlap = False
         self._capturing = False
         self.high_priority_chain = os.environ.get("B2C_CHAIN_PRIORITY", "1") != "0"
@@ -59,8 +61,12 @@ class GraphedKDStep:
         # write it directly into the flat all-reduce buffer (saves ~35 accumulate kernels + the buffer zeroing per step)
         self.direct_grads = direct_grads
         loss_module.assume_unit_grad = True      # _fwd_bwd calls loss.backward() with the implicit grad_output of exactly 1
-        if direct_grads:
-            _ops.set_grad_destinations(reducer.grad_views())
+        # Per-model call options (nothing process-global): gradient destinations, deferred weight-gradient join, the event hook
+        # behind the decoder backward, and the device-side dropout step counter.  They are attached to the modules only for the
+        # duration of this object's own forward/backward (see _fwd_bwd), so an eager loop on the same model is unaffected.
+        dev = self.static["targets"].device
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._opts = _ops.CallOptions(grad_dest=reducer.grad_views() if direct_grads else None, seed_dev=self.step_counter)
         # Data parallel: NCCL stays OUTSIDE the graphs (graph 1 = forward + loss + backward, graph 2 = clip + AdamW); the two
         # exchanges (non-PAD count, flat gradient buffer) are issued eagerly around / alongside graph 1, see overlap_comm below.
         # B2C_FAKE_DP=1: exercise the multi-rank control flow (two graphs, overlapped exchanges) on ONE GPU with an identity in
@@ -105,11 +111,61 @@ class GraphedKDStep:
             self._all_reduce(self.nval)
             self.loss_module.n_valid_global = self.nval
 
+    def _modules(self):
+        mods = [self.model.decoder, self.projector]
+        if getattr(self.model, "use_attention_refinement", False):
+            mods.append(self.model.attention_refinement)
+        return mods
+
+    def _attach_options(self):
+        o = self._opts
+        # Single rank: the weight-gradient branch of b2c_decoder_backward (side stream) is joined AFTER the whole backward, so the
+        # refinement backward overlaps it instead of waiting 0.26 ms for it (the parameters' gradients are first read by the
+        # optimizer).  Multi-rank with the overlapped exchange: the communication stream needs the decoder's gradients right behind
+        # the call, so the hook below joins the side branch on the MAIN stream only when it has to record the event there.
+        early = self._capturing and self.overlap_comm and self._early is not None
+        o.defer_join = self.defer_weight_grad_join and self.direct_grads and (not self._multi or early)
+        o.after_backward = self._after_decoder_backward if early else None
+        for m in self._modules():
+            m.b2c_options = o
+
+    def _after_decoder_backward(self):
+        """Runs right behind b2c_decoder_backward (autograd thread, capture stream).  The communication stream may start the
+        all-reduce of the decoder's gradient segment once BOTH the main chain up to here and the library's weight-gradient side
+        branch are done; the main chain itself does not wait for that branch (the refinement backward follows immediately), so the
+        event is recorded on an auxiliary captured stream that joins the two."""
+        main = torch.cuda.current_stream()
+        if self._opts.join_pending:
+            self._opts.join_pending = False
+            self._aux.wait_stream(main)
+            with torch.cuda.stream(self._aux):
+                _ops.join_side_work()
+                self._ev_dec.record()
+            self._aux_used = True
+        else:
+            self._ev_dec.record()
+
+    def _detach_options(self):
+        for m in self._modules():
+            m.b2c_options = None
+
+    def release(self):
+        """Drop the graphs and every hook this object attached (the model can then be trained eagerly, e.g. with gradient
+        accumulation, without its gradients being redirected into the flat buffer)."""
+        self._detach_options()
+        self.graph = self.graph_opt = None
+
+    def _dropout_active(self):
+        return any(m.training for m in self._modules())
+
     def _fwd_bwd(self):
         inp = self.static
         feats = inp["encoder_features"]
         if feats.grad is not None:
             feats.grad = None
+        self._attach_options()
+        if self._dropout_active():
+            _ops.bump_counter(self.step_counter)     # a fresh dropout mask per step, also when the step is a graph replay
         ctx = torch.autocast("cuda", dtype=self.autocast_dtype) if self.autocast_dtype is not None else torch.autocast("cuda", enabled=False)
         # The projector does not depend on the student: it runs on a side stream underneath the decoder's latency-bound
         # recurrence (fork / join are recorded as parallel branches by the graph capture).
@@ -136,22 +192,16 @@ class GraphedKDStep:
             self.reducer.detach_grads()          # backward kernels write every parameter gradient straight into the flat buffer
         else:
             self.reducer.zero_grad()
-        if self._capturing and self.overlap_comm and self._early is not None:
-            _ops.after_decoder_backward = self._ev_dec.record            # event-record node right behind b2c_decoder_backward
-        # Single rank: the weight-gradient branch of b2c_decoder_backward (side stream) is joined AFTER the whole backward, so the
-        # refinement backward overlaps it instead of waiting 0.26 ms for it (the parameters' gradients are first read by the
-        # optimizer).  Multi-rank keeps the join inside the call: the early all-reduce reads the decoder's gradients right after it.
-        defer = self.defer_weight_grad_join and not self._multi
-        lib = _ops.load_library()
-        if defer:
-            lib.b2c_set_defer_side_join(1)
         try:
             loss.backward()
         finally:
-            _ops.after_decoder_backward = None
-            if defer:
-                lib.b2c_set_defer_side_join(0)
-                _ops._check(lib.b2c_join_side_work(_ops._stream()), "b2c_join_side_work")
+            self._detach_options()
+            if self._opts.join_pending:          # the decoder backward deferred its weight-gradient join (B2C_BWD_DEFER_JOIN)
+                self._opts.join_pending = False
+                _ops.join_side_work()
+            if self._aux_used:                   # the auxiliary branch that carries the event record rejoins the capture stream
+                self._aux_used = False
+                torch.cuda.current_stream().wait_stream(self._aux)
         if self.direct_grads:
             self.reducer.attach_views()          # the flat buffer is authoritative (the kernels wrote into it), whatever autograd kept
         return out5

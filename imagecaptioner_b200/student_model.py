@@ -6,8 +6,9 @@ reference (``/root/reference/src/student_model.py``), so ``train_student_kd.py``
 What differs is the body of the hot path: ``LSTMDecoder.forward`` (reference :205-256) and the
 greedy loop of ``CaptioningStudent.caption_image`` (reference :314-381) are single calls into the
 hand-written sm_100a kernels behind ``include/b2c.h``.  The ResNet encoder and the (once per
-sequence) ``AttentionRefinement`` block stay stock ``torch.nn`` modules — SURVEY.md §8 keeps the
-encoder out of the path and lists the refinement block as the next row.
+sequence) ``AttentionRefinement`` block keeps its parameters in the reference's stock submodules (same
+``state_dict`` keys) but computes through ``b2c_refinement_forward`` / ``_backward`` (SURVEY.md §8f row 1);
+only the ResNet encoder stays a stock ``torch.nn`` module — SURVEY.md §8 keeps it out of the path.
 
 Precision mode of the decoder: bf16 (tcgen05 tensor-core tiles) when called under
 ``torch.autocast`` — the reference trains under fp16 autocast, ``train_student_kd.py:271`` — or when
@@ -91,7 +92,8 @@ class AttentionRefinement(nn.Module):
         seed = (torch.initial_seed() + 0xD1B54A32D192ED03 * self._step) & 0xFFFFFFFFFFFFFFFF if p > 0 else 0
         dt = torch.bfloat16 if torch.is_autocast_enabled() else getattr(self, "compute_dtype", torch.float32)
         named = dict(self.named_parameters())
-        return _ops.RefinementFunction.apply(features, dt, p, seed, self.num_heads, *[named[k] for k in _ops.REFINE_PARAM_ORDER])
+        return _ops.RefinementFunction.apply(features, dt, p, seed, self.num_heads, getattr(self, "b2c_options", None),
+                                             *[named[k] for k in _ops.REFINE_PARAM_ORDER])
 
 
 class HiddenStateList(list):
@@ -164,7 +166,7 @@ class LSTMDecoder(nn.Module):
         self._step += 1
         seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * self._step) & 0xFFFFFFFFFFFFFFFF if p > 0 else 0
         logits, hid, attw = _ops.DecoderFunction.apply(image_features, captions, self._mode(), p, seed, self.num_layers, prepared,
-                                                       *self._param_list())
+                                                       getattr(self, "b2c_options", None), *self._param_list())
         hidden_states = HiddenStateList(hid.unbind(0))
         hidden_states.stacked = hid
         return logits, hidden_states, list(attw.unbind(0))

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define B2C_ABI_VERSION 1
+#define B2C_ABI_VERSION 2
 #define B2C_MAX_LAYERS 4
 
 enum { B2C_OK = 0, B2C_EINVAL = -1, B2C_EARCH = -2, B2C_ECUDA = -3, B2C_ENOMEM = -4 };
@@ -79,8 +79,13 @@ typedef struct B2CGrads {
 
 /* Dropout of the reference's training mode (decoder p in output_projection and between LSTM layers,
  * src/student_model.py:142-156).  p == 0 disables it (eval mode / parity runs).  The keep mask is a
- * counter-based hash of (seed, site, element index): backward regenerates it, nothing is stored. */
-typedef struct B2CDropout { float p; uint64_t seed; } B2CDropout;
+ * counter-based hash of (seed, site, element index): backward regenerates it, nothing is stored.
+ * seed_dev (may be NULL): a device counter that is mixed into the seed by the kernels at run time, so a captured CUDA graph
+ * (whose kernel arguments, `seed` included, are frozen at capture) draws a fresh mask on every replay: the caller bumps the
+ * counter once per step, before the forward (b2c_bump_counter), and passes the same pointer to forward and backward. */
+typedef struct B2CDropout { float p; uint64_t seed; const uint64_t* seed_dev; } B2CDropout;
+/* *counter += 1 (device, on `stream`): the per-step dropout counter of B2CDropout.seed_dev. */
+int b2c_bump_counter(uint64_t* counter, void* stream);
 
 int b2c_abi_version(void);
 const char* b2c_last_error(void);
@@ -115,16 +120,15 @@ int b2c_decoder_forward_prepared(const B2CShape* shape, const B2CParams* params,
 int b2c_decoder_backward(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
                          const void* hidden_top, const float* attn_w, const void* dlogits, const void* dhidden_top,
                          const B2CGrads* grads, float* dfeats, void* workspace, size_t ws_bytes,
-                         int dtype, const B2CDropout* dropout, void* stream);
+                         int dtype, const B2CDropout* dropout, int flags, void* stream);
 
-/* b2c_decoder_backward contracts every weight gradient on an internal side stream next to the chain that produces dfeats, and by
- * default makes `stream` wait for that branch before it returns ("all work is enqueued on stream").  A caller that does not read
- * parameter gradients until later (an optimizer step after the rest of the backward) may defer the wait so that whatever it
- * enqueues next (the refinement backward) overlaps the weight-gradient contractions:
- *   b2c_set_defer_side_join(1);  b2c_decoder_backward(...);  ... more work on stream ...;  b2c_join_side_work(stream);
- * The flag is process-wide (autograd engines call the backward from worker threads).  With the flag set, parameter gradients are
- * defined only after b2c_join_side_work. */
-int b2c_set_defer_side_join(int on);
+/* b2c_decoder_backward contracts every weight gradient on an internal (per-device) side stream next to the chain that produces
+ * dfeats, and by default makes `stream` wait for that branch before it returns ("all work is enqueued on stream").  A caller that
+ * does not read parameter gradients until later (an optimizer step after the rest of the backward) passes
+ * flags = B2C_BWD_DEFER_JOIN so that whatever it enqueues next (the refinement backward) overlaps the weight-gradient
+ * contractions, and calls b2c_join_side_work(stream) before the gradients are read.  The choice is per call: there is no
+ * process-wide state besides the per-device stream / event set. */
+#define B2C_BWD_DEFER_JOIN 1
 int b2c_join_side_work(void* stream);
 
 /* Batched greedy decode: every sample starts at start_id and steps shape->T (= max_len) times with its own

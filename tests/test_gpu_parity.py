@@ -125,10 +125,35 @@ def test_training_mode_dropout_is_consistent():
     feats = torch.randn(B, 49, E, device=DEV)
     cap = torch.randint(1, V, (T, B), device=DEV)
 
+    counter = torch.zeros(1, dtype=torch.int64, device=DEV)
+    opts = _ops.CallOptions(seed_dev=counter)
+
     def fwd(f, seed=123):
-        return _ops.DecoderFunction.apply(f, cap, torch.float32, 0.3, seed, L, None, *plist)
+        return _ops.DecoderFunction.apply(f, cap, torch.float32, 0.3, seed, L, None, opts, *plist)
     y1, h1, _ = fwd(feats); y2, _, _ = fwd(feats); y3, _, _ = fwd(feats, seed=124)
     assert torch.equal(y1, y2) and not torch.equal(y1, y3)
+    # the device-side step counter (B2CDropout.seed_dev) changes the mask without touching the by-value seed: a CUDA graph, whose
+    # kernel arguments are frozen at capture, draws a fresh mask on every replay once the counter is bumped inside the graph
+    _ops.bump_counter(counter)
+    y4, _, _ = fwd(feats)
+    assert int(counter.item()) == 1 and not torch.equal(y1, y4)
+    counter.zero_()
+    assert torch.equal(fwd(feats)[0], y1)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fwd(feats)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.no_grad(), torch.cuda.graph(graph):
+        _ops.bump_counter(counter)
+        yg = fwd(feats)[0]
+    graph.replay(); torch.cuda.synchronize(); r1 = yg.clone()
+    graph.replay(); torch.cuda.synchronize(); r2 = yg.clone()
+    assert int(counter.item()) == 2 and not torch.equal(r1, r2)          # two replays, two different masks
+    assert torch.equal(r1, y4)                                           # replay 1 saw counter == 1, like the eager call above
+    counter.zero_()
     f = feats.clone().requires_grad_(True)
     y, _, _ = fwd(f)
     w = torch.randn_like(y)
