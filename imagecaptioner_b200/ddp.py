@@ -26,7 +26,7 @@ class FlatGradAllReducer:
     accumulates straight into the buffer and the collective is a single call with no packing copies."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
-                 offsets: Optional[List[int]] = None, numel: Optional[int] = None):
+                 offsets: Optional[List[int]] = None, numel: Optional[int] = None, single_process: bool = False):
         """``offsets`` / ``numel``: optional explicit layout (element offset of every trainable parameter, total length), used
         by optim.FlatAdamW to keep the gradient buffer congruent with its parameter and moment buffers."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
@@ -34,7 +34,8 @@ class FlatGradAllReducer:
             raise ValueError("no trainable parameters")
         dev = self.params[0].device
         self.group = group
-        self.world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        # single_process: no exchange even when torch.distributed is initialised (a one-GPU reference run inside a multi-rank job)
+        self.world_size = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized() and not single_process) else 1
         if offsets is None:
             offsets, off = [], 0
             for p in self.params:

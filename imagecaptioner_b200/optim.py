@@ -26,14 +26,24 @@ from . import _ops
 from .ddp import FlatGradAllReducer
 
 
-def reference_param_groups(student_model, projectors, learning_rate: float):
-    """The reference's three LR groups and two clip groups (train_student_kd.py:219-234, :293-297) as FlatAdamW groups."""
+def reference_param_groups(student_model, projectors, learning_rate: float, active=("encoder",)):
+    """The reference's three LR groups and two clip groups (train_student_kd.py:219-234, :293-297) as FlatAdamW groups.
+
+    `active`: keys of the `projectors` dict whose parameters take part in the step.  The reference hands every projector to
+    AdamW (:227-228), but only projectors['encoder'] is ever called in its loop (:281), so the 'hidden' projector's gradients
+    stay None and torch.optim.AdamW skips it entirely (no moment update, no weight decay).  A flat-buffer optimizer cannot see
+    "grad is None" -- an untouched gradient slot reads as zeros and would still be decayed -- so parameters that never receive
+    a gradient are left out of the flat buffers here, which gives the same result."""
     other = []
     if getattr(student_model, "use_attention_refinement", False):
         other += list(student_model.attention_refinement.parameters())
     proj = []
-    for pr in (projectors.values() if isinstance(projectors, dict) else [projectors]):
-        proj += list(pr.parameters())
+    if isinstance(projectors, dict):
+        for key, pr in projectors.items():
+            if active is None or key in active:
+                proj += list(pr.parameters())
+    else:
+        proj += list(projectors.parameters())
     return [
         {"params": list(student_model.encoder.parameters()), "lr": learning_rate * 0.1, "clip_group": 0},
         {"params": list(student_model.decoder.parameters()), "lr": learning_rate, "clip_group": 0},
@@ -52,7 +62,7 @@ class FlatAdamW:
 
     def __init__(self, param_groups, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
                  max_grad_norm: Optional[float] = 1.0, loss_scale: Optional[float] = None, growth_factor: float = 2.0,
-                 backoff_factor: float = 0.5, growth_interval: int = 2000, process_group=None):
+                 backoff_factor: float = 0.5, growth_interval: int = 2000, process_group=None, single_process: bool = False):
         if not isinstance(param_groups, (list, tuple)) or (param_groups and not isinstance(param_groups[0], dict)):
             param_groups = [{"params": list(param_groups)}]
         groups = []
@@ -100,7 +110,7 @@ class FlatAdamW:
                 p.data = view
         self.exp_avg = torch.zeros_like(self.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
-        self.reducer = FlatGradAllReducer(self.params, group=process_group, offsets=self.offsets, numel=off)
+        self.reducer = FlatGradAllReducer(self.params, group=process_group, offsets=self.offsets, numel=off, single_process=single_process)
         # grad_scale: the data-parallel average (1/world after the SUM all-reduce) is folded into the update kernel when the
         # caller asks for it (GraphedKDStep does); FlatGradAllReducer.finish() then must not be called.
         self.hyper = _ops.B2COptHyper(betas[0], betas[1], eps, float(max_grad_norm) if max_grad_norm else 0.0, 1.0,

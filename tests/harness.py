@@ -88,3 +88,56 @@ def compare_step(got, ref, tol, verbose=True, metric="max", loosen=None):
             print(f"   {name:55s} {e:.3e}{'   <-- FAIL' if not e < lim(name) else ''}")
     assert not bad, f"{len(bad)} quantities exceed rel tol {tol}: {bad[:4]}"
     return worst
+
+
+def to_device(d, device, dtype=None):
+    """dict of tensors (or None) -> same dict on `device` (floating tensors optionally cast)."""
+    out = {}
+    for k, v in d.items():
+        if v is None or not torch.is_tensor(v):
+            out[k] = v
+        else:
+            out[k] = v.to(device=device, dtype=dtype) if (dtype is not None and v.is_floating_point()) else v.to(device)
+    return out
+
+
+def step_errors(got, ref, metric="l2"):
+    """name -> relative error of every output / gradient / loss component of a KD step (same names as compare_step)."""
+    err = relerr if metric == "max" else relerr_l2
+    cpu = lambda t: t.detach().float().cpu() if torch.is_tensor(t) else t
+    rows = {}
+    for k in ("logits", "hidden_states", "attention_weights", "teacher_projected", "d_encoder_features"):
+        rows[k] = err(cpu(got[k]), cpu(ref[k]))
+    for k, v in ref["grads"].items():
+        rows["grad:" + k] = err(cpu(got["grads"][k]), cpu(v))
+    for k, v in ref["proj_grads"].items():
+        rows["pgrad:" + k] = err(cpu(got["proj_grads"][k]), cpu(v))
+    for k, v in ref["loss"].items():
+        rows["loss:" + k] = abs(got["loss"][k] - v) / (abs(v) + 1e-30) if v != 0 else abs(got["loss"][k])
+    return rows
+
+
+def autocast_reference_errors(params, proj_params, meta, batch, ref, device, autocast_dtype=torch.bfloat16, metric="l2", use_refinement=True):
+    """What reduced-precision autocast does to the REFERENCE's own arithmetic: the stock torch.nn composition of the reference
+    (oracle/eager_torch.py) run on the GPU under torch.autocast(dtype), per-tensor error against `ref` (an fp32 / fp64 result).
+    This is the yardstick for the bf16 mode of the native kernels: kernel error <= max(2e-2, 1.2 x this)."""
+    from oracle import eager_torch as ET
+    Et = batch["teacher_features"].shape[-1]
+    model, proj = ET.build(params, proj_params, meta["V"], meta["E"], meta["H"], meta["L"], use_refinement, Et, batch["encoder_features"].shape[1], device)
+    got = ET.kd_step(model, proj, batch, autocast_dtype, meta.get("alpha", 0.7), meta.get("beta", 0.2), meta.get("gamma", 0.1), meta.get("temperature", 4.0))
+    return step_errors(got, ref, metric)
+
+
+def compare_step_calibrated(got, ref, ref_err, base_tol=2e-2, factor=1.2, metric="l2", verbose=True):
+    """Every quantity within max(base_tol, factor x the autocast reference's own error on the same inputs)."""
+    rows = step_errors(got, ref, metric)
+    bad = []
+    for name, e in rows.items():
+        lim = max(base_tol, factor * ref_err.get(name, 0.0))
+        flag = not e < lim
+        if flag:
+            bad.append((name, e, lim))
+        if verbose or flag:
+            print(f"   {name:55s} kernel {e:.3e}   autocast reference {ref_err.get(name, float('nan')):.3e}   limit {lim:.3e}{'   <-- FAIL' if flag else ''}")
+    assert not bad, f"{len(bad)} quantities exceed max({base_tol}, {factor} x autocast-reference error): {bad[:4]}"
+    return rows

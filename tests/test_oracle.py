@@ -149,3 +149,27 @@ def test_validation_oracle_matches_reference_fixture():
     ev = O.eval_step(case["params"], case["proj_params"], case["batch"])
     assert torch.equal(ev["predicted_tokens"], fx["kd_small_default"]["predicted_tokens"])
     assert torch.allclose(ev["bleu"], fx["kd_small_default"]["bleu"], atol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["default", "identity_projection_3_layers_no_hiddens"])
+def test_stock_module_restatement_matches_oracle(case):
+    """oracle/eager_torch.py (the reference's composition of stock torch.nn modules: nn.LSTM stepped per token, nn.MultiheadAttention,
+    F.kl_div, ...) against the plain-arithmetic oracle that is pinned on the real reference: every output, loss part and gradient.
+    It is the GPU-side baseline of bench.py and the yardstick of the bf16 tolerance (tests/harness.py:autocast_reference_errors)."""
+    from oracle import eager_torch as ET
+    from tests.harness import step_errors
+    if case == "default":
+        V, E, H, L, B, T, Et, refine, hid = 120, 32, 64, 2, 6, 5, 24, True, True
+    else:
+        V, E, H, L, B, T, Et, refine, hid = 60, 32, 48, 3, 4, 3, 32, False, False
+    params = O.init_student_params(V, E, H, L, refine, seed=3)
+    pparams = O.init_projector_params(Et, E, seed=4)
+    batch = O.synthetic_batch(B, T, V, E, H, Et=Et, seed=5, teacher_hiddens=hid)
+    ref = O.kd_step(params, pparams, batch, use_refinement=refine)
+    model, proj = ET.build(params, pparams, V, E, H, L, refine, Et)
+    got = ET.kd_step(model, proj, batch)
+    errs = step_errors(got, ref, metric="max")
+    assert max(errs.values()) < 2e-5, sorted(errs.items(), key=lambda kv: -kv[1])[:3]
+    # the autocast form runs on the CPU too (bf16): a finite, small but non-zero deviation
+    errs16 = step_errors(ET.kd_step(model, proj, batch, torch.bfloat16), ref, metric="l2")
+    assert 1e-4 < max(errs16.values()) < 0.5
