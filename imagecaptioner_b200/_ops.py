@@ -94,6 +94,7 @@ SYMBOLS = {
     "b2c_decoder_forward_prepared": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_decoder_backward": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _GRD, _vp, _vp, _sz, ctypes.c_int, _DRP, ctypes.c_int, _vp]),
     "b2c_bump_counter": (ctypes.c_int, [_vp, _vp]),
+    "b2c_debug_recur_trace": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     "b2c_join_side_work": (ctypes.c_int, [_vp]),
     "b2c_greedy_decode": (ctypes.c_int, [_SHP, _PRM, _vp, _i64, _i64, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_attention_step": (ctypes.c_int, [_SHP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),

@@ -4,6 +4,7 @@
 #include "gemm.cuh"
 #include "loss_kernels.cuh"
 #include "decoder_kernels.cuh"
+#include "recurrent.cuh"
 #include "refine_kernels.cuh"
 #include "mha_mma.cuh"
 #include "optim_kernels.cuh"
@@ -105,6 +106,8 @@ template <typename T> struct TrainWs {
   float *P, *u; T *emb, *G0, *o1; T* xh[MAXL]; T* gates[MAXL]; float* c[MAXL];
   T* dgates[MAXL]; float* dxh0; float* dxh[MAXL]; float* dc[MAXL]; T* do1; float* dHext; float* ds; T* du; T* dq; T* dP; float* demb; float* partial;
   float *dWx32, *dWe32; T *dWxT, *dWeT; float* partial_side;
+  unsigned int* sync;                 // grid-barrier arrival counters of the persistent recurrence kernels (recurrent.cuh)
+  float* EP;                          // e^{2P} (B, S, E) fp32: the attention phase of the persistent forward kernel streams it instead of P
   size_t bytes;
   void carve(void* base, const B2CShape& s) {
     Carver c{reinterpret_cast<unsigned char*>(base), 0};
@@ -127,6 +130,8 @@ template <typename T> struct TrainWs {
     dWx32 = c.take<float>(4 * H * E); dWe32 = c.take<float>(4 * H * E); dWxT = c.take<T>(4 * H * E); dWeT = c.take<T>(4 * H * E);
     size_t mc = (size_t)s.V; if ((size_t)4 * H > mc) mc = 4 * H; if (E > mc) mc = E;
     partial = c.take<float>((size_t)COLSUM_RS * mc); partial_side = c.take<float>((size_t)COLSUM_RS * mc);
+    sync = c.take<unsigned int>(128 + 160 * 32);         // four arrival-counter lines + one 128-byte flag line per CTA
+    EP = c.take<float>(B * S * E);
     bytes = align_up(c.off, 256);
   }
 };
@@ -283,6 +288,56 @@ int join_subs(SubPlan& sp) {
   return 0;
 }
 
+// ------------------------------------------------------------------ persistent forward recurrence (recurrent.cuh)
+// Debug aid (B2C_RECUR_TRACE=1): per CTA, per step, 8 clock64() stamps of the epilogue group, read back with b2c_debug_recur_trace.
+struct RecurTrace { unsigned long long* dev; size_t n; int grid, T; };
+inline RecurTrace& recur_trace_state() { static RecurTrace t{nullptr, 0, 0, 0}; return t; }
+inline unsigned long long* recur_trace_buffer(size_t n) {
+  static const bool on = getenv("B2C_RECUR_TRACE") != nullptr;
+  if (!on) return nullptr;
+  RecurTrace& t = recur_trace_state();
+  if (t.n < n) { if (t.dev) cudaFree(t.dev); t.dev = nullptr; if (cudaMalloc(&t.dev, n * 8) != cudaSuccess) { t.n = 0; return nullptr; } t.n = n; }
+  return t.dev;
+}
+
+template <typename T> int recur_forward(cudaStream_t, const B2CShape&, const RecurPlan&, const TrainWs<T>&, const T*, T*, float*, const B2CDropout&) {
+  return set_err(B2C_EINVAL, "the persistent recurrence kernel is bf16 only");
+}
+template <>
+int recur_forward<bf16>(cudaStream_t st, const B2CShape& s, const RecurPlan& pl, const TrainWs<bf16>& W, const bf16* feats, bf16* hid_top, float* attw,
+                        const B2CDropout& dr) {
+  RecurMaps maps; RecurParams p{};
+  p.B = s.B; p.T = s.T; p.S = s.S; p.E = s.E; p.H = s.H; p.L = s.L;
+  p.tiles_m = pl.tiles_m; p.tiles_n = pl.tiles_n; p.u_tiles_n = pl.u_tiles_n; p.n_fbuf = pl.n_fbuf; p.f_resident = pl.f_resident; p.tmem_cols = pl.tmem_cols;
+  p.P = W.P; p.EP = W.EP; p.F = feats; p.u = W.u; p.attw = attw; p.G0 = W.G0; p.hid_top = hid_top;
+  p.trace = recur_trace_buffer((size_t)pl.grid * s.T * 16);
+  for (int k = 0; k < s.L; ++k) {
+    const int in = in_dim(s, k), ld = in + s.H;
+    p.xh[k] = W.xh[k]; p.ld[k] = ld; p.in[k] = in; p.bias[k] = (k == 0) ? nullptr : W.w.bcat[k]; p.c[k] = W.c[k]; p.gates[k] = W.gates[k];
+    B2C_TRY(make_tmap_bf16_3d(&maps.a[k], W.xh[k], ld, s.B, s.T + 1, ld, TC_BM));
+    B2C_TRY(make_tmap_bf16(&maps.w[k], W.w.Wcat[k], ld, 4 * s.H, ld, RC_BN));
+  }
+  for (int k = s.L; k < RC_MAXL; ++k) { maps.a[k] = maps.a[0]; maps.w[k] = maps.w[0]; }
+  B2C_TRY(make_tmap_bf16(&maps.wh, W.w.Wh, s.H, s.E, s.H, RC_BNU));
+  p.drop_p = dr.p; p.seed = dr.seed; p.seed_dev = (const unsigned long long*)dr.seed_dev;
+  { const char* e = getenv("B2C_RECUR_EARLY"); p.early = (e && e[0] == '0') ? 0 : 1; }
+  { const char* e = getenv("B2C_RECUR_EPNC"); p.ep_nc = (e && e[0] == '1') ? 1 : 0; }
+  p.barrier = W.sync; p.flags = W.sync + 128;
+  B2C_CHECK_ARG(pl.grid <= 160, "unexpected grid %d", pl.grid);
+  B2C_CUDA(cudaMemsetAsync(W.sync, 0, (128 + 160 * 32) * sizeof(unsigned int), st));
+  void (*kern)(const RecurMaps, const RecurParams) = pl.nq == 1 ? recur_fwd_kernel<1> : (pl.nq == 2 ? recur_fwd_kernel<2> : recur_fwd_kernel<3>);
+  B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3(RC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;      // every CTA is resident: they wait on one another
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p));
+  B2C_LAUNCH_CHECK("recur_fwd_kernel");
+  recur_trace_state().grid = pl.grid; recur_trace_state().T = s.T;
+  return 0;
+}
+
 // ------------------------------------------------------------------ decoder forward (teacher forced)
 // Per step: u = q W_h^T  ->  attention (ctx lands in layer 0's operand)  ->  L fused gate-GEMM + cell kernels.
 // The feature-independent part of the forward: packed operands (bf16 copies, attention_combine folded into layer 0), embedding
@@ -319,7 +374,12 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
   SubPlan sp;
   B2C_TRY(fork_subs(sp, B, st));
   pdl_full_dependency_next();        // P / F are final before any kernel of the recurrence can start (attention prologues read them early)
-  for (int t = 0; t < Tn; ++t) {
+  // bf16 mode: the whole T loop as ONE persistent cooperative kernel when the shape fits its plan (recurrent.cuh); the
+  // per-step kernels below remain for fp32 parity mode, other shapes and B2C_PERSISTENT=0 (A/B)
+  RecurPlan rplan{}; rplan.ok = false;
+  if (sizeof(T) == 2 && sp.ns == 1) rplan = recur_plan(s);
+  if (rplan.ok) B2C_TRY(recur_forward<T>(st, s, rplan, W, feats, hid_top, attw, dr));
+  for (int t = 0; t < (rplan.ok ? 0 : Tn); ++t) {
     for (int i = 0; i < sp.ns; ++i) {
       cudaStream_t ss = sp.st[i];
       const long b0 = sp.b0[i];
@@ -951,6 +1011,17 @@ int b2c_decoder_backward(const B2CShape* shape, const B2CParams* params, const v
   if (dtype == B2C_F32) return decoder_backward_impl<float>(*shape, *params, (const float*)feats, captions, (const float*)hidden_top, attn_w, (const float*)dlogits, (const float*)dhidden_top, *grads, dfeats, workspace, ws_bytes, dr, st, flags);
   if (dtype == B2C_BF16) return decoder_backward_impl<bf16>(*shape, *params, (const bf16*)feats, captions, (const bf16*)hidden_top, attn_w, (const bf16*)dlogits, (const bf16*)dhidden_top, *grads, dfeats, workspace, ws_bytes, dr, st, flags);
   return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_debug_recur_trace(uint64_t* out_host, int64_t n, int32_t* grid_out, int32_t* steps_out) {
+  RecurTrace& t = recur_trace_state();
+  B2C_CHECK_ARG(t.dev != nullptr && out_host && n > 0, "no trace recorded (set B2C_RECUR_TRACE=1 before the first forward)");
+  B2C_CUDA(cudaDeviceSynchronize());
+  const size_t m = (size_t)n < t.n ? (size_t)n : t.n;
+  B2C_CUDA(cudaMemcpy(out_host, t.dev, m * 8, cudaMemcpyDeviceToHost));
+  if (grid_out) *grid_out = t.grid;
+  if (steps_out) *steps_out = t.T;
+  return 0;
 }
 
 int b2c_bump_counter(uint64_t* counter, void* stream) {

@@ -249,6 +249,10 @@ int b2c_optimizer_step(float* param, const float* grad, float* exp_avg, float* e
                        const float* lr, int32_t n_lr, int32_t* step, float* loss_scale, int32_t* growth_tracker,
                        float* stats, void* scratch, void* stream);
 
+/* Debug aid: with B2C_RECUR_TRACE=1 in the environment the persistent forward-recurrence kernel stamps clock64() at its phase
+ * boundaries (per CTA, per time step, 8 stamps); this copies the last launch's stamps to the host (synchronises the device). */
+int b2c_debug_recur_trace(uint64_t* out_host, int64_t n, int32_t* grid_out, int32_t* steps_out);
+
 /* C[m,n] = act(alpha * sum_k A(m,k) B(n,k) + bias[n]) + beta*C[m,n];  a_mn/b_mn = 1 when the operand is stored
  * MN-major (A[k*lda+m]) instead of K-major (A[m*lda+k]).  dtype = operand type; c_dtype = output type.
  * impl: 0 = the mode's default (tcgen05 for bf16 when TMA can describe the operands, FFMA otherwise), 1 = force FFMA tiles. */

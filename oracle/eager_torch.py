@@ -14,7 +14,7 @@ It is pinned on the CPU against kd_oracle (tests/test_oracle.py), which is itsel
   decoder.{embedding, attention, attention_combine, lstm, output_projection.{0,3}}     src/student_model.py:125-156
   attention_refinement.{attention, ffn.{0,3}, norm1, norm2}                            src/student_model.py:76-101
   feature_projection.{0,3}                                                             src/distillation_utils.py:213-231
-Everything runs in eval mode (dropout off), like the oracle.
+Every dropout probability is 0 (the arithmetic of eval mode, like the oracle); the modules stay in train() for cuDNN.
 """
 from __future__ import annotations
 
@@ -126,7 +126,8 @@ def build(params: Dict[str, Tensor], proj_params: Dict[str, Tensor], V, E, H, L,
     proj = EagerProjector(Et, E, S)
     if proj_params:
         proj.load_state_dict({k: v.float() for k, v in proj_params.items()})
-    return model.to(device).eval(), proj.to(device).eval()
+    # train(): cuDNN's RNN backward refuses eval mode; every Dropout above has p = 0, so the arithmetic is the eval-mode one
+    return model.to(device).train(), proj.to(device).train()
 
 
 def _forward_loss(model, proj, batch, autocast_dtype, feats, alpha=0.7, beta=0.2, gamma=0.1, temperature=4.0):

@@ -53,3 +53,13 @@ for s, e, st, name in last:
 for st, ks in streams.items():
     busy = sum(e - s for s, e, _ in ks)
     print(f"stream {st}: {len(ks)} kernels, busy {busy:.1f} us, first {ks[0][0]:.1f} last-end {ks[-1][1]:.1f}")
+# the longest kernels and the gaps on the busiest stream (where does the step time go)
+top = sorted(last, key=lambda r: r[0] - r[1])[:12]
+for s, e, st, name in top:
+    print(f"  {e - s:9.1f} us  start {s - t0:8.1f}  stream {st}  {name[:90]}")
+fam = {}
+for s, e, st, name in last:
+    key = name.split("<")[0].split("(")[0][-48:]
+    fam.setdefault(key, [0, 0.0]); fam[key][0] += 1; fam[key][1] += e - s
+for key, (n, tot) in sorted(fam.items(), key=lambda kv: -kv[1][1])[:14]:
+    print(f"  {tot:9.1f} us  x{n:<4d} {key}")
