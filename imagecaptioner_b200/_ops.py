@@ -106,7 +106,7 @@ SYMBOLS = {
     "b2c_kd_token_loss": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _f, _f, _f, _f, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
     "b2c_kd_token_eval": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _f, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
     "b2c_bleu1": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
-    "b2c_aux_loss": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _f, _f, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
+    "b2c_aux_loss": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _f, _f, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp]),
     "b2c_loss_finalize": (ctypes.c_int, [_vp, _vp, _i64, _vp, _f, _vp, _i32, _i32, _vp, _i32, _i32, _f, _f, _f, _f, _f, _vp, _vp]),
     "b2c_scale_inplace": (ctypes.c_int, [_vp, _i64, ctypes.c_int, _vp, _vp]),
     "b2c_optimizer_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.POINTER(B2COptSegment), _i32, ctypes.POINTER(B2COptHyper),
@@ -452,8 +452,11 @@ class KDLossFunction(torch.autograd.Function):
                "b2c_kd_token_loss")
         fs = ft = hs = ht = dfs = dft = dhs = feat_part = hid_part = None
         Ss = St = E = H = Th = 0
+        fcode = code
         if feats_s is not None and feats_t is not None:
-            fs = feats_s.detach().to(cdt).contiguous()
+            # fp32 student features stay fp32 (the reference's encoder features reach the loss un-cast); otherwise the compute type
+            fs = feats_s.detach().contiguous() if feats_s.dtype == torch.float32 else feats_s.detach().to(cdt).contiguous()
+            fcode = dtype_code(fs.dtype)
             ft = feats_t.detach().to(device=dev, dtype=torch.float32).contiguous()
             _, Ss, E = fs.shape
             St = ft.shape[1]
@@ -468,7 +471,7 @@ class KDLossFunction(torch.autograd.Function):
             hid_part = torch.empty(Th * B, 2, dtype=torch.float32, device=dev)
         if fs is not None or hs is not None:
             _check(lib.b2c_aux_loss(_ptr(fs), _ptr(ft), B, Ss, St, E, _ptr(hs), _ptr(ht), hs.shape[0] if hs is not None else 0, Th, H,
-                                    float(beta), float(gamma), _ptr(dfs), _ptr(dft), _ptr(dhs), _ptr(feat_part), _ptr(hid_part), code, st),
+                                    float(beta), float(gamma), _ptr(dfs), _ptr(dft), _ptr(dhs), _ptr(feat_part), _ptr(hid_part), code, fcode, st),
                    "b2c_aux_loss")
         out5 = torch.empty(5, dtype=torch.float32, device=dev)
         _check(lib.b2c_loss_finalize(rows[0].data_ptr(), rows[1].data_ptr(), N, nval.data_ptr(), float(ce_mult), _ptr(feat_part), B, E,
@@ -524,8 +527,10 @@ def kd_eval(logits, teacher_logits, targets, feats_s, feats_t, hid_s, hid_t, alp
                                  rows[1].data_ptr(), pred.data_ptr(), code, st), "b2c_kd_token_eval")
     fs = ft = hs = ht = feat_part = hid_part = None
     Ss = St = E = H = Th = 0
+    fcode = code
     if feats_s is not None and feats_t is not None:
-        fs = feats_s.detach().to(cdt).contiguous()
+        fs = feats_s.detach().contiguous() if feats_s.dtype == torch.float32 else feats_s.detach().to(cdt).contiguous()
+        fcode = dtype_code(fs.dtype)
         ft = feats_t.detach().to(device=dev, dtype=torch.float32).contiguous()
         _, Ss, E = fs.shape
         St = ft.shape[1]
@@ -537,7 +542,7 @@ def kd_eval(logits, teacher_logits, targets, feats_s, feats_t, hid_s, hid_t, alp
         hid_part = torch.empty(Th * B, 2, dtype=torch.float32, device=dev)
     if fs is not None or hs is not None:
         _check(lib.b2c_aux_loss(_ptr(fs), _ptr(ft), B, Ss, St, E, _ptr(hs), _ptr(ht), hs.shape[0] if hs is not None else 0, Th, H,
-                                float(beta), float(gamma), None, None, None, _ptr(feat_part), _ptr(hid_part), code, st), "b2c_aux_loss")
+                                float(beta), float(gamma), None, None, None, _ptr(feat_part), _ptr(hid_part), code, fcode, st), "b2c_aux_loss")
     out5 = torch.empty(5, dtype=torch.float32, device=dev)
     _check(lib.b2c_loss_finalize(rows[0].data_ptr(), rows[1].data_ptr(), N, nval.data_ptr(), float(ce_mult), _ptr(feat_part), B, E,
                                  _ptr(hid_part), Th, H, float(temperature), float(alpha), float(beta), float(gamma), float(w_ce),

