@@ -420,6 +420,7 @@ def run_ours(args):
             legs = {"decode_b2048_len30": decode_leg(dev, peaks, steps=5)}
             for Bl in (32, 256):
                 legs[f"large_variant_b{Bl}"] = large_variant_leg(dev, Bl, peaks, steps=max(10, min(args.steps, 30)))
+            legs["validation_b512"] = validation_leg(dev, peaks)
             eager = gpu_eager_baseline(dev)
     mode = "eval mode (dropout off)" if args.eval_mode else f"training mode (dropout {DROPOUT} decoder, 0.1 refinement, 0.1 projector; fresh mask per replay)"
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup if args.warmup >= 3 else warmup,
@@ -493,6 +494,47 @@ def large_variant_leg(dev, B, peaks, steps):
             "ms_per_step": ms, "samples_per_s": B / ms * 1e3, "loss": loss[0],
             "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": fl / (ms * 1e-3) / 1e12 / peaks["tf_sustained"], "algorithmic_flops": fl}}
+
+
+def validation_leg(dev, peaks, steps=10):
+    """validate_student_model's per-batch body at BASELINE configs[1] sizes (B=512, T=20, V=5000, bf16): the student forward + the
+    loss without gradients + argmax, with the logits materialised (b2c_decoder_forward + b2c_kd_token_eval) and without
+    (b2c_decoder_forward_eval: partials in the vocabulary-head GEMM's epilogue)."""
+    from imagecaptioner_b200.distillation_utils import DistillationLoss
+    from oracle import kd_oracle as O
+    from tests.harness import build_student
+    cfg = CFG
+    B, T, V, E, H, L = cfg["B"], cfg["T"], cfg["V"], cfg["E"], cfg["H"], cfg["L"]
+    params = O.init_student_params(V, E, H, L, True, seed=0)
+    pparams = O.init_projector_params(cfg["Et"], E, seed=1)
+    model, projector = build_student(params, pparams, V, E, H, L, True, cfg["Et"], dev)
+    model.decoder.compute_dtype = torch.bfloat16
+    model.attention_refinement.compute_dtype = torch.bfloat16
+    projector.compute_dtype = torch.bfloat16
+    batch = {k: (v.to(dev) if v is not None else None) for k, v in make_batch(cfg, 99).items()}
+    loss_mod = DistillationLoss(0.7, 0.2, 0.1, 4.0, vocab_size=V)
+    out = {"workload": "validate_student_model body, B=512 T=20 V=5000 bf16 (student forward + loss without gradients + argmax), eager launches"}
+    with torch.no_grad():
+        t_out = {"logits": batch["teacher_logits"], "encoder_features": projector(batch["teacher_features"]), "hidden_states": None}
+
+        def unfused():
+            logits, enc, hids, _ = model(batch["encoder_features"], batch["captions_input"])
+            return loss_mod.evaluate({"logits": logits, "encoder_features": enc, "hidden_states": hids}, t_out, batch["targets"])[1]
+
+        def fused():
+            return loss_mod.evaluate_fused(model, batch["encoder_features"], batch["captions_input"], t_out, batch["targets"])[1]
+        for name, fn in (("logits_materialised", unfused), ("logits_free", fused)):
+            for _ in range(3):
+                d = fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record()
+            for _ in range(steps):
+                d = fn()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"ms_per_batch": ms, "samples_per_s": B / ms * 1e3, "total_loss": d["total_loss"]}
+    out["logits_bytes_not_written_or_read"] = 2 * T * B * V * 2
+    return out
 
 
 def run_decode(args):

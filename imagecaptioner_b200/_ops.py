@@ -91,6 +91,7 @@ SYMBOLS = {
     "b2c_workspace_bytes": (_sz, [_SHP, ctypes.c_int, ctypes.c_int]),
     "b2c_decoder_forward": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_decoder_prepare": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _sz, ctypes.c_int, _vp]),
+    "b2c_decoder_forward_eval": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_decoder_forward_prepared": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_decoder_backward": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _GRD, _vp, _vp, _sz, ctypes.c_int, _DRP, ctypes.c_int, _vp]),
     "b2c_bump_counter": (ctypes.c_int, [_vp, _vp]),
@@ -505,26 +506,11 @@ class KDLossFunction(torch.autograd.Function):
         return cast(sv["dlogits"], dt_l), None, None, cast(sv["dfs"], dt_fs), cast(sv["dft"], dt_ft), cast(sv["dhs"], dt_hs), None, None
 
 
-@torch.no_grad()
-def kd_eval(logits, teacher_logits, targets, feats_s, feats_t, hid_s, hid_t, alpha, beta, gamma, temperature, w_ce, nval_global=None,
-            ce_mult=1.0):
-    """DistillationLoss without gradients (validate_student_model): -> (out5 device tensor [total, ce, token_kd, feature_kd,
-    hidden_kd], predicted tokens (T,B) int32 = logits.argmax(-1), taken in the same pass over the logits)."""
+def _eval_finish(rows, nval, B, feats_s, feats_t, hid_s, hid_t, alpha, beta, gamma, temperature, w_ce, ce_mult, cdt, code, dev):
+    """feature / hidden KD without gradients + the fixed-order finalize on per-row token partials -> out5 (device)."""
     lib = load_library()
-    _require_cuda(logits, "student logits")
-    T, B, V = logits.shape
-    N, dev = T * B, logits.device
-    cdt = logits.dtype if logits.dtype in (torch.float32, torch.bfloat16) else torch.float32
-    code = dtype_code(cdt)
-    y = logits.detach().to(cdt).contiguous()
-    z = teacher_logits.detach().to(device=dev, dtype=torch.float32).contiguous()
-    tg = targets.detach().to(device=dev, dtype=torch.int64).contiguous()
     st = _stream()
-    nval = nval_global if nval_global is not None else count_valid(tg, V)
-    rows = torch.empty(2, N, dtype=torch.float32, device=dev)
-    pred = torch.empty(T, B, dtype=torch.int32, device=dev)
-    _check(lib.b2c_kd_token_eval(y.data_ptr(), z.data_ptr(), tg.data_ptr(), N, V, float(temperature), nval.data_ptr(), rows[0].data_ptr(),
-                                 rows[1].data_ptr(), pred.data_ptr(), code, st), "b2c_kd_token_eval")
+    N = rows.shape[1]
     fs = ft = hs = ht = feat_part = hid_part = None
     Ss = St = E = H = Th = 0
     fcode = code
@@ -547,6 +533,73 @@ def kd_eval(logits, teacher_logits, targets, feats_s, feats_t, hid_s, hid_t, alp
     _check(lib.b2c_loss_finalize(rows[0].data_ptr(), rows[1].data_ptr(), N, nval.data_ptr(), float(ce_mult), _ptr(feat_part), B, E,
                                  _ptr(hid_part), Th, H, float(temperature), float(alpha), float(beta), float(gamma), float(w_ce),
                                  out5.data_ptr(), st), "b2c_loss_finalize")
+    return out5
+
+
+@torch.no_grad()
+def kd_eval(logits, teacher_logits, targets, feats_s, feats_t, hid_s, hid_t, alpha, beta, gamma, temperature, w_ce, nval_global=None,
+            ce_mult=1.0):
+    """DistillationLoss without gradients (validate_student_model): -> (out5 device tensor [total, ce, token_kd, feature_kd,
+    hidden_kd], predicted tokens (T,B) int32 = logits.argmax(-1), taken in the same pass over the logits)."""
+    lib = load_library()
+    _require_cuda(logits, "student logits")
+    T, B, V = logits.shape
+    N, dev = T * B, logits.device
+    cdt = logits.dtype if logits.dtype in (torch.float32, torch.bfloat16) else torch.float32
+    code = dtype_code(cdt)
+    y = logits.detach().to(cdt).contiguous()
+    z = teacher_logits.detach().to(device=dev, dtype=torch.float32).contiguous()
+    tg = targets.detach().to(device=dev, dtype=torch.int64).contiguous()
+    nval = nval_global if nval_global is not None else count_valid(tg, V)
+    rows = torch.empty(2, N, dtype=torch.float32, device=dev)
+    pred = torch.empty(T, B, dtype=torch.int32, device=dev)
+    _check(lib.b2c_kd_token_eval(y.data_ptr(), z.data_ptr(), tg.data_ptr(), N, V, float(temperature), nval.data_ptr(), rows[0].data_ptr(),
+                                 rows[1].data_ptr(), pred.data_ptr(), code, _stream()), "b2c_kd_token_eval")
+    out5 = _eval_finish(rows, nval, B, feats_s, feats_t, hid_s, hid_t, alpha, beta, gamma, temperature, w_ce, ce_mult, cdt, code, dev)
+    return out5, pred
+
+
+@torch.no_grad()
+def decoder_forward_eval(feats: torch.Tensor, captions: torch.Tensor, teacher_logits: torch.Tensor, targets: torch.Tensor,
+                         temperature: float, L: int, params: Sequence[torch.Tensor]):
+    """Teacher-forced decoder forward for validation WITHOUT the logits tensor (b2c_decoder_forward_eval, bf16 mode): ->
+    hidden_top (T,B,H) bf16, attention weights (T,B,S) fp32, rows (2, T*B) fp32 = per-row [KL, CE] partials, predicted tokens (T,B)."""
+    lib = load_library()
+    _require_cuda(feats, "image_features")
+    B, S, E = feats.shape
+    T = captions.shape[0]
+    H = params[1].shape[1] - E
+    V = params[0].shape[0]
+    dev = feats.device
+    shape = B2CShape(B, T, S, E, H, L, V)
+    code = B2C_BF16
+    f = feats.detach().to(torch.bfloat16).contiguous()
+    cap = captions.detach().to(device=dev, dtype=torch.int64).contiguous()
+    z = teacher_logits.detach().to(device=dev, dtype=torch.float32).contiguous()
+    tg = targets.detach().to(device=dev, dtype=torch.int64).contiguous()
+    if tuple(z.shape) != (T, B, V) or tuple(tg.shape) != (T, B):
+        raise ValueError(f"teacher logits {tuple(z.shape)} / targets {tuple(tg.shape)} do not match (T,B,V) = {(T, B, V)}")
+    master = _master(params)
+    ws = torch.empty(workspace_bytes(shape, code, B2C_WS_TRAIN), dtype=torch.uint8, device=dev)
+    hid = torch.empty(T, B, H, dtype=torch.bfloat16, device=dev)
+    attw = torch.empty(T, B, S, dtype=torch.float32, device=dev)
+    rows = torch.empty(2, T * B, dtype=torch.float32, device=dev)
+    pred = torch.empty(T, B, dtype=torch.int32, device=dev)
+    prm = _fill_struct(B2CParams(), master, L)
+    _check(lib.b2c_decoder_forward_eval(ctypes.byref(shape), ctypes.byref(prm), f.data_ptr(), cap.data_ptr(), z.data_ptr(), tg.data_ptr(),
+                                        float(temperature), hid.data_ptr(), attw.data_ptr(), rows[0].data_ptr(), rows[1].data_ptr(),
+                                        pred.data_ptr(), ws.data_ptr(), ws.numel(), code, _stream()), "b2c_decoder_forward_eval")
+    return hid, attw, rows, pred
+
+
+@torch.no_grad()
+def kd_eval_rows(rows, pred, targets, V, feats_s, feats_t, hid_s, hid_t, alpha, beta, gamma, temperature, w_ce, nval_global=None, ce_mult=1.0):
+    """The rest of the validation loss on per-row token partials that came out of decoder_forward_eval: -> (out5, pred)."""
+    dev = rows.device
+    tg = targets.detach().to(device=dev, dtype=torch.int64).contiguous()
+    nval = nval_global if nval_global is not None else count_valid(tg, V)
+    out5 = _eval_finish(rows, nval, tg.shape[1], feats_s, feats_t, hid_s, hid_t, alpha, beta, gamma, temperature, w_ce, ce_mult,
+                        torch.bfloat16, B2C_BF16, dev)
     return out5, pred
 
 

@@ -108,6 +108,7 @@ template <typename T> struct TrainWs {
   float *dWx32, *dWe32; T *dWxT, *dWeT; float* partial_side;
   unsigned int* sync;                 // grid-barrier arrival counters of the persistent recurrence kernels (recurrent.cuh)
   float* EP;                          // e^{2P} (B, S, E) fp32: the attention phase of the persistent forward kernel streams it instead of P
+  float* evalp;                       // (T*B, ceil(V/32), 8) partials of the validation epilogue of the vocabulary-head GEMM
   size_t bytes;
   void carve(void* base, const B2CShape& s) {
     Carver c{reinterpret_cast<unsigned char*>(base), 0};
@@ -132,6 +133,7 @@ template <typename T> struct TrainWs {
     partial = c.take<float>((size_t)COLSUM_RS * mc); partial_side = c.take<float>((size_t)COLSUM_RS * mc);
     sync = c.take<unsigned int>(128 + 160 * 32);         // four arrival-counter lines + one 128-byte flag line per CTA
     EP = c.take<float>(B * S * E);
+    evalp = c.take<float>(TB * (size_t)cdiv(s.V, 32) * EVAL_PART_FLOATS);
     bytes = align_up(c.off, 256);
   }
 };
@@ -360,9 +362,12 @@ int decoder_prepare_impl(const B2CShape& s, const B2CParams& p, const int64_t* c
   return 0;
 }
 
+struct EvalOut { const float* teacher; const int64_t* targets; float temperature; float* row_kl; float* row_ce; int* argmax; };
+
 template <typename T>
 int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, const int64_t* cap, T* logits, T* hid_top,
-                         float* attw, void* ws, size_t ws_bytes, const B2CDropout& dr, cudaStream_t st, bool prepared) {
+                         float* attw, void* ws, size_t ws_bytes, const B2CDropout& dr, cudaStream_t st, bool prepared,
+                         const EvalOut* ev = nullptr) {
   TrainWs<T> W; W.carve(ws, s);
   B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
   const int B = s.B, Tn = s.T, S = s.S, E = s.E, H = s.H, L = s.L, V = s.V;
@@ -405,6 +410,18 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
   if (dr.p > 0.f) {
     dropout_inplace_kernel<T><<<ew_grid(TB * E), 256, 0, st>>>(W.o1, TB * E, dr.p, dr.seed, 100u, (const unsigned long long*)dr.seed_dev);
     B2C_LAUNCH_CHECK("dropout_inplace_kernel");
+  }
+  if (ev) {
+    // validation: the vocabulary-head GEMM reduces its tiles to per-row partials of token KD / CE / argmax against the teacher
+    // logits (no logits tensor is written or read back), merged by one small kernel
+    GemmArgs gv{(int)TB, V, E, 1.f, 0.f, W.o1, (long)E, 0, W.w.W2, (long)E, 0, nullptr, (long)V, p.out3_b, 0};
+    B2C_CHECK_ARG(sizeof(T) == 2 && tc_eligible(gv), "the logits-free validation forward needs bf16 mode and a TMA-describable vocabulary head");
+    EvalEpi ee{ev->teacher, ev->targets, W.evalp, 1.0f / ev->temperature, 0, 0};
+    gv.eval = &ee;
+    B2C_TRY((Gemm<T, float>::run(gv, st)));
+    kd_eval_combine_kernel<<<cdiv(TB, 8), 256, 0, st>>>(W.evalp, ee.nparts, TB, V, ev->targets, 1.0f / ev->temperature, ev->row_kl, ev->row_ce, ev->argmax);
+    B2C_LAUNCH_CHECK("kd_eval_combine_kernel");
+    return 0;
   }
   B2C_TRY((gemm<T, T>(st, (int)TB, V, E, W.o1, E, 0, W.w.W2, E, 0, logits, V, 0.f, p.out3_b)));
   return 0;
@@ -990,6 +1007,20 @@ int b2c_decoder_forward_prepared(const B2CShape* shape, const B2CParams* params,
                                  int dtype, const B2CDropout* dropout, void* stream) {
   return decoder_forward_entry(shape, params, feats, captions, logits, hidden_top, attn_w, workspace, ws_bytes, dtype, dropout, stream, true);
 }
+int b2c_decoder_forward_eval(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
+                             const float* teacher_logits, const int64_t* targets, float temperature,
+                             void* hidden_top, float* attn_w, float* row_kl, float* row_ce, int32_t* argmax_out,
+                             void* workspace, size_t ws_bytes, int dtype, void* stream) {
+  B2C_TRY(check_shape(shape)); B2C_TRY(check_device());
+  B2C_CHECK_ARG(params && feats && captions && teacher_logits && targets && hidden_top && attn_w && row_kl && row_ce && workspace, "NULL argument");
+  B2C_CHECK_ARG(temperature > 0.f, "temperature %f", temperature);
+  B2C_CHECK_ARG(dtype == B2C_BF16, "the logits-free validation forward is a bf16-mode path (fp32 parity mode keeps the logits)");
+  const B2CDropout dr{0.f, 0, nullptr};
+  const EvalOut ev{teacher_logits, targets, temperature, row_kl, row_ce, argmax_out};
+  return decoder_forward_impl<bf16>(*shape, *params, (const bf16*)feats, captions, (bf16*)nullptr, (bf16*)hidden_top, attn_w, workspace, ws_bytes, dr,
+                                    (cudaStream_t)stream, false, &ev);
+}
+
 int b2c_decoder_prepare(const B2CShape* shape, const B2CParams* params, const int64_t* captions, void* workspace, size_t ws_bytes,
                         int dtype, void* stream) {
   B2C_TRY(check_shape(shape)); B2C_TRY(check_device());

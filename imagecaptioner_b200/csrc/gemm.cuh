@@ -37,6 +37,16 @@ struct LstmEpi {
   const unsigned long long* seed_dev;   // optional device step counter mixed into the seed (CUDA-graph replays)
 };
 
+// Validation (validate_student_model, reference src/train_student_kd.py:29-86) needs, per logits row, only the token-KD term, the CE
+// term and the argmax.  The vocabulary-head GEMM can reduce every accumulator tile in its epilogue to per-row PARTIALS of those
+// (online-softmax form) against the teacher logits it streams alongside, instead of writing the (T,B,V) logits that a second
+// kernel would read back: 8 floats per (row, part), a part being the run of `cols_per_part` columns one epilogue thread drains.
+//   my, s1 = sum e^{y-my}, sT = sum e^{(y-my)/Temp};  mz, sZ = sum e^{(z-mz)/Temp}, sA = sum e^{(z-mz)/Temp} ((z-mz) - (y-my))/Temp;
+//   y[target] if the target column lies in the part; the part's argmax column (lowest index among equals).
+// kd_eval_combine_kernel (loss_kernels.cuh) merges the parts of a row.  The descriptor travels in the LstmEpi slot: enabled == 3.
+constexpr int EVAL_PART_FLOATS = 8;
+struct EvalEpi { const float* teacher; const int64_t* targets; float* parts; float inv_temp; int nparts; int cols_per_part; };
+
 // Greedy decoding needs argmax_n C[m, n] only: the vocabulary-head GEMM can reduce every accumulator tile to per-row partial
 // (max, index) pairs in its epilogue instead of writing the logits (41 MB per step at B = 2048, V = 5000, read again by the argmax
 // kernel).  One partial per (row, part): a part is the run of `cols_per_part` columns one epilogue warp drains of one tile.
@@ -45,6 +55,12 @@ struct ArgmaxEpi { float* pmax; int* pidx; int nparts; int cols_per_part; };
 inline LstmEpi pack_argmax(const ArgmaxEpi& a) {
   LstmEpi le{};
   le.enabled = 2; le.H = a.nparts; le.c_out = a.pmax; le.gates_out = a.pidx; le.ld_rec = a.cols_per_part;
+  return le;
+}
+inline LstmEpi pack_eval(const EvalEpi& e) {
+  LstmEpi le{};
+  le.enabled = 3; le.H = e.nparts; le.c_out = e.parts; le.addend = e.teacher; le.h_rec = const_cast<int64_t*>(e.targets);
+  le.ld_rec = e.cols_per_part; le.drop_p = e.inv_temp;
   return le;
 }
 
@@ -468,6 +484,76 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
     constexpr int NCHUNK = BN / CH;                      // 128-byte column chunks per tile row
     constexpr int C_PER = (NCHUNK + 1) / 2;
+    if (le.enabled == 3) {
+      // ---- validation epilogue (EvalEpi): this thread owns one logits row and C_PER * CH columns of it
+      const float* zt = reinterpret_cast<const float*>(le.addend);
+      const int64_t* tg = reinterpret_cast<const int64_t*>(le.h_rec);
+      float* parts = le.c_out;
+      const int nparts = le.H, grow = m0 + q * 32 + lane;
+      const float inv_temp = le.drop_p, L2E = 1.4426950408889634f, kT = inv_temp * L2E;
+      const bool row_ok = grow < M;
+      const long tcol = row_ok ? (long)tg[grow] : -1;
+      float my = -INFINITY, s1 = 0.f, sT = 0.f, mz = -INFINITY, sZ = 0.f, sA = 0.f, ytgt = 0.f; int bidx = 0x7fffffff;
+#pragma unroll 1
+      for (int ci = half * C_PER; ci < (half + 1) * C_PER && ci < NCHUNK; ++ci) {
+#pragma unroll 1
+        for (int h = 0; h < CH / 32; ++h) {
+          const int colb = n0 + ci * CH + h * 32;
+          if (colb >= N) break;                             // warp-uniform
+          float v[32], z[32];
+          tmem_ld32(tacc + (uint32_t)(ci * CH + h * 32), v);
+          const bool full = colb + 32 <= N;
+          const float* zr = zt + (long)(row_ok ? grow : 0) * N + colb;
+          if (full && ((((uintptr_t)zr) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(zr) + j); z[4 * j] = t4.x; z[4 * j + 1] = t4.y; z[4 * j + 2] = t4.z; z[4 * j + 3] = t4.w; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) z[j] = (colb + j < N) ? __ldg(zr + j) : -INFINITY;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (colb + j < N) ? fmaf(alpha, v[j], bias != nullptr ? __ldg(bias + colb + j) : 0.f) : -INFINITY;
+          // chunk-local maxima, then merge the running sums onto the new maxima
+          float cmy = v[0], cmz = z[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) { cmy = fmaxf(cmy, v[j]); cmz = fmaxf(cmz, z[j]); }
+          if (cmy > my) {                                   // strict: an equal later value keeps the earlier (lower) column
+#pragma unroll
+            for (int j = 31; j >= 0; --j) if (v[j] == cmy) bidx = colb + j;
+          }
+          const float nmy = fmaxf(my, cmy), nmz = fmaxf(mz, cmz);
+          const float ry = my - nmy, rz = (mz - nmz) * inv_temp;          // <= 0 (-inf on the first chunk)
+          const float c1 = ex2_ftz(ry * L2E), cT = ex2_ftz(ry * kT), cZ = ex2_ftz(rz * L2E);
+          // sA' = cZ (sA + sZ (rz - ry / Temp));  guard the first chunk (sZ = 0, rz = -inf)
+          sA = (sZ > 0.f) ? cZ * (sA + sZ * (rz - ry * inv_temp)) : 0.f;
+          s1 *= c1; sT *= cT; sZ *= cZ;
+          my = nmy; mz = nmz;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float yd = v[j] - my, zd = (z[j] - mz) * inv_temp;
+            const float eT = ex2_ftz(yd * kT), e1 = ex2_ftz(yd * L2E), ez = ex2_ftz(zd * L2E);
+            s1 += e1; sT += eT; sZ += ez;
+            sA += (ez > 0.f) ? ez * (zd - yd * inv_temp) : 0.f;       // masked columns: e^{-inf} * (-inf + inf) must not produce NaN
+          }
+          if (tcol >= colb && tcol < colb + 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (colb + j == tcol) ytgt = v[j];
+          }
+        }
+      }
+      if (row_ok) {
+        const int part = (n0 + half * C_PER * CH) / (C_PER * CH);
+        if (part < nparts) {
+          float4* o = reinterpret_cast<float4*>(parts + ((long)grow * nparts + part) * EVAL_PART_FLOATS);
+          o[0] = make_float4(my, s1, sT, mz);
+          o[1] = make_float4(sZ, sA, ytgt, __int_as_float(bidx));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      continue;
+    }
     if (le.enabled == 2) {
       // ---- argmax epilogue (ArgmaxEpi): this thread owns one row and C_PER * CH columns of it: running (max, lowest index)
       float* pmax = le.c_out; int* pidx = reinterpret_cast<int*>(le.gates_out);
@@ -688,6 +774,7 @@ struct GemmArgs {
   int row_unperm_h = 0;              // != 0: output row m is written to row (m & 3) * H + (m >> 2) (gate-interleaved -> gate-major)
   const LstmEpi* lstm = nullptr;     // fused LSTM-cell epilogue instead of writing C
   ArgmaxEpi* amax = nullptr;         // per-row partial argmax instead of writing C (tcgen05 path only; nparts / cols_per_part are filled in)
+  EvalEpi* eval = nullptr;           // per-row partials of token KD / CE / argmax instead of writing C (tcgen05 path only; nparts filled in)
 };
 
 inline bool tc_eligible(const GemmArgs& g) {
@@ -700,7 +787,7 @@ inline bool tc_eligible(const GemmArgs& g) {
 struct TcPlan { int bn, splits, kb_per_split; };
 inline TcPlan plan_tc(const GemmArgs& g, int elem_c, int sms) {
   const int num_kb = cdiv(g.K, TC_BK);
-  const bool can_split = (elem_c == 4) && !g.relu && (g.beta == 0.f || g.beta == 1.f) && (g.lstm == nullptr) && (g.amax == nullptr);
+  const bool can_split = (elem_c == 4) && !g.relu && (g.beta == 0.f || g.beta == 1.f) && (g.lstm == nullptr) && (g.amax == nullptr) && (g.eval == nullptr);
   TcPlan best{64, 1, num_kb}; double best_cost = 1e30;
   const int cand[3] = {256, 128, 64};
   for (int ci = 0; ci < 3; ++ci) {
@@ -757,6 +844,13 @@ int launch_tc(const GemmArgs& g, const TcPlan& plan, cudaStream_t st) {
     g.amax->cols_per_part = CPER * CHc;
     g.amax->nparts = cdiv(g.N, g.amax->cols_per_part);
     epi = pack_argmax(*g.amax);
+  }
+  if (g.eval) {
+    B2C_CHECK_ARG(!g.lstm && !g.amax && splits == 1 && g.eval->teacher && g.eval->targets && g.eval->parts, "validation epilogue: no K split, no other epilogue, buffers required");
+    constexpr int CHc = 128 / (int)sizeof(TC), CPER = (BN / CHc + 1) / 2;
+    g.eval->cols_per_part = CPER * CHc;
+    g.eval->nparts = cdiv(g.N, g.eval->cols_per_part);          // the caller sized `parts` for the smallest part (32 columns)
+    epi = pack_eval(*g.eval);
   }
   B2C_CUDA(launch_pdl(kern, dim3(grid), dim3(TC_THREADS), TcCfg<BN>::SMEM_BYTES, st, ta, tb, g.M, g.N, g.K, g.alpha, g.beta, (TC*)g.C, g.ldc,
                       g.bias, g.relu, kb_per_split, tiles_m, tiles_n, splits, g.row_unperm_h, epi));

@@ -179,6 +179,40 @@ kd_token_loss_kernel(const TS* __restrict__ y, const float* __restrict__ z, cons
   }
 }
 
+// Merge of the per-(row, part) partials the vocabulary-head GEMM's validation epilogue leaves (gemm.cuh EvalEpi): one warp per
+// logits row, lanes over the parts, fixed order.  Same outputs as the evaluation form of kd_token_loss_kernel:
+//   row_kl = sA / sZ - log sZ + log sT,  row_ce = log s1 + my - y[target] (0 on PAD rows),  argmax (lowest index among equals).
+__global__ void __launch_bounds__(256)
+kd_eval_combine_kernel(const float* __restrict__ parts, int nparts, long N, int V, const int64_t* __restrict__ tgt, float inv_temp,
+                       float* __restrict__ row_kl, float* __restrict__ row_ce, int* __restrict__ argmax_out) {
+  const long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= N) return;
+  const float4* p = reinterpret_cast<const float4*>(parts + r * (long)nparts * 8);
+  float MY = -INFINITY, MZ = -INFINITY;
+  for (int i = lane; i < nparts; i += 32) { const float4 a = p[2 * i]; MY = fmaxf(MY, a.x); MZ = fmaxf(MZ, a.w); }
+  MY = warp_max(MY); MZ = warp_max(MZ);
+  float s1 = 0.f, sT = 0.f, sZ = 0.f, sA = 0.f, ytgt = 0.f; int best = 0x7fffffff;
+  for (int i = lane; i < nparts; i += 32) {
+    const float4 a = p[2 * i], b = p[2 * i + 1];
+    const float dy = a.x - MY, dz = (a.w - MZ) * inv_temp;          // <= 0
+    const float cz = __expf(dz);
+    s1 += a.y * __expf(dy); sT += a.z * __expf(dy * inv_temp); sZ += b.x * cz;
+    sA += cz * (b.y + b.x * (dz - dy * inv_temp));
+    ytgt += b.z;                                                    // exactly one part holds the target column, the others wrote 0
+    if (a.x == MY) best = min(best, __float_as_int(b.w));
+  }
+  s1 = warp_sum(s1); sT = warp_sum(sT); sZ = warp_sum(sZ); sA = warp_sum(sA); ytgt = warp_sum(ytgt);
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if (lane == 0) {
+    const long t64 = tgt[r];
+    const bool valid = (t64 > 0) && (t64 < V);
+    row_kl[r] = sA / sZ - __logf(sZ) + __logf(sT);
+    row_ce[r] = valid ? (__logf(s1) + MY - ytgt) : 0.0f;
+    if (argmax_out) argmax_out[r] = best == 0x7fffffff ? 0 : best;
+  }
+}
+
 // Kernel (3), default form (V % 8 == 0, V <= 16384; NCH == ceil(V/8/256) so only the last chunk can be partial): persistent CTAs (grid = SMs x resident CTAs), each looping over logits
 // rows.  The NEXT row's student and teacher logits are prefetched into a double-buffered shared-memory slot by two 1-D TMA
 // bulk copies on an mbarrier while the CURRENT row is processed entirely in registers: one 128-bit shared-memory read per

@@ -114,6 +114,31 @@ class DistillationLoss(nn.Module):
                      "feature_kd_loss": vals[3], "hidden_kd_loss": vals[4]}
         return out5[0], loss_dict, pred
 
+    @torch.no_grad()
+    def evaluate_fused(self, student_model, images, captions_input, teacher_outputs, targets):
+        """`evaluate` without a logits tensor: the student's validation forward reduces the vocabulary head straight to the per-row
+        token-KD / CE partials and the argmax (CaptioningStudent.forward_validation); the feature / hidden terms and the weighting
+        follow as in `evaluate`.  -> (total_loss 0-dim tensor, loss_dict of 5 floats, predicted_tokens (T,B) int32)."""
+        rows, pred, enc, hids, _ = student_model.forward_validation(images, captions_input, teacher_outputs["logits"], targets, self.temperature)
+        feats_t = teacher_outputs.get("encoder_features")
+        feats_s = enc if feats_t is not None else None
+        if feats_s is not None and feats_s.shape[-1] != feats_t.shape[-1]:
+            raise ValueError(f"Feature dimensions don't match: student {feats_s.shape[-1]}, teacher {feats_t.shape[-1]}")
+        hid_s, hid_t = _stack_hidden(hids), _stack_hidden(teacher_outputs.get("hidden_states"))
+        if hid_t is not None:
+            if hid_s.shape[-1] != hid_t.shape[-1]:
+                raise ValueError(f"Hidden dimensions don't match: student {hid_s.shape[-1]}, teacher {hid_t.shape[-1]}")
+            hid_t = hid_t[:min(hid_s.shape[0], hid_t.shape[0])]
+        else:
+            hid_s = None
+        w_ce = 1 - self.alpha - self.beta - self.gamma
+        out5, pred = _ops.kd_eval_rows(rows, pred, targets, student_model.vocab_size, feats_s, feats_t, hid_s, hid_t, self.alpha, self.beta,
+                                       self.gamma, self.temperature, w_ce, self.n_valid_global, float(self.world_size))
+        vals = out5.tolist()
+        loss_dict = {"total_loss": vals[0], "ce_loss": vals[1], "token_kd_loss": vals[2],
+                     "feature_kd_loss": vals[3], "hidden_kd_loss": vals[4]}
+        return out5[0], loss_dict, pred
+
     # ---- the reference's individual terms, each through the same kernels --------------------------
     def _dummy_targets(self, logits):
         # any non-PAD id: the CE term is weighted by exactly 0 in the single-term entry points below

@@ -238,6 +238,24 @@ class CaptioningStudent(nn.Module):
         outputs, hidden_states, attention_weights = self.decoder(refined, captions, prepared=prepared)
         return outputs, encoder_features, hidden_states, attention_weights
 
+    def supports_fused_validation(self) -> bool:
+        """The logits-free validation forward exists in bf16 mode (autocast, or decoder.compute_dtype = bfloat16) for vocabularies
+        TMA can describe (V % 8 == 0)."""
+        return self.decoder._mode() == torch.bfloat16 and self.vocab_size % 8 == 0
+
+    @torch.no_grad()
+    def forward_validation(self, images, captions, teacher_logits, targets, temperature):
+        """validate_student_model's student forward (reference src/train_student_kd.py:56) fused with the token part of the loss:
+        -> (rows (2, T*B) per-row [KL, CE] partials, predicted tokens (T,B) = logits.argmax(-1), encoder_features (B,49,E) un-refined,
+        hidden_states list, attention_weights list).  No (T,B,V) logits tensor exists at any point (b2c_decoder_forward_eval)."""
+        encoder_features = self.encoder(images)
+        refined = self.attention_refinement(encoder_features) if self.use_attention_refinement else encoder_features
+        hid, attw, rows, pred = _ops.decoder_forward_eval(refined, captions, teacher_logits, targets, temperature,
+                                                          self.decoder.num_layers, self.decoder._param_list())
+        hidden_states = HiddenStateList(hid.unbind(0))
+        hidden_states.stacked = hid
+        return rows, pred, encoder_features, hidden_states, list(attw.unbind(0))
+
     @torch.no_grad()
     def caption_images(self, images, vocabulary, max_length=20):
         """Batched form of caption_image: one device-side greedy decode for the whole batch."""

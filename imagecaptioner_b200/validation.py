@@ -16,7 +16,7 @@ from .distillation_utils import TeacherWrapper
 
 @torch.no_grad()
 def validate_student_model(student_model, teacher_model, data_loader, distill_loss, projectors, device, vocab=None, max_batches=50,
-                           bleu_all_samples=False):
+                           bleu_all_samples=False, fused=True):
     """-> (average loss per sample, average BLEU-1).  `vocab` is accepted for signature compatibility: the metric is computed
     on token ids (the vocabulary maps ids to words one-to-one)."""
     was_training = student_model.training
@@ -29,11 +29,16 @@ def validate_student_model(student_model, teacher_model, data_loader, distill_lo
         imgs, captions = imgs.to(device), captions.to(device)
         captions_input, captions_target = captions[:-1, :], captions[1:, :]
         teacher_outputs = teacher_wrapper(imgs.float(), captions_input.long())
-        student_logits, student_encoder_features, student_hidden_states, _ = student_model(imgs, captions_input)
-        student_outputs = {"logits": student_logits, "encoder_features": student_encoder_features,
-                           "hidden_states": student_hidden_states}
         teacher_outputs["encoder_features"] = projectors["encoder"](teacher_outputs["encoder_features"])
-        _, loss_dict, predicted = distill_loss.evaluate(student_outputs, teacher_outputs, captions_target)
+        if fused and student_model.supports_fused_validation():
+            # bf16 mode: the vocabulary head is reduced to the loss partials and the argmax in the GEMM's epilogue -- the (T,B,V)
+            # student logits are never written
+            _, loss_dict, predicted = distill_loss.evaluate_fused(student_model, imgs, captions_input, teacher_outputs, captions_target)
+        else:
+            student_logits, student_encoder_features, student_hidden_states, _ = student_model(imgs, captions_input)
+            student_outputs = {"logits": student_logits, "encoder_features": student_encoder_features,
+                               "hidden_states": student_hidden_states}
+            _, loss_dict, predicted = distill_loss.evaluate(student_outputs, teacher_outputs, captions_target)
         n = imgs.size(0)
         total_loss += loss_dict["total_loss"] * n
         total_samples += n

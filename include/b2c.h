@@ -103,6 +103,17 @@ int b2c_decoder_forward(const B2CShape* shape, const B2CParams* params, const vo
                         void* logits, void* hidden_top, float* attn_w, void* workspace, size_t ws_bytes,
                         int dtype, const B2CDropout* dropout, void* stream);
 
+/* Validation forward WITHOUT materialising the logits (validate_student_model, src/train_student_kd.py:29-86; SURVEY.md section 8f
+ * row 4): the teacher-forced decoder forward in eval mode whose vocabulary-head contraction reduces every accumulator tile, in its
+ * epilogue, to per-row partials of the token-KD term, the CE term and the argmax against the teacher logits it streams alongside
+ * (online-softmax form); a second small kernel merges the partials.  Outputs as b2c_kd_token_eval: row_kl (T*B), row_ce (T*B, 0 on
+ * PAD rows), argmax_out (T*B, may be NULL) = student_logits.argmax(-1); hidden_top / attn_w as b2c_decoder_forward.  bf16 mode only.
+ * The (T,B,V) logits are never written: 102 MB less written and 102 MB less read at BASELINE configs[1] sizes. */
+int b2c_decoder_forward_eval(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
+                             const float* teacher_logits, const int64_t* targets, float temperature,
+                             void* hidden_top, float* attn_w, float* row_kl, float* row_ce, int32_t* argmax_out,
+                             void* workspace, size_t ws_bytes, int dtype, void* stream);
+
 /* The part of b2c_decoder_forward that does not read the image features: operand packing (compute-type copies of the weights,
  * attention_combine folded into layer 0), the embedding rows of `captions`, the time-batched embedding half of layer 0's
  * gates and the zero initial state, all written into `workspace` (mode B2C_WS_TRAIN).  It may be enqueued on a different

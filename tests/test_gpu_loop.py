@@ -209,3 +209,25 @@ def test_eager_accumulation_after_graphed_step_is_not_redirected():
     loss.backward()
     g2 = model.decoder.lstm.weight_hh_l0.grad.detach().float().cpu()
     assert relerr(g2, 2 * g1) < 1e-5
+
+
+def test_two_rank_nccl_step_equals_global_batch():
+    """bench.py --check under torchrun on 2 GPUs (NCCL): the averaged all-reduced gradient, the loss parts and the weights after 3
+    optimizer steps equal a 1-GPU run on the concatenated batch, with the overlapped exchange and with serial collectives.
+    Skipped on a one-GPU box (there, the same control flow runs with identity collectives in test_graphed_step_equals_eager_step
+    and `bench.py --check`); profiles/r2_check_dp_n2.json holds the 2-GPU result of this round."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out", "check_n2_test.json")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "bench.py"), "--gpus", "2", "--check", "--out", out],
+                       cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rep = json.load(open(out))
+    assert rep["ok"] and rep["overlap_comm_1"]["overlapped_exchange"] and rep["overlap_comm_1"]["grad_step1_rel_err_worst_tensor"] < 1e-4

@@ -384,3 +384,45 @@ def test_fused_argmax_decode_equals_logits_path(tmp_path):
     assert torch.equal(outs[0]["tokens"], outs[1]["tokens"])
     assert torch.equal(outs[0]["lengths"], outs[1]["lengths"])
     assert outs[0]["tokens"].unique().numel() > 8              # not a degenerate caption (19 distinct ids over columns 171..4393)
+
+
+@pytest.mark.parametrize("V,B,T", [(5000, 96, 7), (1000, 33, 3)])
+def test_logits_free_validation_matches_logits_path_and_oracle(V, B, T):
+    """b2c_decoder_forward_eval: the vocabulary-head GEMM's epilogue reduces its tiles to per-row partials
+    of the token-KD / CE terms and the argmax against the teacher logits, so validation never materialises the (T,B,V) logits.
+    Against (i) the fp64 oracle (loss parts, predictions where the oracle's top-2 margin is not a rounding tie) and (ii) the bf16
+    logits path `DistillationLoss.evaluate` on the same inputs.  V = 5000: an edge N tile; B*T not a multiple of the 128-row tile."""
+    from imagecaptioner_b200.distillation_utils import DistillationLoss
+    E, H, L = 64, 128, 2
+    params = O.init_student_params(V, E, H, L, True, seed=21, logit_scale=6.0)
+    pparams = O.init_projector_params(48, E, seed=22)
+    batch = O.synthetic_batch(B, T, V, E, H, Et=48, seed=23)
+    ref = O.kd_step(to_device(params, DEV), to_device(pparams, DEV), to_device(batch, DEV), dtype=torch.float64)
+    model, projector = build_student(params, pparams, V, E, H, L, True, 48, DEV)
+    model.decoder.compute_dtype = torch.bfloat16
+    model.attention_refinement.compute_dtype = torch.bfloat16
+    projector.compute_dtype = torch.bfloat16
+    assert model.supports_fused_validation()
+    loss_mod = DistillationLoss(0.5, 0.2, 0.1, 4.0, vocab_size=V)          # CE weight 0.2: the CE partials matter
+    dev_b = to_device(batch, DEV)
+    th = dev_b["teacher_hiddens"]
+    with torch.no_grad():
+        t_out = {"logits": dev_b["teacher_logits"], "encoder_features": projector(dev_b["teacher_features"]),
+                 "hidden_states": [th[t] for t in range(th.shape[0])]}
+        _, fused, pred_f = loss_mod.evaluate_fused(model, dev_b["encoder_features"], dev_b["captions_input"], t_out, dev_b["targets"])
+        logits, enc, hids, _ = model(dev_b["encoder_features"], dev_b["captions_input"])
+        _, unfused, pred_u = loss_mod.evaluate({"logits": logits, "encoder_features": enc, "hidden_states": hids}, t_out, dev_b["targets"])
+    ref_loss = O.kd_step(params, pparams, batch, 0.5, 0.2, 0.1, 4.0)["loss"]
+    for k, v in ref_loss.items():
+        assert abs(fused[k] - v) <= BF16_TOL * max(abs(v), 1e-6), (k, fused[k], v)
+        assert abs(fused[k] - unfused[k]) <= 5e-3 * max(abs(v), 1e-6), (k, fused[k], unfused[k])
+    # predictions: identical to the oracle's argmax wherever its top-2 margin exceeds bf16-mode noise; the fused path keeps the
+    # fp32 accumulators, the logits path rounds them to bf16 first, so the two may differ on near-ties only
+    y = ref["logits"].double()
+    top2 = y.topk(2, dim=-1).values
+    clear = ((top2[..., 0] - top2[..., 1]) > 2e-2 * y.abs().amax()).cpu()
+    oracle_pred = y.argmax(-1).cpu()
+    assert int(clear.sum()) >= 10
+    assert torch.equal(pred_f.cpu().long()[clear], oracle_pred[clear])
+    assert float((pred_f.cpu().long() == oracle_pred).float().mean()) > 0.9
+    assert float((pred_f == pred_u).float().mean()) > 0.97
