@@ -10,10 +10,11 @@ projector parameter and the encoder features, gradient all-reduce (N>1), two-gro
   python bench.py --impl reference ...                             # the reference algorithm on the host CPU cores
   torchrun ... bench.py --gpus N --check                           # N-rank step == 1-GPU step on the concatenated batch (fp32)
 
-Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM and the reference's training-mode dropout
-(decoder 0.3, refinement 0.1, projector 0.1; SURVEY.md section 8d "p=0.3 for throughput runs"); `value_dropout_off` = the
-same step in the parity configuration (eval mode); `e2e` = the step through the public modules with every step's inputs
-copied from pinned host memory and the loss read back.  `legs` carries BASELINE configs[3] (greedy decode) and configs[4]
+Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM in the parity configuration (eval mode, dropout
+off: the configuration every parity test and the CPU / GPU baselines run, and round 1's headline); `value_dropout` = the same step
+in the reference's training mode (dropout 0.3 decoder, 0.1 refinement, 0.1 projector; SURVEY.md section 8d "p=0.3 for throughput
+runs"; a fresh mask per graph replay); `e2e` = the step through the public modules with every step's inputs copied from pinned
+host memory and the loss read back.  `legs` carries BASELINE configs[3] (greedy decode) and configs[4]
 (large variant, 32 and 256 per GPU); `gpu_eager_baseline` the stock torch.nn path on the same GPU; `cpu_baseline` the oracle
 port on the host cores at the SAME batch size.
 """
@@ -342,7 +343,7 @@ def run_ours(args):
     # ---- value: the whole step (fwd, loss, bwd, all-reduce, clip, AdamW) as ONE CUDA graph over static, HBM-resident inputs,
     # training mode (dropout 0.3 / 0.1 / 0.1 like the reference's loop; a fresh mask per replay through the device-side counter)
     n_before = lib.b2c_launch_count()
-    kd, model, projector, opt, pinned, resident = build_step(cfg, dev, rank, train_mode=not args.eval_mode, use_graph=not args.no_graph,
+    kd, model, projector, opt, pinned, resident = build_step(cfg, dev, rank, train_mode=args.train_mode, use_graph=not args.no_graph,
                                                              torch_optimizer=args.torch_optimizer)
     launches_per_step = None if args.no_graph else (lib.b2c_launch_count() - n_before) // 4      # 3 warm-up bodies + 1 captured body
     log("step object ready (warm-up + capture done)")
@@ -403,14 +404,14 @@ def run_ours(args):
     e2e_val = B * world / (e2e_ms * 1e-3)
     log("e2e leg done")
 
-    # ---- the same step in the parity configuration (eval mode: dropout off), resident inputs
-    value_off = ms_off = None
-    if not args.eval_mode and not args.quick:
-        kd2, *_ = build_step(cfg, dev, rank, train_mode=False, use_graph=not args.no_graph, torch_optimizer=args.torch_optimizer)
-        ms_off, _ = time_steps(kd2, args.steps, warmup, barrier_sync, world, dev)
-        value_off = B * world / (ms_off * 1e-3)
+    # ---- the same step in the reference's training mode (dropout 0.3 / 0.1 / 0.1, fresh mask per replay), resident inputs
+    value_drop = ms_drop = None
+    if not args.train_mode and not args.quick:
+        kd2, *_ = build_step(cfg, dev, rank, train_mode=True, use_graph=not args.no_graph, torch_optimizer=args.torch_optimizer)
+        ms_drop, _ = time_steps(kd2, args.steps, warmup, barrier_sync, world, dev)
+        value_drop = B * world / (ms_drop * 1e-3)
         del kd2
-        log(f"dropout-off leg done: {ms_off:.3f} ms/step")
+        log(f"dropout leg done: {ms_drop:.3f} ms/step")
 
     peaks = read_peaks()
     roof, extra, legs, eager = None, {}, None, None
@@ -422,13 +423,13 @@ def run_ours(args):
                 legs[f"large_variant_b{Bl}"] = large_variant_leg(dev, Bl, peaks, steps=max(10, min(args.steps, 30)))
             legs["validation_b512"] = validation_leg(dev, peaks)
             eager = gpu_eager_baseline(dev)
-    mode = "eval mode (dropout off)" if args.eval_mode else f"training mode (dropout {DROPOUT} decoder, 0.1 refinement, 0.1 projector; fresh mask per replay)"
+    mode = f"training mode (dropout {DROPOUT} decoder, 0.1 refinement, 0.1 projector; fresh mask per replay)" if args.train_mode else "eval mode (dropout off): the parity configuration"
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup if args.warmup >= 3 else warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": dict(workload_config(world), mode=mode), "clocks": clocks,
+            "data": "synthetic", "config": workload_config(world), "mode": mode, "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 20, "ms_per_step": e2e_ms,
                     "h2d_gbs_per_rank": h2d_bytes / (e2e_ms * 1e-3) / 1e9},
-            "value_dropout_off": value_off, "ms_per_step_dropout_off": ms_off,
+            "value_dropout": value_drop, "ms_per_step_dropout": ms_drop,
             "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": launches_per_step, "cuda_graph": not args.no_graph,
             "optimizer": "torch fused AdamW + global clip" if args.torch_optimizer else "native b2c_optimizer_step (3 LR groups, 2 clip groups)",
             "roofline": roof, "kernels": extra, "legs": legs, "gpu_eager_baseline": eager, "loss": final_loss}
@@ -705,7 +706,7 @@ def main():
     ap.add_argument("--impl", default="b2c", choices=["b2c", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="value + e2e + kernel rooflines only (no legs, no eager / CPU baselines, no dropout-off leg)")
-    ap.add_argument("--eval-mode", action="store_true", help="time the parity configuration (dropout off) as the headline instead of training mode")
+    ap.add_argument("--train-mode", action="store_true", help="time the reference's training mode (dropout on) as the headline instead of the parity configuration")
     ap.add_argument("--workload", default="kd_step", choices=["kd_step", "decode"], help="kd_step = the contract's metric (default); decode = configs[3] greedy decode leg alone")
     ap.add_argument("--torch-optimizer", action="store_true", help="A/B: torch fused AdamW + one global clip instead of the native optimizer step")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying one CUDA graph")

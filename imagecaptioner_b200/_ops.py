@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb2c.so")
+LIB_PATH = os.environ.get("B2C_LIB") or os.path.join(_HERE, "lib", "libb2c.so")      # B2C_LIB: A/B builds (development only)
 
 B2C_MAX_LAYERS = 4
 B2C_F32, B2C_BF16 = 0, 1

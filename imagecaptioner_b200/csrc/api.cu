@@ -175,6 +175,16 @@ inline int ew_grid(long n) { long g = (n + 255) / 256; if (g > 148 * 8) g = 148 
 
 template <typename T>
 int colsum(cudaStream_t st, const T* A, long rows, int cols, long ld, float* partial, float* out, float* out2 = nullptr, int unperm_h = 0) {
+  if (ld == cols && cols % 8 == 0 && ((uintptr_t)A & 15) == 0 && rows >= 256) {
+    // contiguous, 16-byte rows: the vectorised kernel (a warp covers 256 columns of a row with one 512-byte access, four rows in flight)
+    const int gx = cdiv(cols, 256);
+    int rs = (int)((rows + 31) / 32); if (rs > 592 / gx) rs = 592 / gx; if (rs > COLSUM_RS) rs = COLSUM_RS; if (rs < 1) rs = 1;
+    colsum_vec_kernel<T, false><<<dim3(gx, rs), 256, 0, st>>>(const_cast<T*>(A), (const T*)nullptr, rows, cols, 1.f, partial);
+    B2C_LAUNCH_CHECK("colsum_vec_kernel");
+    colsum_final_kernel<<<cdiv(cols, 256), 256, 0, st>>>(partial, rs, cols, out, out2, unperm_h);
+    B2C_LAUNCH_CHECK("colsum_final_kernel");
+    return 0;
+  }
   int rs = (int)((rows + 255) / 256); if (rs > COLSUM_RS) rs = COLSUM_RS; if (rs < 1) rs = 1;
   colsum_partial_kernel<T><<<dim3(cdiv(cols, 32), rs), 256, 0, st>>>(A, rows, cols, ld, partial);
   B2C_LAUNCH_CHECK("colsum_partial_kernel");
@@ -713,7 +723,7 @@ int ln_bwd(cudaStream_t st, const TDY* dy, const float* dpool, int L, int O, con
 template <typename T>
 int colsum_vec(cudaStream_t st, T* A, const T* act, long rows, int cols, float inv_keep, float* partial, float* out) {
   const int gx = cdiv(cols, 256);
-  int rs = (int)((rows + 63) / 64); if (rs > 296 / gx) rs = 296 / gx; if (rs > COLSUM_RS) rs = COLSUM_RS; if (rs < 1) rs = 1;
+  int rs = (int)((rows + 31) / 32); if (rs > 592 / gx) rs = 592 / gx; if (rs > COLSUM_RS) rs = COLSUM_RS; if (rs < 1) rs = 1;
   dim3 grid(gx, rs);
   if (act) colsum_vec_kernel<T, true><<<grid, 256, 0, st>>>(A, act, rows, cols, inv_keep, partial);
   else colsum_vec_kernel<T, false><<<grid, 256, 0, st>>>(A, act, rows, cols, inv_keep, partial);

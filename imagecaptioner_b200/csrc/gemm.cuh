@@ -241,7 +241,13 @@ constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_EPI_BYTES = TC_EPI_WARPS * 32 * TC_EPI_PITCH;    // one 32-row staging tile per epilogue warp
 
 template <int BN> struct TcCfg {
-  static constexpr int STAGES = BN == 256 ? 3 : 4;      // 48 KB stages at BN = 256: three fit beside the epilogue staging
+#ifndef B2C_STAGES64
+#define B2C_STAGES64 4
+#endif
+#ifndef B2C_STAGES128
+#define B2C_STAGES128 4
+#endif
+  static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? B2C_STAGES128 : B2C_STAGES64);      // 48 KB stages at BN = 256: three fit beside the epilogue staging
   static constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   static constexpr uint32_t STAGE_BYTES = TC_A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (128 / 256 / 512 columns)

@@ -239,7 +239,30 @@ colsum_vec_kernel(T* __restrict__ A, const T* __restrict__ act, long rows, int c
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (ch < nch) {
-    for (long r = r0 + ry; r < r1; r += 8) {
+    long r = r0 + ry;
+    // four independent 16-byte row loads in flight per thread (the one-row-at-a-time loop was a chain of L2 / HBM round trips:
+    // 68 us for the 42 MB gate-gradient matrix = 0.6 TB/s, on the branch that ends the step; profiles/README.md round 2)
+    for (; r + 24 < r1; r += 32) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Vec8<T>::load(A + (r + 8 * u) * cols + ch * 8, v[u]);
+      if (RELU_BWD) {
+        float a[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) Vec8<T>::load(act + (r + 8 * u) * cols + ch * 8, a[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = a[u][j] > 0.f ? v[u][j] * inv_keep : 0.f;
+          Vec8<T>::store(A + (r + 8 * u) * cols + ch * 8, v[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
+    }
+    for (; r < r1; r += 8) {
       float v[8];
       Vec8<T>::load(A + r * cols + ch * 8, v);
       if (RELU_BWD) {
