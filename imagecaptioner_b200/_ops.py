@@ -100,7 +100,7 @@ SYMBOLS = {
     "b2c_greedy_decode": (ctypes.c_int, [_SHP, _PRM, _vp, _i64, _i64, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_attention_step": (ctypes.c_int, [_SHP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_refinement_forward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CRefineParams), _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
-    "b2c_refinement_backward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CRefineParams), _vp, ctypes.POINTER(B2CRefineGrads), _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
+    "b2c_refinement_backward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CRefineParams), _vp, _vp, ctypes.POINTER(B2CRefineGrads), _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_projector_forward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CProjParams), _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_projector_backward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CProjParams), _vp, ctypes.POINTER(B2CProjGrads), _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_count_valid": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
@@ -642,25 +642,25 @@ class RefinementFunction(torch.autograd.Function):
         xf = x.detach().to(torch.float32).contiguous()
         master = _master(params)
         ws = torch.empty(workspace_bytes(shape, code, B2C_WS_REFINE), dtype=torch.uint8, device=x.device)
-        out = torch.empty(B, S, E, dtype=compute_dtype, device=x.device)
+        out = torch.empty(B, S, E, dtype=torch.float32, device=x.device)      # fp32 residual stream in both modes
         prm = _fill_flat(B2CRefineParams(), master)
         drop = _dropout(dropout_p, seed, opts)
         _check(lib.b2c_refinement_forward(ctypes.byref(shape), ctypes.byref(prm), xf.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
                                           code, ctypes.byref(drop), _stream()), "b2c_refinement_forward")
-        ctx.b2c = (shape, code, drop, ws, master, x.dtype, [p.dtype for p in params], compute_dtype, opts)
+        ctx.b2c = (shape, code, drop, ws, master, x.dtype, [p.dtype for p in params], xf, opts)
         ctx.b2c_params = params
         return out
 
     @staticmethod
     def backward(ctx, dout):
         lib = load_library()
-        shape, code, drop, ws, master, x_dtype, pdtypes, cdt, opts = ctx.b2c
-        dout = dout.to(cdt).contiguous()
+        shape, code, drop, ws, master, x_dtype, pdtypes, xf, opts = ctx.b2c
+        dout = dout.to(torch.float32).contiguous()
         grads, _ = _grad_buffers(ctx.b2c_params, master, opts)
         dx = torch.empty(shape.B, shape.S, shape.E, dtype=torch.float32, device=dout.device)
         prm = _fill_flat(B2CRefineParams(), master)
         grd = _fill_flat(B2CRefineGrads(), grads)
-        _check(lib.b2c_refinement_backward(ctypes.byref(shape), ctypes.byref(prm), dout.data_ptr(), ctypes.byref(grd), dx.data_ptr(),
+        _check(lib.b2c_refinement_backward(ctypes.byref(shape), ctypes.byref(prm), xf.data_ptr(), dout.data_ptr(), ctypes.byref(grd), dx.data_ptr(),
                                            ws.data_ptr(), ws.numel(), code, ctypes.byref(drop), _stream()), "b2c_refinement_backward")
         grads = [g if g.dtype == dt else g.to(dt) for g, dt in zip(grads, pdtypes)]
         return (dx if x_dtype == torch.float32 else dx.to(x_dtype), None, None, None, None, None, *grads)

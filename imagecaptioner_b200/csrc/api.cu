@@ -669,6 +669,7 @@ template <typename T> struct RefineWs {
   T *x, *qkv, *probs, *attn, *proj, *x1, *f1, *f2;               // forward saves
   float *mean1, *rstd1, *mean2, *rstd2;
   T *dz2, *df1, *dz1, *dattn, *dqkv; float *dz1f, *lnpart, *partial;
+  float *x1f, *dz2f;                                              // fp32 residual stream: LN1's output, and its gradient
   size_t bytes;
   void carve(void* base, const B2CShape& s) {
     Carver c{reinterpret_cast<unsigned char*>(base), 0};
@@ -679,6 +680,7 @@ template <typename T> struct RefineWs {
     mean1 = c.take<float>(R); rstd1 = c.take<float>(R); mean2 = c.take<float>(R); rstd2 = c.take<float>(R);
     dz2 = c.take<T>(R * E); df1 = c.take<T>(R * 2 * E); dz1 = c.take<T>(R * E); dattn = c.take<T>(R * E); dqkv = c.take<T>(R * 3 * E);
     dz1f = c.take<float>(R * E); lnpart = c.take<float>((size_t)LN_GRID * 3 * E); partial = c.take<float>((size_t)COLSUM_RS * 3 * E);
+    x1f = c.take<float>(R * E); dz2f = c.take<float>(R * E);
     bytes = align_up(c.off, 256);
   }
 };
@@ -693,23 +695,23 @@ int check_refine_shape(const B2CShape* s) {
   return 0;
 }
 
-template <typename TX, typename TY>
-int ln_fwd(cudaStream_t st, const TX* x, const TX* res, const float* g, const float* b, TY* y, float* mean, float* rstd, long R, int E) {
+template <typename TX, typename TR, typename TY>
+int ln_fwd(cudaStream_t st, const TX* x, const TR* res, const float* g, const float* b, TY* y, float* y32, float* mean, float* rstd, long R, int E) {
   long grid = (R + 7) / 8; if (grid > 148 * 8) grid = 148 * 8;
-  if (E <= 256) ln_fwd_kernel<TX, TY, 1><<<(unsigned)grid, LN_THREADS, 0, st>>>(x, res, g, b, y, mean, rstd, R, E, 1e-5f);
-  else ln_fwd_kernel<TX, TY, 2><<<(unsigned)grid, LN_THREADS, 0, st>>>(x, res, g, b, y, mean, rstd, R, E, 1e-5f);
+  if (E <= 256) ln_fwd_kernel<TX, TR, TY, 1><<<(unsigned)grid, LN_THREADS, 0, st>>>(x, res, g, b, y, y32, mean, rstd, R, E, 1e-5f);
+  else ln_fwd_kernel<TX, TR, TY, 2><<<(unsigned)grid, LN_THREADS, 0, st>>>(x, res, g, b, y, y32, mean, rstd, R, E, 1e-5f);
   B2C_LAUNCH_CHECK("ln_fwd_kernel");
   return 0;
 }
 // LayerNorm backward; dy is a tensor (dpool == nullptr) or pooled window gradients (projector).  dbias_prev (optional) receives
 // the column sums of dz = the bias gradient of the Linear whose output entered the LayerNorm.
-template <typename TX, typename TDY, typename TDZ>
-int ln_bwd(cudaStream_t st, const TDY* dy, const float* dpool, int L, int O, const TX* x, const TX* res, const float* mean, const float* rstd,
+template <typename TX, typename TR, typename TDY, typename TDZ>
+int ln_bwd(cudaStream_t st, const TDY* dy, const float* dpool, int L, int O, const TX* x, const TR* res, const float* mean, const float* rstd,
            const float* gamma, TDZ* dz, float* dz32, float* part, float* dgamma, float* dbeta, float* dbias_prev, long R, int E) {
   long grid = (R + 7) / 8; if (grid > LN_GRID) grid = LN_GRID;
   const size_t smem = (size_t)(LN_THREADS / 32) * 3 * E * 4;
-#define B2C_LNB(POOLED, NC) do { B2C_TRY(set_smem(ln_bwd_kernel<TX, TDY, TDZ, POOLED, NC>, smem)); \
-    ln_bwd_kernel<TX, TDY, TDZ, POOLED, NC><<<(unsigned)grid, LN_THREADS, smem, st>>>(dy, dpool, L, O, x, res, mean, rstd, gamma, dz, dz32, part, R, E); } while (0)
+#define B2C_LNB(POOLED, NC) do { B2C_TRY(set_smem(ln_bwd_kernel<TX, TR, TDY, TDZ, POOLED, NC>, smem)); \
+    ln_bwd_kernel<TX, TR, TDY, TDZ, POOLED, NC><<<(unsigned)grid, LN_THREADS, smem, st>>>(dy, dpool, L, O, x, res, mean, rstd, gamma, dz, dz32, part, R, E); } while (0)
   if (dpool) { if (E <= 256) B2C_LNB(true, 1); else B2C_LNB(true, 2); }
   else { if (E <= 256) B2C_LNB(false, 1); else B2C_LNB(false, 2); }
 #undef B2C_LNB
@@ -755,7 +757,7 @@ template <> inline bool mha_use_mma<bf16>(int S, int hd) {
 }
 
 template <typename T>
-int refinement_forward_impl(const B2CShape& s, const B2CRefineParams& p, const float* x, T* out, void* ws, size_t ws_bytes,
+int refinement_forward_impl(const B2CShape& s, const B2CRefineParams& p, const float* x, float* out, void* ws, size_t ws_bytes,
                             const B2CDropout& dr, cudaStream_t st) {
   RefineWs<T> W; W.carve(ws, s);
   B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
@@ -776,19 +778,21 @@ int refinement_forward_impl(const B2CShape& s, const B2CRefineParams& p, const f
     B2C_LAUNCH_CHECK("mha_fwd_kernel");
   }
   B2C_TRY((gemm<T, T>(st, (int)R, E, E, W.attn, E, 0, W.Wo, E, 0, W.proj, E, 0.f, p.out_b)));
-  B2C_TRY((ln_fwd<T, T>(st, W.x, W.proj, p.n1_w, p.n1_b, W.x1, W.mean1, W.rstd1, R, E)));
+  // The residual stream stays in fp32 in both modes (torch.autocast runs LayerNorm in fp32 too): LN1 takes the fp32 block input
+  // + the branch output and leaves x1 twice, in the compute type (operand of the FFN contractions) and in fp32 (residual of LN2).
+  B2C_TRY((ln_fwd<float, T, T>(st, x, W.proj, p.n1_w, p.n1_b, W.x1, W.x1f, W.mean1, W.rstd1, R, E)));
   B2C_TRY((gemm<T, T>(st, (int)R, 2 * E, E, W.x1, E, 0, W.W1, E, 0, W.f1, 2 * E, 0.f, p.ffn0_b, 1)));
   if (dr.p > 0.f) {
     dropout_inplace_kernel<T><<<ew_grid(R * 2 * E), 256, 0, st>>>(W.f1, R * 2 * E, dr.p, dr.seed, 201u, (const unsigned long long*)dr.seed_dev);
     B2C_LAUNCH_CHECK("dropout_inplace_kernel");
   }
   B2C_TRY((gemm<T, T>(st, (int)R, E, 2 * E, W.f1, 2 * E, 0, W.W2, 2 * E, 0, W.f2, E, 0.f, p.ffn3_b)));
-  B2C_TRY((ln_fwd<T, T>(st, W.x1, W.f2, p.n2_w, p.n2_b, out, W.mean2, W.rstd2, R, E)));
+  B2C_TRY((ln_fwd<float, T, float>(st, W.x1f, W.f2, p.n2_w, p.n2_b, (float*)nullptr, out, W.mean2, W.rstd2, R, E)));
   return 0;
 }
 
 template <typename T>
-int refinement_backward_impl(const B2CShape& s, const B2CRefineParams& p, const T* dout, const B2CRefineGrads& g, float* dx,
+int refinement_backward_impl(const B2CShape& s, const B2CRefineParams& p, const float* x, const float* dout, const B2CRefineGrads& g, float* dx,
                              void* ws, size_t ws_bytes, const B2CDropout& dr, cudaStream_t st) {
   RefineWs<T> W; W.carve(ws, s);
   B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
@@ -797,15 +801,16 @@ int refinement_backward_impl(const B2CShape& s, const B2CRefineParams& p, const 
   const long R = (long)B * S;
   const float inv_keep = dr.p > 0.f ? 1.0f / (1.0f - dr.p) : 1.0f;
   // out = LN2(x1 + f2);  f2 = f1 W2^T + b2  (its bias gradient = column sums of dz2, produced by the same kernel)
-  B2C_TRY((ln_bwd<T, T, T>(st, dout, nullptr, 0, 0, W.x1, W.f2, W.mean2, W.rstd2, p.n2_w, W.dz2, nullptr, W.lnpart, g.n2_w, g.n2_b, g.ffn3_b, R, E)));
+  // (fp32 residual stream: dout arrives in fp32, d(x1 + f2) leaves in the compute type for the contractions AND in fp32)
+  B2C_TRY((ln_bwd<float, T, float, T>(st, dout, nullptr, 0, 0, W.x1f, W.f2, W.mean2, W.rstd2, p.n2_w, W.dz2, W.dz2f, W.lnpart, g.n2_w, g.n2_b, g.ffn3_b, R, E)));
   B2C_TRY((gemm<T, float>(st, E, 2 * E, (int)R, W.dz2, E, 1, W.f1, 2 * E, 1, g.ffn3_w, 2 * E)));
   B2C_TRY((gemm<T, T>(st, (int)R, 2 * E, E, W.dz2, E, 0, W.W2, 2 * E, 1, W.df1, 2 * E)));
   // f1 = Drop(ReLU(x1 W1^T + b1)): mask in place + bias gradient in one pass
   B2C_TRY(colsum_vec<T>(st, W.df1, W.f1, R, 2 * E, inv_keep, W.partial, g.ffn0_b));
   B2C_TRY((gemm<T, float>(st, 2 * E, E, (int)R, W.df1, 2 * E, 1, W.x1, E, 1, g.ffn0_w, E)));
-  B2C_TRY((gemm<T, T>(st, (int)R, E, 2 * E, W.df1, 2 * E, 0, W.W1, E, 1, W.dz2, E, 1.f)));          // dz2 <- d(x1) = dz2 + df1 W1
+  B2C_TRY((gemm<T, float>(st, (int)R, E, 2 * E, W.df1, 2 * E, 0, W.W1, E, 1, W.dz2f, E, 1.f)));      // dz2f <- d(x1) = dz2 + df1 W1, accumulated in fp32
   // x1 = LN1(x + proj);  proj = attn Wo^T + bo
-  B2C_TRY((ln_bwd<T, T, T>(st, W.dz2, nullptr, 0, 0, W.x, W.proj, W.mean1, W.rstd1, p.n1_w, W.dz1, W.dz1f, W.lnpart, g.n1_w, g.n1_b, g.out_b, R, E)));
+  B2C_TRY((ln_bwd<float, T, float, T>(st, W.dz2f, nullptr, 0, 0, x, W.proj, W.mean1, W.rstd1, p.n1_w, W.dz1, W.dz1f, W.lnpart, g.n1_w, g.n1_b, g.out_b, R, E)));
   B2C_TRY((gemm<T, float>(st, E, E, (int)R, W.dz1, E, 1, W.attn, E, 1, g.out_w, E)));
   B2C_TRY((gemm<T, T>(st, (int)R, E, E, W.dz1, E, 0, W.Wo, E, 1, W.dattn, E)));
   if (mha_use_mma<T>(S, hd)) {
@@ -895,7 +900,7 @@ int projector_backward_impl(const B2CShape& s, const B2CProjParams& p, const flo
   const long R = (long)B * St;
   const float inv_keep = dr.p > 0.f ? 1.0f / (1.0f - dr.p) : 1.0f;
   // un-pool + LayerNorm backward in one pass (dy is rebuilt from the pooled gradient), then ReLU mask + bias gradient in one pass
-  B2C_TRY((ln_bwd<T, T, T>(st, (const T*)nullptr, dout, St, So, W.h, (const T*)nullptr, W.mean, W.rstd, p.ln_w, W.dh, nullptr, W.lnpart,
+  B2C_TRY((ln_bwd<T, T, T, T>(st, (const T*)nullptr, dout, St, So, W.h, (const T*)nullptr, W.mean, W.rstd, p.ln_w, W.dh, nullptr, W.lnpart,
                            g.ln_w, g.ln_b, nullptr, R, Es)));
   B2C_TRY(colsum_vec<T>(st, W.dh, W.h, R, Es, inv_keep, W.partial, g.b));
   B2C_TRY((gemm<T, float>(st, Es, Et, (int)R, W.dh, Es, 1, W.xb, Et, 1, g.w, Et)));
@@ -1101,26 +1106,26 @@ int b2c_attention_step(const B2CShape* shape, const float* attn_w, const float* 
   return set_err(B2C_EINVAL, "bad dtype %d", dtype);
 }
 
-int b2c_refinement_forward(const B2CShape* shape, const B2CRefineParams* params, const float* x, void* out,
+int b2c_refinement_forward(const B2CShape* shape, const B2CRefineParams* params, const float* x, float* out,
                            void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream) {
   B2C_TRY(check_refine_shape(shape)); B2C_TRY(check_device());
   B2C_CHECK_ARG(params && x && out && workspace, "NULL argument");
   const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0, nullptr};
   B2C_CHECK_ARG(dr.p >= 0.f && dr.p < 1.f, "dropout p=%f outside [0,1)", dr.p);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == B2C_F32) return refinement_forward_impl<float>(*shape, *params, x, (float*)out, workspace, ws_bytes, dr, st);
-  if (dtype == B2C_BF16) return refinement_forward_impl<bf16>(*shape, *params, x, (bf16*)out, workspace, ws_bytes, dr, st);
+  if (dtype == B2C_F32) return refinement_forward_impl<float>(*shape, *params, x, out, workspace, ws_bytes, dr, st);
+  if (dtype == B2C_BF16) return refinement_forward_impl<bf16>(*shape, *params, x, out, workspace, ws_bytes, dr, st);
   return set_err(B2C_EINVAL, "bad dtype %d", dtype);
 }
 
-int b2c_refinement_backward(const B2CShape* shape, const B2CRefineParams* params, const void* dout, const B2CRefineGrads* grads,
+int b2c_refinement_backward(const B2CShape* shape, const B2CRefineParams* params, const float* x, const float* dout, const B2CRefineGrads* grads,
                             float* dx, void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream) {
   B2C_TRY(check_refine_shape(shape)); B2C_TRY(check_device());
-  B2C_CHECK_ARG(params && dout && grads && dx && workspace, "NULL argument");
+  B2C_CHECK_ARG(params && x && dout && grads && dx && workspace, "NULL argument");
   const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0, nullptr};
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == B2C_F32) return refinement_backward_impl<float>(*shape, *params, (const float*)dout, *grads, dx, workspace, ws_bytes, dr, st);
-  if (dtype == B2C_BF16) return refinement_backward_impl<bf16>(*shape, *params, (const bf16*)dout, *grads, dx, workspace, ws_bytes, dr, st);
+  if (dtype == B2C_F32) return refinement_backward_impl<float>(*shape, *params, x, dout, *grads, dx, workspace, ws_bytes, dr, st);
+  if (dtype == B2C_BF16) return refinement_backward_impl<bf16>(*shape, *params, x, dout, *grads, dx, workspace, ws_bytes, dr, st);
   return set_err(B2C_EINVAL, "bad dtype %d", dtype);
 }
 

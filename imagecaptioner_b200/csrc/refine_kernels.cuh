@@ -26,8 +26,10 @@ __global__ void __launch_bounds__(256) cast_f32_kernel(const float* __restrict__
 constexpr int LN_THREADS = 256;
 constexpr int LN_MAXC = 2;          // kernels are templated on NC = ceil(E / 256) <= LN_MAXC chunks per lane
 
-template <typename TX, int NC>
-__device__ __forceinline__ void ln_load_row(const TX* x, const TX* res, long r, int E, int nch, int lane, float (&v)[NC][8], float& sum) {
+// x and res may differ in type: the residual stream of the refinement block is kept in fp32 also in bf16 mode (x = the fp32 block
+// input / the fp32 copy of LN1's output, res = the bf16 branch output), like torch.autocast does (LayerNorm runs in fp32 there).
+template <typename TX, typename TR, int NC>
+__device__ __forceinline__ void ln_load_row(const TX* x, const TR* res, long r, int E, int nch, int lane, float (&v)[NC][8], float& sum) {
   sum = 0.f;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -36,7 +38,7 @@ __device__ __forceinline__ void ln_load_row(const TX* x, const TX* res, long r, 
     for (int j = 0; j < 8; ++j) v[c][j] = 0.f;
     if (ch < nch) {
       Vec8<TX>::load(x + r * E + ch * 8, v[c]);
-      if (res) { float t[8]; Vec8<TX>::load(res + r * E + ch * 8, t);
+      if (res) { float t[8]; Vec8<TR>::load(res + r * E + ch * 8, t);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[c][j] += t[j]; }
 #pragma unroll
@@ -56,15 +58,15 @@ __device__ __forceinline__ void ln_stats(const float (&v)[NC][8], float sum, int
   rs = rsqrtf(warp_sum(q) / (float)E + eps);
 }
 
-// y = LN(x + res) * gamma + beta
-template <typename TX, typename TY, int NC>
+// y = LN(x + res) * gamma + beta   (y32: optional fp32 copy of y, the residual operand of the next LayerNorm)
+template <typename TX, typename TR, typename TY, int NC>
 __global__ void __launch_bounds__(LN_THREADS)
-ln_fwd_kernel(const TX* __restrict__ x, const TX* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ beta,
-              TY* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, long R, int E, float eps) {
+ln_fwd_kernel(const TX* __restrict__ x, const TR* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ beta,
+              TY* __restrict__ y, float* __restrict__ y32, float* __restrict__ mean, float* __restrict__ rstd, long R, int E, float eps) {
   const int lane = threadIdx.x & 31, wpb = LN_THREADS / 32, nch = E >> 3;
   for (long r = (long)blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += (long)gridDim.x * wpb) {
     float v[NC][8], sum, mu, rs;
-    ln_load_row<TX, NC>(x, res, r, E, nch, lane, v, sum);
+    ln_load_row<TX, TR, NC>(x, res, r, E, nch, lane, v, sum);
     ln_stats<NC>(v, sum, E, nch, lane, eps, mu, rs);
     if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
 #pragma unroll
@@ -75,7 +77,8 @@ ln_fwd_kernel(const TX* __restrict__ x, const TX* __restrict__ res, const float*
         Vec8<float>::load(gamma + ch * 8, g); Vec8<float>::load(beta + ch * 8, b);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = fmaf((v[c][j] - mu) * rs, g[j], b[j]);
-        Vec8<TY>::store(y + r * E + ch * 8, o);
+        if (y) Vec8<TY>::store(y + r * E + ch * 8, o);
+        if (y32) Vec8<float>::store(y32 + r * E + ch * 8, o);
       }
     }
   }
@@ -100,7 +103,7 @@ ln_pool_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, co
     for (int l = lo; l < hi; ++l) {
       const long r = b * L + l;
       float v[NC][8], sum, mu, rs;
-      ln_load_row<TX, NC>(x, (const TX*)nullptr, r, E, nch, lane, v, sum);
+      ln_load_row<TX, TX, NC>(x, (const TX*)nullptr, r, E, nch, lane, v, sum);
       ln_stats<NC>(v, sum, E, nch, lane, eps, mu, rs);
       if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
 #pragma unroll
@@ -127,10 +130,10 @@ ln_pool_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, co
 // dy comes either from `dy` or, for the projector (POOLED), from the pooled output gradient: dy[b,l,:] = sum over windows o
 // containing l of dpool[b,o,:] / len(o).  Per-CTA partial sums of dgamma = sum_r dy*xhat, dbeta = sum_r dy and (the bias
 // gradient of the Linear in front) sum_r dz go to part[(blockIdx, {0,1,2}, e)].
-template <typename TX, typename TDY, typename TDZ, bool POOLED, int NC>
+template <typename TX, typename TR, typename TDY, typename TDZ, bool POOLED, int NC>
 __global__ void __launch_bounds__(LN_THREADS, NC == 1 ? 3 : 2)
 ln_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ dpool, int L, int O,
-              const TX* __restrict__ x, const TX* __restrict__ res, const float* __restrict__ mean,
+              const TX* __restrict__ x, const TR* __restrict__ res, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, TDZ* __restrict__ dz, float* __restrict__ dz32,
               float* __restrict__ part, long R, int E) {
   extern __shared__ float ln_sm[];          // [wpb][3][E]
@@ -145,7 +148,7 @@ ln_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ dpool, int L
   for (long r = (long)blockIdx.x * wpb + warp; r < R; r += (long)gridDim.x * wpb) {
     const float mu = mean[r], rs = rstd[r];
     float v[NC][8], d[NC][8], sum;
-    ln_load_row<TX, NC>(x, res, r, E, nch, lane, v, sum);
+    ln_load_row<TX, TR, NC>(x, res, r, E, nch, lane, v, sum);
     int o_min = 0, o_max = -1; long bo = 0;
     if (POOLED) {
       const long b = r / L; const int l = (int)(r - b * L);

@@ -162,11 +162,13 @@ typedef struct B2CRefineParams {
 typedef struct B2CRefineGrads {
   float *in_w, *in_b, *out_w, *out_b, *ffn0_w, *ffn0_b, *ffn3_w, *ffn3_b, *n1_w, *n1_b, *n2_w, *n2_b;
 } B2CRefineGrads;
-/* x (B,S,E) fp32 -> out (B,S,E) [dtype].  dropout->p is the reference's 0.1 in training (attention probabilities and FFN), 0 in eval. */
-int b2c_refinement_forward(const B2CShape* shape, const B2CRefineParams* params, const float* x, void* out,
+/* x (B,S,E) fp32 -> out (B,S,E) fp32 in both modes: the residual stream (x, LN1's output, out) is carried in fp32 like torch.autocast
+ * does (LayerNorm runs in fp32 there); `dtype` selects the type of the contraction operands and of the branch activations.
+ * dropout->p is the reference's 0.1 in training (attention probabilities and FFN), 0 in eval. */
+int b2c_refinement_forward(const B2CShape* shape, const B2CRefineParams* params, const float* x, float* out,
                            void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream);
-/* dout (B,S,E) [dtype] -> grads (fp32, overwritten), dx (B,S,E) fp32. */
-int b2c_refinement_backward(const B2CShape* shape, const B2CRefineParams* params, const void* dout, const B2CRefineGrads* grads,
+/* x = the forward's input, dout (B,S,E) fp32 -> grads (fp32, overwritten), dx (B,S,E) fp32. */
+int b2c_refinement_backward(const B2CShape* shape, const B2CRefineParams* params, const float* x, const float* dout, const B2CRefineGrads* grads,
                             float* dx, void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream);
 
 /* ---- FeatureProjector: LN(Drop(ReLU(x W^T + b))) on the channel axis, then AdaptiveAvgPool1d over tokens St -> So.

@@ -151,20 +151,24 @@ def kd_loss(model, proj, batch, autocast_dtype: Optional[torch.dtype] = None):
     return _forward_loss(model, proj, batch, autocast_dtype, feats)[0]
 
 
-def kd_step(model, proj, batch, autocast_dtype: Optional[torch.dtype] = None, alpha=0.7, beta=0.2, gamma=0.1, temperature=4.0):
+def kd_step(model, proj, batch, autocast_dtype: Optional[torch.dtype] = None, alpha=0.7, beta=0.2, gamma=0.1, temperature=4.0,
+            loss_scale: float = 1.0):
     """The reference loop body (src/train_student_kd.py:262-288): forward + projector + loss under autocast, then backward.
-    Returns what kd_oracle.kd_step returns (fp32 tensors on the model's device)."""
+    Returns what kd_oracle.kd_step returns (fp32 tensors on the model's device).
+    `loss_scale`: the loss is multiplied by it before backward and the gradients divided afterwards, like the reference's
+    GradScaler (:239, :288-291).  Without it the stock reduced-precision path LOSES most of the recurrent gradients at batch 512
+    (per-element gradients of a mean loss are ~1e-8: measured 75-96 % relative error under bf16 autocast, profiles/r2_bf16_parity.txt)."""
     dev = next(model.parameters()).device
     model.zero_grad(set_to_none=True)
     proj.zero_grad(set_to_none=True)
     feats = batch["encoder_features"].to(dev).clone().requires_grad_(True)
     total, parts, y, hs, ws, tproj = _forward_loss(model, proj, batch, autocast_dtype, feats, alpha, beta, gamma, temperature)
-    total.backward()
-    f32 = lambda t: t.detach().float()
+    (total * loss_scale).backward()
+    f32 = lambda t: t.detach().float() / loss_scale
     return {
         "loss": {k: float(v.detach()) for k, v in parts.items()},
         "grads": {k: f32(v.grad) for k, v in model.named_parameters() if v.grad is not None},
         "proj_grads": {k: f32(v.grad) for k, v in proj.named_parameters() if v.grad is not None},
-        "d_encoder_features": f32(feats.grad), "logits": f32(y), "hidden_states": f32(torch.stack(list(hs))),
-        "attention_weights": f32(torch.stack(list(ws))), "teacher_projected": f32(tproj),
+        "d_encoder_features": f32(feats.grad), "logits": y.detach().float(), "hidden_states": torch.stack(list(hs)).detach().float(),
+        "attention_weights": torch.stack(list(ws)).detach().float(), "teacher_projected": tproj.detach().float(),
     }

@@ -124,26 +124,28 @@ def autocast_reference_errors(params, proj_params, meta, batch, ref, device, aut
     from oracle import eager_torch as ET
     Et = batch["teacher_features"].shape[-1]
     model, proj = ET.build(params, proj_params, meta["V"], meta["E"], meta["H"], meta["L"], use_refinement, Et, batch["encoder_features"].shape[1], device)
-    got = ET.kd_step(model, proj, batch, autocast_dtype, meta.get("alpha", 0.7), meta.get("beta", 0.2), meta.get("gamma", 0.1), meta.get("temperature", 4.0))
+    # with the reference's own loss scaling (GradScaler's initial 2^16): un-scaled, the stock path drops most of the recurrent
+    # gradients at batch 512 (see eager_torch.kd_step), which would make the yardstick meaningless
+    got = ET.kd_step(model, proj, batch, autocast_dtype, meta.get("alpha", 0.7), meta.get("beta", 0.2), meta.get("gamma", 0.1), meta.get("temperature", 4.0),
+                     loss_scale=65536.0)
     return step_errors(got, ref, metric)
 
 
-# Gradients of the Linear layers that sit directly behind a ReLU.  In reduced precision a few pre-activations change sign; each flipped
-# mask element adds or removes a whole term of the gradient sum, and HOW MANY flip is a (roughly Poisson) random count that differs
-# between any two reduced-precision evaluations -- the native kernels and the autocast reference included.  Their error is compared
-# with the autocast reference's at 1.5x instead of 1.2x (measured at BASELINE config 1: kernel 4.9e-2 vs reference 3.6e-2 on
-# output_projection.0.weight, while 30 of the other 33 gradients are 1.5-9x MORE accurate in the kernels than under autocast).
+# Gradients of the Linear layers that sit directly behind a ReLU: in reduced precision a few pre-activations change sign and each
+# flipped mask element adds or removes a whole term of the gradient sum, so these are the tensors whose bf16 error exceeds 2e-2 --
+# in the native kernels AND in the reference's own arithmetic under autocast, by the same amount (profiles/r2_bf16_parity.txt:
+# 2.9-4.4e-2 vs 2.9-4.5e-2 at BASELINE config 2).  They are held to the same 1.2x as everything else.
 RELU_GATED = ("grad:decoder.output_projection.0.weight", "grad:decoder.output_projection.0.bias",
               "grad:attention_refinement.ffn.0.weight", "grad:attention_refinement.ffn.0.bias",
               "pgrad:feature_projection.0.weight", "pgrad:feature_projection.0.bias")
 
 
-def compare_step_calibrated(got, ref, ref_err, base_tol=2e-2, factor=1.2, metric="l2", verbose=True, gated_factor=1.5):
-    """Every quantity within max(base_tol, factor x the autocast reference's own error on the same inputs)."""
+def compare_step_calibrated(got, ref, ref_err, base_tol=2e-2, factor=1.2, metric="l2", verbose=True):
+    """Every quantity within max(base_tol, factor x the (loss-scaled) autocast reference's own error on the same inputs)."""
     rows = step_errors(got, ref, metric)
     bad = []
     for name, e in rows.items():
-        lim = max(base_tol, (gated_factor if name in RELU_GATED else factor) * ref_err.get(name, 0.0))
+        lim = max(base_tol, factor * ref_err.get(name, 0.0))
         flag = not e < lim
         if flag:
             bad.append((name, e, lim))
