@@ -5,6 +5,7 @@
 #include "loss_kernels.cuh"
 #include "decoder_kernels.cuh"
 #include "recurrent.cuh"
+#include "recur_cluster.cuh"
 #include "refine_kernels.cuh"
 #include "mha_mma.cuh"
 #include "optim_kernels.cuh"
@@ -100,6 +101,44 @@ int pack_params(const B2CShape& s, const B2CParams& p, const Weights<T>& w, cuda
   return 0;
 }
 
+// ------------------------------------------------------------------ cluster recurrence (recur_cluster.cuh): shapes and plan
+constexpr int CR_MAX_CLUSTERS = 16;
+inline bool cluster_shape_ok(const B2CShape& s) { return s.H == CR_H && s.E == CR_E && s.L == CR_L && s.S <= CR_SMAX && s.S >= 1; }
+inline bool cluster_enabled() {
+  static int on = -1;
+  // opt-in (B2C_CLUSTER=1): correct, but measured SLOWER than the per-step kernels on B200 (42 vs 31 us per step at B = 512): every
+  // cluster re-streams all 7.6 MB of recurrent weights per step and one SM cannot pull more than ~35 B/clk through TMA
+  // (tools/probe_ingest.cu, profiles/r2_cluster_recurrence.md)
+  if (on < 0) { const char* e = getenv("B2C_CLUSTER"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on != 0;
+}
+// clusters of 8 CTAs the device keeps resident at once (B200: 15); 0 if the query fails
+inline int cluster_max_active() {
+  static int n = -1;
+  if (n >= 0) return n;
+  n = 0;
+  if (cudaFuncSetAttribute(recur_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return n; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(CR_CL * CR_MAX_CLUSTERS); cfg.blockDim = dim3(CR_THREADS); cfg.dynamicSmemBytes = CR_SMEM_BYTES;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CR_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int m = 0;
+  if (cudaOccupancyMaxActiveClusters(&m, recur_cluster_fwd_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return n; }
+  if (const char* e = getenv("B2C_CLUSTER_MAX")) { const int lim = atoi(e); if (lim > 0 && lim < m) m = lim; }
+  n = m > CR_MAX_CLUSTERS ? CR_MAX_CLUSTERS : m;
+  return n;
+}
+// number of row slices (clusters) for batch B: every slice <= 40 rows and all clusters co-resident; 0 = shape not covered
+inline int cluster_plan(const B2CShape& s) {
+  if (!cluster_enabled() || !cluster_shape_ok(s)) return 0;
+  const int mx = cluster_max_active();
+  if (mx <= 0) return 0;
+  int ncl = cdiv(s.B, 32); if (ncl > mx) ncl = mx;
+  if (cdiv(s.B, ncl) > CR_RMAX) return 0;
+  return ncl;
+}
+
 // ------------------------------------------------------------------ workspaces
 template <typename T> struct TrainWs {
   Weights<T> w;
@@ -109,6 +148,7 @@ template <typename T> struct TrainWs {
   unsigned int* sync;                 // grid-barrier arrival counters of the persistent recurrence kernels (recurrent.cuh)
   float* EP;                          // e^{2P} (B, S, E) fp32: the attention phase of the persistent forward kernel streams it instead of P
   float* evalp;                       // (T*B, ceil(V/32), 8) partials of the validation epilogue of the vocabulary-head GEMM
+  T* G0T;                             // (T, ncl, 4H, 40): G0 re-laid out per row slice for the cluster recurrence kernel (recur_cluster.cuh)
   size_t bytes;
   void carve(void* base, const B2CShape& s) {
     Carver c{reinterpret_cast<unsigned char*>(base), 0};
@@ -134,6 +174,7 @@ template <typename T> struct TrainWs {
     sync = c.take<unsigned int>(128 + 160 * 32);         // four arrival-counter lines + one 128-byte flag line per CTA
     EP = c.take<float>(B * S * E);
     evalp = c.take<float>(TB * (size_t)cdiv(s.V, 32) * EVAL_PART_FLOATS);
+    G0T = c.take<T>(cluster_shape_ok(s) ? Tn * (size_t)CR_MAX_CLUSTERS * 4 * H * CR_RMAX : 0);
     bytes = align_up(c.off, 256);
   }
 };
@@ -350,6 +391,36 @@ int recur_forward<bf16>(cudaStream_t st, const B2CShape& s, const RecurPlan& pl,
   return 0;
 }
 
+// ------------------------------------------------------------------ cluster forward recurrence (recur_cluster.cuh)
+template <typename T> int cluster_forward(cudaStream_t, const B2CShape&, int, const TrainWs<T>&, const T*, T*, float*) {
+  return set_err(B2C_EINVAL, "the cluster recurrence kernel is bf16 only");
+}
+template <>
+int cluster_forward<bf16>(cudaStream_t st, const B2CShape& s, int ncl, const TrainWs<bf16>& W, const bf16* feats, bf16* hid_top, float* attw) {
+  ClusterMaps maps; ClusterParams p{};
+  p.B = s.B; p.T = s.T; p.S = s.S; p.ncl = ncl;
+  p.P = W.P; p.EP = W.EP; p.F = feats; p.u = W.u; p.attw = attw; p.xh0 = W.xh[0]; p.xh1 = W.xh[1];
+  p.G0T = W.G0T; p.bias1 = W.w.bcat[1]; p.c0 = W.c[0]; p.c1 = W.c[1]; p.gates0 = W.gates[0]; p.gates1 = W.gates[1]; p.hid_top = hid_top;
+  p.trace = recur_trace_buffer((size_t)ncl * CR_CL * s.T * 8);
+  const long rows = (long)(s.T + 1) * s.B;
+  B2C_TRY(make_tmap_bf16(&maps.w0, W.w.Wcat[0], CR_E + CR_H, 4 * CR_H, CR_E + CR_H, 128));
+  B2C_TRY(make_tmap_bf16(&maps.w1, W.w.Wcat[1], 2 * CR_H, 4 * CR_H, 2 * CR_H, 128));
+  B2C_TRY(make_tmap_bf16(&maps.wh, W.w.Wh, CR_H, CR_E, CR_H, CR_UCOLS));
+  B2C_TRY(make_tmap_bf16(&maps.h0, W.xh[0], CR_E + CR_H, rows, CR_E + CR_H, CR_RMAX));
+  B2C_TRY(make_tmap_bf16(&maps.h1, W.xh[1], 2 * CR_H, rows, 2 * CR_H, CR_RMAX));
+  B2C_TRY(make_tmap_bf16(&maps.ctx, W.xh[0], CR_E + CR_H, rows, CR_E + CR_H, CR_SPC));
+  B2C_CUDA(cudaFuncSetAttribute(recur_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM_BYTES));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ncl * CR_CL); cfg.blockDim = dim3(CR_THREADS); cfg.dynamicSmemBytes = CR_SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = CR_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  B2C_CUDA(cudaLaunchKernelEx(&cfg, recur_cluster_fwd_kernel, maps, p));
+  B2C_LAUNCH_CHECK("recur_cluster_fwd_kernel");
+  recur_trace_state().grid = ncl * CR_CL; recur_trace_state().T = s.T;
+  return 0;
+}
+
 // ------------------------------------------------------------------ decoder forward (teacher forced)
 // Per step: u = q W_h^T  ->  attention (ctx lands in layer 0's operand)  ->  L fused gate-GEMM + cell kernels.
 // The feature-independent part of the forward: packed operands (bf16 copies, attention_combine folded into layer 0), embedding
@@ -369,6 +440,13 @@ int decoder_prepare_impl(const B2CShape& s, const B2CParams& p, const int64_t* c
   }
   // embedding half of layer 0's gate pre-activations for all steps:  G0 = emb (W_ih0 W_ce)^T + b_x
   B2C_TRY((gemm<T, T>(st, (int)TB, 4 * H, E, W.emb, E, 0, W.w.We, E, 0, W.G0, 4 * H, 0.f, W.w.bx)));
+  if constexpr (sizeof(T) == 2) {
+    // the cluster recurrence kernel reads the addend per gate row with the samples of a row slice contiguous
+    if (const int ncl = cluster_plan(s)) {
+      g0_cluster_layout_kernel<<<dim3(4 * H / 64, ncl, Tn), 256, 0, st>>>(reinterpret_cast<const bf16*>(W.G0), B, Tn, ncl, reinterpret_cast<bf16*>(W.G0T));
+      B2C_LAUNCH_CHECK("g0_cluster_layout_kernel");
+    }
+  }
   return 0;
 }
 
@@ -392,8 +470,14 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
   // bf16 mode: the whole T loop as ONE persistent cooperative kernel when the shape fits its plan (recurrent.cuh); the
   // per-step kernels below remain for fp32 parity mode, other shapes and B2C_PERSISTENT=0 (A/B)
   RecurPlan rplan{}; rplan.ok = false;
+  // first choice: independent 8-CTA clusters, one per row slice (recur_cluster.cuh); no inter-layer dropout in that kernel yet
+  int ncl = 0;
+  if (sizeof(T) == 2 && sp.ns == 1 && !(dr.p > 0.f)) ncl = cluster_plan(s);
+  if (ncl > 0) { B2C_TRY(cluster_forward<T>(st, s, ncl, W, feats, hid_top, attw)); rplan.ok = true; }
+  else {
   if (sizeof(T) == 2 && sp.ns == 1) rplan = recur_plan(s);
   if (rplan.ok) B2C_TRY(recur_forward<T>(st, s, rplan, W, feats, hid_top, attw, dr));
+  }
   for (int t = 0; t < (rplan.ok ? 0 : Tn); ++t) {
     for (int i = 0; i < sp.ns; ++i) {
       cudaStream_t ss = sp.st[i];

@@ -426,3 +426,14 @@ def test_logits_free_validation_matches_logits_path_and_oracle(V, B, T):
     assert torch.equal(pred_f.cpu().long()[clear], oracle_pred[clear])
     assert float((pred_f.cpu().long() == oracle_pred).float().mean()) > 0.9
     assert float((pred_f == pred_u).float().mean()) > 0.97
+
+
+def test_cluster_recurrence_kernel_matches_per_step_kernels():
+    """The opt-in cluster forward recurrence (csrc/recur_cluster.cuh, B2C_CLUSTER=1) against the per-step kernels on the same bf16 KD
+    step: every output and gradient within 2e-2 (L2) at batch sizes that give 1 cluster with idle CTAs (16), ragged 35-row slices with
+    an empty CTA (70 -> 3 clusters) and several clusters (240).  The switch is read once per process, hence the subprocesses."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "cluster_ab.py"), "16", "70", "240"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "cluster A/B: OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
