@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("B2C_LIB") or os.path.join(_HERE, "lib", "libb2c.so") 
 B2C_MAX_LAYERS = 4
 B2C_F32, B2C_BF16 = 0, 1
 B2C_WS_TRAIN, B2C_WS_DECODE, B2C_WS_ATTN, B2C_WS_REFINE, B2C_WS_PROJ = 0, 1, 2, 3, 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 B2C_BWD_DEFER_JOIN = 1
 
 c_f32p = ctypes.c_void_p
@@ -91,6 +91,7 @@ SYMBOLS = {
     "b2c_workspace_bytes": (_sz, [_SHP, ctypes.c_int, ctypes.c_int]),
     "b2c_decoder_forward": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_decoder_prepare": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _sz, ctypes.c_int, _vp]),
+    "b2c_decoder_set_initial_state": (ctypes.c_int, [_SHP, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_decoder_forward_eval": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_decoder_forward_prepared": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_decoder_backward": (ctypes.c_int, [_SHP, _PRM, _vp, _vp, _vp, _vp, _vp, _vp, _GRD, _vp, _vp, _sz, ctypes.c_int, _DRP, ctypes.c_int, _vp]),
@@ -305,7 +306,7 @@ class DecoderFunction(torch.autograd.Function):
     """LSTMDecoder.forward (reference src/student_model.py:205-256) as one C-ABI call each way."""
 
     @staticmethod
-    def forward(ctx, feats, captions, compute_dtype, dropout_p, seed, L, prepared, opts, *params):
+    def forward(ctx, feats, captions, compute_dtype, dropout_p, seed, L, prepared, opts, init_state, *params):
         lib = load_library()
         opts = _options(opts)
         _require_cuda(feats, "image_features")
@@ -327,10 +328,21 @@ class DecoderFunction(torch.autograd.Function):
             cap = captions.detach().to(device=feats.device, dtype=torch.int64).contiguous()
             ws = torch.empty(workspace_bytes(shape, code, B2C_WS_TRAIN), dtype=torch.uint8, device=feats.device)
             fwd = lib.b2c_decoder_forward
+        prm = _fill_struct(B2CParams(), master, L)
+        if init_state is not None:
+            # reference LSTMDecoder.forward(..., hidden=(h0, c0)): the split forward with the state written between its halves
+            h0, c0 = (t.detach().to(device=feats.device, dtype=torch.float32).contiguous() for t in init_state)
+            if tuple(h0.shape) != (L, B, H) or tuple(c0.shape) != (L, B, H):
+                raise ValueError(f"hidden must be (h0, c0) of shape {(L, B, H)}, got {tuple(h0.shape)} and {tuple(c0.shape)}")
+            if prepared is None:
+                _check(lib.b2c_decoder_prepare(ctypes.byref(shape), ctypes.byref(prm), cap.data_ptr(), ws.data_ptr(), ws.numel(), code, _stream()),
+                       "b2c_decoder_prepare")
+            _check(lib.b2c_decoder_set_initial_state(ctypes.byref(shape), h0.data_ptr(), c0.data_ptr(), ws.data_ptr(), ws.numel(), code, _stream()),
+                   "b2c_decoder_set_initial_state")
+            fwd = lib.b2c_decoder_forward_prepared
         logits = torch.empty(T, B, V, dtype=compute_dtype, device=feats.device)
         hid = torch.empty(T, B, H, dtype=compute_dtype, device=feats.device)
         attw = torch.empty(T, B, S, dtype=torch.float32, device=feats.device)
-        prm = _fill_struct(B2CParams(), master, L)
         drop = _dropout(dropout_p, seed, opts)
         _check(fwd(ctypes.byref(shape), ctypes.byref(prm), f.data_ptr(), cap.data_ptr(), logits.data_ptr(),
                    hid.data_ptr(), attw.data_ptr(), ws.data_ptr(), ws.numel(), code, ctypes.byref(drop), _stream()),
@@ -367,7 +379,7 @@ class DecoderFunction(torch.autograd.Function):
             opts.after_backward()
         grads = [g if g.dtype == dt else g.to(dt) for g, dt in zip(grads, pdtypes)]
         dfe = dfeats if feats_dtype == torch.float32 else dfeats.to(feats_dtype)
-        return (dfe, None, None, None, None, None, None, None, *grads)
+        return (dfe, None, None, None, None, None, None, None, None, *grads)
 
 
 def greedy_decode(feats: torch.Tensor, params: Sequence[torch.Tensor], L: int, max_len: int, start_id: int, end_id: int,

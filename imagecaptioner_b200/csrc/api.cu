@@ -450,6 +450,20 @@ int decoder_prepare_impl(const B2CShape& s, const B2CParams& p, const int64_t* c
   return 0;
 }
 
+template <typename T>
+int set_initial_state_impl(const B2CShape& s, const float* h0, const float* c0, void* ws, size_t ws_bytes, cudaStream_t st) {
+  TrainWs<T> W; W.carve(ws, s);
+  B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
+  for (int k = 0; k < s.L; ++k) {
+    const int in = in_dim(s, k);
+    // slot 0 of layer k's operand rows is [input_0 ; h_{-1}], slot 0 of its cell buffer is c_{-1}
+    initial_state_kernel<T><<<ew_grid((long)s.B * s.H), 256, 0, st>>>(h0 + (size_t)k * s.B * s.H, c0 + (size_t)k * s.B * s.H, s.B, s.H,
+                                                                     W.xh[k] + in, in + s.H, W.c[k]);
+    B2C_LAUNCH_CHECK("initial_state_kernel");
+  }
+  return 0;
+}
+
 struct EvalOut { const float* teacher; const int64_t* targets; float temperature; float* row_kl; float* row_ce; int* argmax; };
 
 template <typename T>
@@ -1127,6 +1141,16 @@ int b2c_decoder_prepare(const B2CShape* shape, const B2CParams* params, const in
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2C_F32) return decoder_prepare_impl<float>(*shape, *params, captions, workspace, ws_bytes, st);
   if (dtype == B2C_BF16) return decoder_prepare_impl<bf16>(*shape, *params, captions, workspace, ws_bytes, st);
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_decoder_set_initial_state(const B2CShape* shape, const float* h0, const float* c0, void* workspace, size_t ws_bytes,
+                                  int dtype, void* stream) {
+  B2C_TRY(check_shape(shape)); B2C_TRY(check_device());
+  B2C_CHECK_ARG(h0 && c0 && workspace, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) return set_initial_state_impl<float>(*shape, h0, c0, workspace, ws_bytes, st);
+  if (dtype == B2C_BF16) return set_initial_state_impl<bf16>(*shape, h0, c0, workspace, ws_bytes, st);
   return set_err(B2C_EINVAL, "bad dtype %d", dtype);
 }
 

@@ -56,6 +56,18 @@ __global__ void __launch_bounds__(256) embedding_scatter_add_kernel(const float*
   }
 }
 
+// caller-supplied initial LSTM state of one layer (reference src/student_model.py:205 `hidden`): h0 (B,H) fp32 -> the recurrent half of
+// the layer's step-0 operand rows (pitch ld), c0 (B,H) fp32 -> slot 0 of the cell buffer
+template <typename T>
+__global__ void __launch_bounds__(256) initial_state_kernel(const float* __restrict__ h0, const float* __restrict__ c0, int B, int H,
+                                                            T* __restrict__ h_rec, long ld, float* __restrict__ c_slot0) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)B * H; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / H; const int j = (int)(i - b * H);
+    h_rec[b * ld + j] = from_f<T>(h0[i]);
+    c_slot0[i] = c0[i];
+  }
+}
+
 // ======================================================================================
 // Kernel (1): one decode step of spatial attention for one sample per CTA.
 //   s_l = sum_e tanh(P[l,e] + u[e]);  w = softmax_l(s);  ctx[e] = sum_l w_l F[l,e]

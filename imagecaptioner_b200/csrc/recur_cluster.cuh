@@ -321,7 +321,10 @@ recur_cluster_fwd_kernel(const __grid_constant__ ClusterMaps maps, const __grid_
 #pragma unroll
     for (int k = 0; k < CR_L; ++k)
 #pragma unroll
-      for (int s = 0; s < CR_N / 4; ++s) cst[k][s] = 0.f;
+      for (int s = 0; s < CR_N / 4; ++s) {           // c_{-1}: slot 0 of the cell buffers (zeros, or the caller's initial state)
+        const int smp = 4 * s + q;
+        cst[k][s] = smp < n ? (k == 0 ? p.c0 : p.c1)[(long)(r0 + smp) * CR_H + unit] : 0.f;
+      }
     const long SE = (long)S * CR_E;
     // ---- prologue: e^{2P} of this CTA's samples (read back by this CTA only)
     for (int sm = 0; sm < nv; ++sm) {

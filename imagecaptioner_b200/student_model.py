@@ -161,12 +161,16 @@ class LSTMDecoder(nn.Module):
     def forward(self, image_features, captions, hidden=None, prepared=None):
         """image_features (B,S,E), captions (T,B) -> outputs (T,B,V), hidden_states [T x (B,H)], attention [T x (B,S)]."""
         if hidden is not None:
-            raise NotImplementedError("the b2c decoder starts from the zero state (the reference never passes `hidden`)")
+            # reference :205 / :219-222: (h0, c0), each (num_layers, B, hidden_size), seed the recurrence instead of init_hidden's zeros.
+            # The state is an input here, not a differentiable one (nothing in the reference passes it, let alone trains through it).
+            if any(getattr(t, "requires_grad", False) for t in hidden):
+                raise NotImplementedError("gradients with respect to the initial `hidden` state are not produced; pass detached tensors")
+            hidden = (hidden[0], hidden[1])
         p = self.dropout_p if self.training else 0.0
         self._step += 1
         seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * self._step) & 0xFFFFFFFFFFFFFFFF if p > 0 else 0
         logits, hid, attw = _ops.DecoderFunction.apply(image_features, captions, self._mode(), p, seed, self.num_layers, prepared,
-                                                       getattr(self, "b2c_options", None), *self._param_list())
+                                                       getattr(self, "b2c_options", None), hidden, *self._param_list())
         hidden_states = HiddenStateList(hid.unbind(0))
         hidden_states.stacked = hid
         return logits, hidden_states, list(attw.unbind(0))

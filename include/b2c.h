@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define B2C_ABI_VERSION 2
+#define B2C_ABI_VERSION 3
 #define B2C_MAX_LAYERS 4
 
 enum { B2C_OK = 0, B2C_EINVAL = -1, B2C_EARCH = -2, B2C_ECUDA = -3, B2C_ENOMEM = -4 };
@@ -125,6 +125,13 @@ int b2c_decoder_prepare(const B2CShape* shape, const B2CParams* params, const in
 int b2c_decoder_forward_prepared(const B2CShape* shape, const B2CParams* params, const void* feats, const int64_t* captions,
                         void* logits, void* hidden_top, float* attn_w, void* workspace, size_t ws_bytes,
                         int dtype, const B2CDropout* dropout, void* stream);
+
+/* LSTMDecoder.forward(image_features, captions, hidden) with a caller-supplied initial state (reference src/student_model.py:205,
+ * :219-222: `hidden` replaces init_hidden's zeros and seeds nn.LSTM at :243).  h0, c0: (L,B,H) fp32 on the device.  Call it between
+ * b2c_decoder_prepare (which writes the zero state) and b2c_decoder_forward_prepared, on the same stream as the latter; the backward
+ * then differentiates through the non-zero state (no gradient with respect to h0 / c0 is returned). */
+int b2c_decoder_set_initial_state(const B2CShape* shape, const float* h0, const float* c0, void* workspace, size_t ws_bytes,
+                                  int dtype, void* stream);
 
 /* Backward of b2c_decoder_forward.  dlogits (T,B,V) [dtype]; dhidden_top (T,B,H) [dtype] or NULL;
  * hidden_top / attn_w are the forward outputs.  out: grads (fp32, all fields), dfeats (B,S,E) fp32. */

@@ -151,18 +151,22 @@ def decoder_step(p: Dict[str, Tensor], feats: Tensor, emb_t: Tensor,
     return y, w
 
 
-def decoder_forward(p: Dict[str, Tensor], feats: Tensor, captions: Tensor, prefix: str = "decoder."):
-    """LSTMDecoder.forward (src/student_model.py:205-256), eval mode, hidden=None.
+def decoder_forward(p: Dict[str, Tensor], feats: Tensor, captions: Tensor, prefix: str = "decoder.", hidden=None):
+    """LSTMDecoder.forward (src/student_model.py:205-256), eval mode.
 
-    feats (B,S,E) refined features, captions (T,B) int64 ->
+    feats (B,S,E) refined features, captions (T,B) int64, hidden = None (zero state, :219-220) or (h0, c0) each (L,B,H) ->
     outputs (T,B,V), hidden_states list of T (B,H) (top layer), attention list of T (B,S).
     """
     T, B = captions.shape
     L = num_lstm_layers(p, prefix)
     H = p[prefix + "lstm.weight_hh_l0"].shape[1]
     emb = p[prefix + "embedding.weight"][captions]                         # (T,B,E)  :224
-    h = [feats.new_zeros(B, H) for _ in range(L)]                          # :167-171
-    c = [feats.new_zeros(B, H) for _ in range(L)]
+    if hidden is None:
+        h = [feats.new_zeros(B, H) for _ in range(L)]                      # :167-171
+        c = [feats.new_zeros(B, H) for _ in range(L)]
+    else:                                                                   # :205: the caller's (h0, c0) seeds nn.LSTM's state (:243)
+        h = [hidden[0][k].to(feats.dtype) for k in range(L)]
+        c = [hidden[1][k].to(feats.dtype) for k in range(L)]
     outs, hids, atts = [], [], []
     for t in range(T):
         y, w = decoder_step(p, feats, emb[t], h, c, prefix)

@@ -291,7 +291,7 @@ def test_decoder_prepare_split_is_bit_identical(dtype):
             p.grad = None
         f = feats.clone().requires_grad_(True)
         prepared = _ops.decoder_prepare(cap, S, dtype, L, plist) if split else None
-        logits, hid, attw = _ops.DecoderFunction.apply(f, cap, dtype, 0.0, 0, L, prepared, None, *plist)
+        logits, hid, attw = _ops.DecoderFunction.apply(f, cap, dtype, 0.0, 0, L, prepared, None, None, *plist)
         (logits.float() * w).sum().backward()
         torch.cuda.synchronize()
         outs.append([logits.detach().clone(), hid.detach().clone(), attw.clone(), f.grad.clone()] + [p.grad.clone() for p in plist])
@@ -301,7 +301,7 @@ def test_decoder_prepare_split_is_bit_identical(dtype):
         else:
             assert relerr(a, b) < 1e-6                     # backward: split-K reductions may add in a different order
     with pytest.raises(ValueError, match="prepared for"):
-        _ops.DecoderFunction.apply(feats[:4], cap[:, :4], dtype, 0.0, 0, L, _ops.decoder_prepare(cap, S, dtype, L, plist), None, *plist)
+        _ops.DecoderFunction.apply(feats[:4], cap[:, :4], dtype, 0.0, 0, L, _ops.decoder_prepare(cap, S, dtype, L, plist), None, None, *plist)
 
 
 def test_bleu1_kernel_matches_reference_fixture():

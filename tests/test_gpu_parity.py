@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import kd_oracle as O
-from tests.harness import (GOLDEN, autocast_reference_errors, build_student, compare_step, compare_step_calibrated, relerr, run_kd_step,
+from tests.harness import (GOLDEN, autocast_reference_errors, build_student, compare_step, compare_step_calibrated, relerr, relerr_l2, run_kd_step,
                            step_errors, to_device)
 
 pytestmark = pytest.mark.gpu
@@ -130,7 +130,7 @@ def test_training_mode_dropout_is_consistent():
     opts = _ops.CallOptions(seed_dev=counter)
 
     def fwd(f, seed=123):
-        return _ops.DecoderFunction.apply(f, cap, torch.float32, 0.3, seed, L, None, opts, *plist)
+        return _ops.DecoderFunction.apply(f, cap, torch.float32, 0.3, seed, L, None, opts, None, *plist)
     y1, h1, _ = fwd(feats); y2, _, _ = fwd(feats); y3, _, _ = fwd(feats, seed=124)
     assert torch.equal(y1, y2) and not torch.equal(y1, y3)
     # the device-side step counter (B2CDropout.seed_dev) changes the mask without touching the by-value seed: a CUDA graph, whose
@@ -437,3 +437,34 @@ def test_cluster_recurrence_kernel_matches_per_step_kernels():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "cluster_ab.py"), "16", "70", "240"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "cluster A/B: OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_decoder_forward_with_initial_hidden_state_matches_reference():
+    """LSTMDecoder.forward(image_features, captions, hidden=(h0, c0)) (reference src/student_model.py:205, :219-222): outputs, hidden
+    states, attention weights and every gradient against the REFERENCE's own run (tests/golden/hidden_init_case.pt, generator
+    oracle/pin_hidden.py), fp32 <= 1e-4; bf16 within 2e-2 (L2); with and without the split (prepared) forward."""
+    g = torch.load(os.path.join(GOLDEN, "hidden_init_case.pt"), weights_only=False)
+    m, ref = g["meta"], g["reference"]
+    model, _ = build_student(g["params"], {}, m["V"], m["E"], m["H"], m["L"], False, m["E"], DEV)
+    dec = model.decoder
+    cap = g["captions"].to(DEV)
+    hidden = (g["h0"].to(DEV), g["c0"].to(DEV))
+    for dtype, tol, metric in ((torch.float32, FP32_TOL, relerr), (torch.bfloat16, 2e-2, relerr_l2)):
+        for split in (False, True):
+            dec.compute_dtype = dtype
+            dec.zero_grad(set_to_none=True)
+            f = g["feats"].to(DEV).clone().requires_grad_(True)
+            prepared = dec.prepare(cap, m["S"]) if split else None
+            out, hids, atts = dec(f, cap, hidden, prepared=prepared)
+            (out.float() * g["dout"].to(DEV)).sum().backward()
+            assert metric(out.float().cpu(), ref["outputs"]) < tol
+            assert metric(torch.stack(list(hids)).float().cpu(), ref["hidden_states"]) < tol
+            assert metric(torch.stack(atts).float().cpu(), ref["attention_weights"]) < tol
+            assert metric(f.grad.float().cpu(), ref["d_feats"]) < tol
+            for k, v in ref["grads"].items():
+                got = dict(model.named_parameters())[k].grad.float().cpu()
+                assert metric(got, v) < (tol if dtype == torch.float32 else 4e-2), (k, str(dtype), metric(got, v))
+    with pytest.raises(NotImplementedError):
+        dec(g["feats"].to(DEV), cap, (hidden[0].clone().requires_grad_(True), hidden[1]))
+    with pytest.raises(ValueError):
+        dec(g["feats"].to(DEV), cap, (hidden[0][:1], hidden[1][:1]))

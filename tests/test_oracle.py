@@ -173,3 +173,20 @@ def test_stock_module_restatement_matches_oracle(case):
     # the autocast form runs on the CPU too (bf16): a finite, small but non-zero deviation
     errs16 = step_errors(ET.kd_step(model, proj, batch, torch.bfloat16), ref, metric="l2")
     assert 1e-4 < max(errs16.values()) < 0.5
+
+
+def test_oracle_decoder_forward_with_initial_hidden_state_matches_reference_fixture():
+    """oracle.decoder_forward(..., hidden=(h0, c0)) against the reference's own LSTMDecoder.forward(hidden=...) outputs
+    (tests/golden/hidden_init_case.pt, written by oracle/pin_hidden.py from the real reference module)."""
+    import os
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hidden_init_case.pt"), weights_only=False)
+    out, hids, atts = O.decoder_forward(g["params"], g["feats"], g["captions"], hidden=(g["h0"], g["c0"]))
+    ref = g["reference"]
+    assert float((out - ref["outputs"]).abs().max()) < 2e-5
+    assert float((torch.stack(hids) - ref["hidden_states"]).abs().max()) < 2e-5
+    assert float((torch.stack(atts) - ref["attention_weights"]).abs().max()) < 2e-5
+    # and the zero state is the default
+    z = torch.zeros_like(g["h0"])
+    a = O.decoder_forward(g["params"], g["feats"], g["captions"])[0]
+    b = O.decoder_forward(g["params"], g["feats"], g["captions"], hidden=(z, z))[0]
+    assert torch.equal(a, b)
