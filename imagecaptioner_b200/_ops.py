@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("B2C_LIB") or os.path.join(_HERE, "lib", "libb2c.so") 
 B2C_MAX_LAYERS = 4
 B2C_F32, B2C_BF16 = 0, 1
 B2C_WS_TRAIN, B2C_WS_DECODE, B2C_WS_ATTN, B2C_WS_REFINE, B2C_WS_PROJ = 0, 1, 2, 3, 4
-ABI_VERSION = 3
+ABI_VERSION = 4
 B2C_BWD_DEFER_JOIN = 1
 
 c_f32p = ctypes.c_void_p
@@ -98,6 +98,7 @@ SYMBOLS = {
     "b2c_bump_counter": (ctypes.c_int, [_vp, _vp]),
     "b2c_debug_recur_trace": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     "b2c_join_side_work": (ctypes.c_int, [_vp]),
+    "b2c_set_gemm_cta_limit": (ctypes.c_int, [ctypes.c_int32]),
     "b2c_greedy_decode": (ctypes.c_int, [_SHP, _PRM, _vp, _i64, _i64, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_attention_step": (ctypes.c_int, [_SHP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_refinement_forward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CRefineParams), _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
@@ -212,10 +213,14 @@ class CallOptions:
     after_backward  callable run right after b2c_decoder_backward is enqueued (same stream): GraphedKDStep records an event there
                     so the all-reduce of the decoder's gradient segment can start while the refinement backward still runs.
     seed_dev        int64 device tensor (1 element): the per-step dropout counter the kernels mix into the seed (B2CDropout.seed_dev),
-                    so CUDA-graph replays draw fresh masks."""
+                    so CUDA-graph replays draw fresh masks.
+    background_ctas ProjectorFunction.backward only: CTA budget of its contractions when it overlaps the decoder's reverse recurrence."""
 
-    def __init__(self, grad_dest=None, defer_join=False, after_backward=None, seed_dev=None):
+    def __init__(self, grad_dest=None, defer_join=False, after_backward=None, seed_dev=None, background_ctas=0):
         self.grad_dest, self.defer_join, self.after_backward, self.seed_dev = grad_dest, defer_join, after_backward, seed_dev
+        # > 0: the projector's backward runs as background work next to a latency-bound chain on another stream: its persistent GEMMs
+        # are confined to this many CTAs (b2c_set_gemm_cta_limit) so they cannot starve the chain of SMs
+        self.background_ctas = background_ctas
         self.join_pending = False      # set by DecoderFunction.backward when it deferred the join
 
 
@@ -713,8 +718,15 @@ class ProjectorFunction(torch.autograd.Function):
         grads, _ = _grad_buffers(ctx.b2c_params, master, opts)
         prm = _fill_flat(B2CProjParams(), master)
         grd = _fill_flat(B2CProjGrads(), grads)
-        _check(lib.b2c_projector_backward(ctypes.byref(shape), ctypes.byref(prm), dout.data_ptr(), ctypes.byref(grd), ws.data_ptr(), ws.numel(),
-                                          code, ctypes.byref(drop), _stream()), "b2c_projector_backward")
+        bg = int(getattr(opts, "background_ctas", 0) or 0)
+        if bg > 0:
+            _check(lib.b2c_set_gemm_cta_limit(bg), "b2c_set_gemm_cta_limit")
+        try:
+            _check(lib.b2c_projector_backward(ctypes.byref(shape), ctypes.byref(prm), dout.data_ptr(), ctypes.byref(grd), ws.data_ptr(), ws.numel(),
+                                              code, ctypes.byref(drop), _stream()), "b2c_projector_backward")
+        finally:
+            if bg > 0:
+                lib.b2c_set_gemm_cta_limit(0)
         grads = [g if g.dtype == dt else g.to(dt) for g, dt in zip(grads, pdtypes)]
         return (None, None, None, None, None, None, None, *grads)
 

@@ -537,6 +537,14 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
 
 
 
+// CTAs granted to persistent GEMMs that run on a side stream UNDER a recurrence (B2C_BG_CTAS, 0 = no limit; default 20 = the SMs the
+// chain's <= 128-CTA kernels leave free), and the number of time-step chunks in which the LSTM weight gradients are contracted under
+// the reverse recurrence instead of after it (B2C_WGRAD_CHUNKS, 0 = all after the loop).  Measured on B200, same box (KD step):
+// no cap 2.675 ms; cap 20 -> 2.660; cap 20 + 2 / 4 / 5 chunks under the loop -> 2.666 / 2.857 / 3.07 ms (20 CTAs do not finish a chunk
+// before the next one is due, and the post-loop work queues behind them); cap 12 / 32 with 4 chunks -> 3.22 / 2.71 ms.
+inline int bg_ctas() { static int v = -1; if (v < 0) { const char* e = getenv("B2C_BG_CTAS"); v = e ? atoi(e) : 20; } return v; }
+inline int wgrad_chunks() { static int v = -1; if (v < 0) { const char* e = getenv("B2C_WGRAD_CHUNKS"); v = e ? atoi(e) : 0; } return v; }
+
 // ------------------------------------------------------------------ decoder backward (BPTT), oracle/manual_backward.py v2
 template <typename T>
 int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats, const int64_t* cap, const T* hid_top,
@@ -566,10 +574,13 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
   B2C_LAUNCH_CHECK("relu_bwd_inplace_kernel");
   B2C_CUDA(cudaEventRecord(hs->fork, st));
   B2C_CUDA(cudaStreamWaitEvent(side, hs->fork, 0));
-  B2C_TRY((gemm<T, float>(side, V, E, (int)TB, dlogits, V, 1, W.o1, E, 1, g.out3_w, E)));
-  B2C_TRY(colsum<T>(side, dlogits, TB, V, V, W.partial_side, g.out3_b));
-  B2C_TRY((gemm<T, float>(side, E, H, (int)TB, W.do1, E, 1, hid_top, H, 1, g.out0_w, H)));
-  B2C_TRY(colsum<T>(side, W.do1, TB, E, E, W.partial_side, g.out0_b));
+  {
+    GemmCapScope bg(bg_ctas());          // these run under the reverse recurrence: confined to the SMs the chain leaves free
+    B2C_TRY((gemm<T, float>(side, V, E, (int)TB, dlogits, V, 1, W.o1, E, 1, g.out3_w, E)));
+    B2C_TRY(colsum<T>(side, dlogits, TB, V, V, W.partial_side, g.out3_b));
+    B2C_TRY((gemm<T, float>(side, E, H, (int)TB, W.do1, E, 1, hid_top, H, 1, g.out0_w, H)));
+    B2C_TRY(colsum<T>(side, W.do1, TB, E, E, W.partial_side, g.out0_b));
+  }
   B2C_CUDA(cudaEventRecord(hs->join[MAX_SUB - 1], side));
   B2C_TRY((gemm<T, float>(st, (int)TB, H, E, W.do1, E, 0, W.w.W1, H, 1, W.dHext, H)));
   // ---- reverse time loop
@@ -592,6 +603,12 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
     B2C_TRY((gemm<T, float>(s2, 4 * H, H, K, W.dgates[0] + r0 * 4 * H, 4 * H, 1, W.xh[0] + r0 * (E + H) + E, E + H, 1, g.w_hh[0], H, beta, nullptr, 0, 1.f, H)));
     return 0;
   };
+  // LSTM weight gradients of the steps already traversed, contracted in chunks on the side stream while the loop goes on (capped
+  // grid, see gemm_cta_cap): the side branch that used to end ~70 us after the main chain is mostly done when the loop ends.
+  const int n_chunks = (sp.ns == 1 && bg_ctas() > 0) ? wgrad_chunks() : 0;
+  const int chunk_steps = n_chunks > 0 ? cdiv(Tn, n_chunks) : 0;
+  long wg_done_from = TB;              // rows [wg_done_from, TB) have been contracted
+  bool wg_any = false;
   pdl_full_dependency_next();        // the forward's saves (P, u, attention weights) are final before the reverse recurrence starts
   for (int t = Tn - 1; t >= 0; --t) {
     const bool last = (t == Tn - 1);
@@ -619,12 +636,20 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
       B2C_TRY(attn_bwd<T>(ss, Bh, S, E, W.P + b0 * S * E, feats + b0 * S * E, W.u + row * E, attw + row * S, dctx_t, (long)(E + H), W.ds + row * S, du_t));
       if (t > 0) B2C_TRY((gemm<T, T>(ss, Bh, H, E, du_t, E, 0, W.w.Wh, H, 1, W.dq + b0 * H, H)));
     }
+    if (chunk_steps > 0 && t > 0 && (Tn - t) % chunk_steps == 0 && t >= chunk_steps) {
+      // steps t .. t + chunk_steps - 1 are final (their dgates rows are written by the cell adjoints above)
+      B2C_CUDA(cudaEventRecord(hs->ev[0], st));
+      B2C_CUDA(cudaStreamWaitEvent(side, hs->ev[0], 0));
+      GemmCapScope bg(bg_ctas());
+      B2C_TRY(weight_grads(side, (long)t * B, wg_done_from, wg_any ? 1.f : 0.f));
+      wg_done_from = (long)t * B; wg_any = true;
+    }
   }
   B2C_TRY(join_subs(sp));
   // ---- post-loop.  Main stream: the chain the caller waits for (attn_post -> dF).  Side stream: every weight gradient.
   B2C_CUDA(cudaEventRecord(hs->ev[1], st));
   B2C_CUDA(cudaStreamWaitEvent(side, hs->ev[1], 0));
-  B2C_TRY(weight_grads(side, 0, TB, 0.f));
+  B2C_TRY(weight_grads(side, 0, wg_done_from, wg_any ? 1.f : 0.f));
   for (int k = 0; k < L; ++k) B2C_TRY(colsum<T>(side, W.dgates[k], TB, 4 * H, 4 * H, W.partial_side, g.b_ih[k], g.b_hh[k], H));
   {
     // layer 0 with attention_combine folded in:  dW_x = dg0^T ctx,  dW_e = dg0^T emb,  db_x = colsum(dg0)
@@ -1183,6 +1208,12 @@ int b2c_bump_counter(uint64_t* counter, void* stream) {
   B2C_CHECK_ARG(counter != nullptr, "NULL counter");
   bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(counter));
   B2C_LAUNCH_CHECK("bump_counter_kernel");
+  return 0;
+}
+
+int b2c_set_gemm_cta_limit(int32_t max_ctas) {
+  B2C_CHECK_ARG(max_ctas >= 0, "max_ctas=%d must be >= 0", max_ctas);
+  gemm_cta_cap() = max_ctas;
   return 0;
 }
 

@@ -820,6 +820,19 @@ inline int sm_count() {
   return n;
 }
 
+// Background contractions.  The tcgen05 GEMM is persistent: a CTA keeps its SM (160-220 KB of shared memory) until the kernel ends, so
+// a full-grid GEMM on a side stream starves a latency-bound chain on another stream even when that chain has the higher priority
+// (measured: the first four steps of the reverse recurrence took 83 / 65 / 63 / 50 us instead of 37 under the output head's weight
+// gradients).  The chain's own GEMMs never use more than 128 CTAs, so work issued as "background" is confined to `cap` CTAs (20 =
+// 148 - 128).  Thread-local and scoped: the issuing code sets it around its side-stream launches.
+inline int& gemm_cta_cap() { static thread_local int c = 0; return c; }
+struct GemmCapScope {
+  int saved;
+  explicit GemmCapScope(int cap) : saved(gemm_cta_cap()) { gemm_cta_cap() = cap; }
+  ~GemmCapScope() { gemm_cta_cap() = saved; }
+};
+inline int gemm_sms() { const int n = sm_count(), c = gemm_cta_cap(); return (c > 0 && c < n) ? c : n; }
+
 template <int BN, bool A_MN, bool B_MN, typename TC>
 int launch_tc(const GemmArgs& g, const TcPlan& plan, cudaStream_t st) {
   CUtensorMap ta, tb;
@@ -842,7 +855,7 @@ int launch_tc(const GemmArgs& g, const TcPlan& plan, cudaStream_t st) {
     B2C_CUDA(cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(TC), 0, (size_t)g.N * sizeof(TC), (size_t)g.M, st));
   const int tiles_m = cdiv(g.M, TC_BM), tiles_n = cdiv(g.N, BN);
   const long total = (long)tiles_m * tiles_n * splits;
-  const int grid = (int)(total < sm_count() ? total : sm_count());
+  const int grid = (int)(total < gemm_sms() ? total : gemm_sms());
   LstmEpi epi = g.lstm ? *g.lstm : LstmEpi{};
   if (g.amax) {
     B2C_CHECK_ARG(!g.lstm && splits == 1 && g.amax->pmax && g.amax->pidx, "argmax epilogue: no K split, no LSTM epilogue, partial buffers required");
@@ -875,7 +888,7 @@ int launch_tc_major(const GemmArgs& g, const TcPlan& plan, cudaStream_t st) {
 // bf16 operands on tensor cores; TC = bf16 or float output.
 template <typename TC>
 int gemm_bf16_tc(const GemmArgs& g, cudaStream_t st) {
-  const TcPlan plan = plan_tc(g, (int)sizeof(TC), sm_count());
+  const TcPlan plan = plan_tc(g, (int)sizeof(TC), gemm_sms());
   if (plan.bn == 256) return launch_tc_major<256, TC>(g, plan, st);
   if (plan.bn == 128) return launch_tc_major<128, TC>(g, plan, st);
   return launch_tc_major<64, TC>(g, plan, st);

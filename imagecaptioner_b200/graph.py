@@ -57,6 +57,7 @@ class GraphedKDStep:
         self._capturing = False
         self.high_priority_chain = os.environ.get("B2C_CHAIN_PRIORITY", "1") != "0"
         self.defer_weight_grad_join = os.environ.get("B2C_DEFER_JOIN", "1") != "0"
+        self.background_ctas = int(os.environ.get("B2C_BG_CTAS", "20"))       # CTA budget of GEMMs that overlap a recurrence (0 = no limit)
         # every trainable parameter here gets exactly one gradient per step from one native backward call, so the kernels may
         # write it directly into the flat all-reduce buffer (saves ~35 accumulate kernels + the buffer zeroing per step)
         self.direct_grads = direct_grads
@@ -126,6 +127,8 @@ class GraphedKDStep:
         early = self._capturing and self.overlap_comm and self._early is not None
         o.defer_join = self.defer_weight_grad_join and self.direct_grads and (not self._multi or early)
         o.after_backward = self._after_decoder_backward if early else None
+        # under capture the projector (forward and backward) lives on a side stream next to the decoder's recurrences
+        o.background_ctas = self.background_ctas if self._overlap else 0
         for m in self._modules():
             m.b2c_options = o
 

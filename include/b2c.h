@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define B2C_ABI_VERSION 3
+#define B2C_ABI_VERSION 4
 #define B2C_MAX_LAYERS 4
 
 enum { B2C_OK = 0, B2C_EINVAL = -1, B2C_EARCH = -2, B2C_ECUDA = -3, B2C_ENOMEM = -4 };
@@ -148,6 +148,12 @@ int b2c_decoder_backward(const B2CShape* shape, const B2CParams* params, const v
  * process-wide state besides the per-device stream / event set. */
 #define B2C_BWD_DEFER_JOIN 1
 int b2c_join_side_work(void* stream);
+
+/* Background hint for the CALLING THREAD's subsequent b2c calls: their tensor-core contractions use at most `max_ctas` CTAs
+ * (0 = no limit, the default).  The GEMM kernels are persistent -- a CTA keeps its SM until the kernel ends -- so a caller that
+ * overlaps one b2c call on a side stream with a latency-bound one on another stream (e.g. b2c_projector_backward next to the reverse
+ * recurrence of b2c_decoder_backward) wraps the background call in b2c_set_gemm_cta_limit(20) ... b2c_set_gemm_cta_limit(0). */
+int b2c_set_gemm_cta_limit(int32_t max_ctas);
 
 /* Batched greedy decode: every sample starts at start_id and steps shape->T (= max_len) times with its own
  * argmax fed back on the device (no host sync per token).  out: tokens (T,B) int64; lengths (B) int32 =
