@@ -56,12 +56,14 @@ int check_shape(const B2CShape* s) {
 // layer 0 (oracle/manual_backward.py v2):  Wcat[0] = [W_ih0 W_cc | W_hh0],  We = W_ih0 W_ce,  bx = W_ih0 b_c + b_ih0 + b_hh0.
 template <typename T> struct Weights {
   T *Wf, *Wh, *Wce, *Wcc, *W1, *W2, *Wih0, *We; T* Wcat[MAXL]; float* bcat[MAXL]; float* bx;
+  T* Wuh;      // [W_h ; W_hh of the top layer (interleaved rows)], (E + 4H) x H: both act on the top layer's h_{t-1}, one contraction
   void carve(Carver& c, const B2CShape& s) {
     Wf = c.take<T>((size_t)s.E * s.E); Wh = c.take<T>((size_t)s.E * s.H);
     Wce = c.take<T>((size_t)s.E * s.E); Wcc = c.take<T>((size_t)s.E * s.E);
     W1 = c.take<T>((size_t)s.E * s.H); W2 = c.take<T>((size_t)s.V * s.E);
     Wih0 = c.take<T>((size_t)4 * s.H * s.E); We = c.take<T>((size_t)4 * s.H * s.E); bx = c.take<float>((size_t)4 * s.H);
     for (int k = 0; k < s.L; ++k) { Wcat[k] = c.take<T>((size_t)4 * s.H * (in_dim(s, k) + s.H)); bcat[k] = c.take<float>((size_t)4 * s.H); }
+    Wuh = c.take<T>((size_t)(s.E + 4 * s.H) * s.H);
   }
 };
 
@@ -91,6 +93,8 @@ int pack_params(const B2CShape& s, const B2CParams& p, const Weights<T>& w, cuda
     add(p.w_hh[k], w.Wcat[k] + in, 4 * H, H, H, in + H, H);
     if (k > 0) add(p.b_ih[k], w.bcat[k], 4 * H, 1, 1, 1, H, p.b_hh[k], 1);
   }
+  add(p.attn_w, w.Wuh, E, H, H + E, H);
+  add(p.w_hh[s.L - 1], w.Wuh + (size_t)E * H, 4 * H, H, H, H, H);
   pack_params_kernel<T><<<dim3(96, tab.n), 256, 0, st>>>(tab);
   B2C_LAUNCH_CHECK("pack_params_kernel");
   // W_x = W_ih0 W_cc -> Wcat[0][:, :E];  W_e = W_ih0 W_ce;  b_x
@@ -149,6 +153,7 @@ template <typename T> struct TrainWs {
   float* EP;                          // e^{2P} (B, S, E) fp32: the attention phase of the persistent forward kernel streams it instead of P
   float* evalp;                       // (T*B, ceil(V/32), 8) partials of the validation epilogue of the vocabulary-head GEMM
   T* G0T;                             // (T, ncl, 4H, 40): G0 re-laid out per row slice for the cluster recurrence kernel (recur_cluster.cuh)
+  float* UR;                          // (B, E + 4H) fp32, one step: [u_t | W_hh h_{t-1} of the top layer] from the merged contraction
   size_t bytes;
   void carve(void* base, const B2CShape& s) {
     Carver c{reinterpret_cast<unsigned char*>(base), 0};
@@ -175,6 +180,7 @@ template <typename T> struct TrainWs {
     EP = c.take<float>(B * S * E);
     evalp = c.take<float>(TB * (size_t)cdiv(s.V, 32) * EVAL_PART_FLOATS);
     G0T = c.take<T>(cluster_shape_ok(s) ? Tn * (size_t)CR_MAX_CLUSTERS * 4 * H * CR_RMAX : 0);
+    UR = c.take<float>(B * (E + 4 * H));
     bytes = align_up(c.off, 256);
   }
 };
@@ -243,13 +249,15 @@ template <typename K> int set_smem(K kern, size_t bytes) {
 // Preconditions (see decoder_kernels.cuh): P and F are complete before the kernel that precedes this one in the stream
 // started -- callers issue pdl_full_dependency_next() once between the producers of P / F and that kernel.
 template <typename T>
-int attn_fwd(cudaStream_t st, const B2CShape& s, const float* P, const T* F, const float* u, T* ctx, long ldctx, float* attw) {
+int attn_fwd(cudaStream_t st, const B2CShape& s, const float* P, const T* F, const float* u, T* ctx, long ldctx, float* attw,
+             long ldu = 0, float* u_save = nullptr) {
+  if (ldu == 0) ldu = s.E;
   const size_t smem = (size_t)s.S * s.E * sizeof(T) + (size_t)(s.E + s.S) * 4;
   const int nq = cdiv(s.E / 4, 32);
   // E <= 256: 4 of the <= 7 token rows per warp are fetched in the prologue, the kernel fits 64 registers and all B = 512 CTAs
   // are resident in one wave (measured on B200: 3.23 ms / step vs 3.28 with all 7 rows up front at 80 registers, 3 CTAs / SM)
 #define B2C_ATT_(NQ, KA) do { B2C_TRY(set_smem(attn_step_fwd_kernel<T, NQ, KA>, smem)); \
-    B2C_CUDA(launch_pdl(attn_step_fwd_kernel<T, NQ, KA>, dim3(s.B), dim3(ATT_THREADS), smem, st, P, F, u, (long)s.E, s.S, s.E, ctx, ldctx, attw)); } while (0)
+    B2C_CUDA(launch_pdl(attn_step_fwd_kernel<T, NQ, KA>, dim3(s.B), dim3(ATT_THREADS), smem, st, P, F, u, ldu, s.S, s.E, ctx, ldctx, attw, u_save)); } while (0)
   if (nq == 1) B2C_ATT_(1, 4); else if (nq == 2) B2C_ATT_(2, 4); else if (nq == 3) B2C_ATT_(3, ATT_MAXTOK); else B2C_ATT_(0, ATT_MAXTOK);
 #undef B2C_ATT_
   B2C_LAUNCH_CHECK("attn_step_fwd_kernel");
@@ -273,14 +281,16 @@ int attn_bwd(cudaStream_t st, int B, int S, int E, const float* P, const T* F, c
 template <typename T>
 int lstm_layer_fwd(cudaStream_t st, const B2CShape& s, const Weights<T>& w, int k, const T* xh_t, const T* addend,
                    const float* c_prev, float* c_out, T* gates_out, T* h_rec, T* h_next, T* h_top,
-                   const B2CDropout& dr, long row_base) {
+                   const B2CDropout& dr, long row_base, const float* rec32 = nullptr, long ld_rec32 = 0) {
   const int in = in_dim(s, k), ld = in + s.H;
   LstmEpi le{};
+  le.addend32 = rec32; le.ld_addend32 = ld_rec32;
   le.enabled = 1; le.H = s.H; le.addend = addend; le.bias = (k == 0) ? nullptr : w.bcat[k];     // layer 0: b_x is inside the addend
   le.c_prev = c_prev; le.c_out = c_out; le.gates_out = gates_out;
   le.h_rec = h_rec; le.ld_rec = ld; le.h_next = h_next; le.ld_next = 2 * s.H; le.h_top = h_top; le.ld_top = s.H;
   le.drop_p = dr.p; le.seed = dr.seed; le.site = (unsigned)k; le.row_base = row_base; le.seed_dev = (const unsigned long long*)dr.seed_dev;
-  return gemm_lstm<T>(st, s.B, s.H, ld, xh_t, ld, w.Wcat[k], ld, le);
+  // rec32 != null: the recurrent half W_hh h_{t-1} is already in rec32, only the input half (K = in) is contracted here
+  return gemm_lstm<T>(st, s.B, s.H, rec32 ? in : ld, xh_t, ld, w.Wcat[k], ld, le);
 }
 
 // ------------------------------------------------------------------ sub-batch streams
@@ -483,6 +493,7 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
   pdl_full_dependency_next();        // P / F are final before any kernel of the recurrence can start (attention prologues read them early)
   // bf16 mode: the whole T loop as ONE persistent cooperative kernel when the shape fits its plan (recurrent.cuh); the
   // per-step kernels below remain for fp32 parity mode, other shapes and B2C_PERSISTENT=0 (A/B)
+  static const bool merge_rec = []() { const char* e = getenv("B2C_MERGE_REC"); return !(e && e[0] == '0'); }();      // A/B switch
   RecurPlan rplan{}; rplan.ok = false;
   // first choice: independent 8-CTA clusters, one per row slice (recur_cluster.cuh); no inter-layer dropout in that kernel yet
   int ncl = 0;
@@ -500,15 +511,28 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
       const long row = (long)t * B + b0;                       // first row of this sub-batch at step t in a (T,B,.) buffer
       const T* q = W.xh[L - 1] + row * ldL + inL;
       float* u_t = W.u + row * E;
-      B2C_TRY((gemm<T, float>(ss, sh.B, E, H, q, ldL, 0, W.w.Wh, H, 0, u_t, E)));
-      B2C_TRY(attn_fwd<T>(ss, sh, W.P + b0 * S * E, feats + b0 * S * E, u_t, W.xh[0] + row * (E + H), E + H, attw + row * S));
+      // bf16 mode: W_h and the top layer's W_hh both act on the top layer's h_{t-1}, so ONE contraction [u_t | W_hh h_{t-1}] =
+      // h_{t-1} [W_h ; W_hh]^T (N = E + 4H: 144 tiles instead of 16 at the same per-CTA feed, so the same ~5.5 us) takes the
+      // recurrent half out of the top layer's gate GEMM: its K drops from in + H to in (393 -> 196 KB of TMA feed per CTA, the
+      // bound of that kernel).  The attention kernel writes the dense u_t the backward reads.
+      const bool merged = merge_rec && sizeof(T) == 2;
+      const long ldur = E + 4 * H;
+      float* ur = W.UR + b0 * ldur;
+      if (merged) {
+        B2C_TRY((gemm<T, float>(ss, sh.B, E + 4 * H, H, q, ldL, 0, W.w.Wuh, H, 0, ur, ldur)));
+        B2C_TRY(attn_fwd<T>(ss, sh, W.P + b0 * S * E, feats + b0 * S * E, ur, W.xh[0] + row * (E + H), E + H, attw + row * S, ldur, u_t));
+      } else {
+        B2C_TRY((gemm<T, float>(ss, sh.B, E, H, q, ldL, 0, W.w.Wh, H, 0, u_t, E)));
+        B2C_TRY(attn_fwd<T>(ss, sh, W.P + b0 * S * E, feats + b0 * S * E, u_t, W.xh[0] + row * (E + H), E + H, attw + row * S));
+      }
       for (int k = 0; k < L; ++k) {
         const int in = in_dim(s, k), ld = in + H;
+        const bool rec = merged && k == L - 1;
         B2C_TRY(lstm_layer_fwd<T>(ss, sh, W.w, k, W.xh[k] + row * ld, k == 0 ? W.G0 + row * 4 * H : (const T*)nullptr,
                                   W.c[k] + row * H, W.c[k] + (row + B) * H,
                                   W.gates[k] + row * 4 * H, W.xh[k] + (row + B) * ld + in,
                                   k + 1 < L ? W.xh[k + 1] + row * 2 * H : nullptr, k == L - 1 ? hid_top + row * H : nullptr,
-                                  dr, row));
+                                  dr, row, rec ? ur + E : nullptr, ldur));
       }
     }
   }

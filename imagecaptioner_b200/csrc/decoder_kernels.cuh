@@ -88,7 +88,8 @@ constexpr int ATT_MAXTOK = 7;     // tokens per warp held in registers (S <= 56 
 template <typename T, int NQ, int KA>  // NQ = float4 per lane per token (ceil(E/128)); 0 = generic loop.  KA = tokens per warp fetched in the prologue
 __global__ void __launch_bounds__(ATT_THREADS, KA >= ATT_MAXTOK ? 1 : 4)
 attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const float* __restrict__ u, long ldu,
-                     int S, int E, T* __restrict__ ctx, long ldctx, float* __restrict__ attw /* (B,S) or null */) {
+                     int S, int E, T* __restrict__ ctx, long ldctx, float* __restrict__ attw /* (B,S) or null */,
+                     float* __restrict__ u_save /* (B,E) or null: dense copy of u (a forward save when u sits inside a wider row) */) {
   extern __shared__ __align__(128) unsigned char att_smem[];
   const int SE = S * E;
   T* Fs = reinterpret_cast<T*>(att_smem);
@@ -125,7 +126,7 @@ attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
   }
   pdl_wait();
   // u is the only operand produced by the preceding kernel
-  for (int e = tid; e < E; e += ATT_THREADS) us[e] = __ldcg(u + (long)b * ldu + e);
+  for (int e = tid; e < E; e += ATT_THREADS) { const float uv = __ldcg(u + (long)b * ldu + e); us[e] = uv; if (u_save) u_save[(long)b * E + e] = uv; }
   __syncthreads();
   // scores: warp per token, lanes over E in float4 units
   auto score = [&](const float4 (&pv)[NQR], int l) {

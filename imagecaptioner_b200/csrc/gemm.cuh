@@ -35,6 +35,8 @@ struct LstmEpi {
   void* h_rec; long ld_rec; void* h_next; long ld_next; void* h_top; long ld_top;
   float drop_p; unsigned long long seed; unsigned int site; long row_base;
   const unsigned long long* seed_dev;   // optional device step counter mixed into the seed (CUDA-graph replays)
+  const float* addend32; long ld_addend32;   // optional fp32 addend (rows, >= 4H) with its own pitch: the recurrent half W_hh h_{t-1} of the
+                                        // pre-activations when it was contracted ahead of time (tcgen05 path only)
 };
 
 // Validation (validate_student_model, reference src/train_student_kd.py:29-86) needs, per logits row, only the token-KD term, the CE
@@ -395,7 +397,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool add_bias = (bias != nullptr) && (sp == 0);
     // LSTM epilogue: the operands that do not come from the MMA (bias, the time-batched addend, c_{t-1}) of this warp's first 32
     // columns are fetched BEFORE waiting for the accumulator, so their L2 latency runs under the main loop.
-    [[maybe_unused]] float4 pre_b[8]; [[maybe_unused]] uint4 pre_a[4]; [[maybe_unused]] float4 pre_c0, pre_c1;
+    [[maybe_unused]] float4 pre_b[8]; [[maybe_unused]] uint4 pre_a[4]; [[maybe_unused]] float4 pre_c0, pre_c1; [[maybe_unused]] float4 pre_r[8];
     [[maybe_unused]] int pre_ci = -1;
     if constexpr (LSTM) {
       constexpr int NC32 = BN / 32, C32_PER = (NC32 + 1) / 2;
@@ -410,6 +412,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(le.addend) + (long)grow * N + col0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) pre_a[j] = ap[j];
+        }
+        if (le.addend32) {
+          const float4* rp = reinterpret_cast<const float4*>(le.addend32 + (long)grow * le.ld_addend32 + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pre_r[j] = __ldcg(rp + j);
         }
         pre_c0 = *reinterpret_cast<const float4*>(le.c_prev + (long)grow * le.H + (col0 >> 2));
         pre_c1 = *reinterpret_cast<const float4*>(le.c_prev + (long)grow * le.H + (col0 >> 2) + 4);
@@ -447,6 +454,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint4 a = pre ? pre_a[j] : ap[j];
               v[j * 8 + 0] += bf16_lo(a.x); v[j * 8 + 1] += bf16_hi(a.x); v[j * 8 + 2] += bf16_lo(a.y); v[j * 8 + 3] += bf16_hi(a.y);
               v[j * 8 + 4] += bf16_lo(a.z); v[j * 8 + 5] += bf16_hi(a.z); v[j * 8 + 6] += bf16_lo(a.w); v[j * 8 + 7] += bf16_hi(a.w);
+            }
+          }
+          if (le.addend32) {
+            const float4* rp = reinterpret_cast<const float4*>(le.addend32 + (long)grow * le.ld_addend32 + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r4 = pre ? pre_r[j] : __ldcg(rp + j);
+              v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
             }
           }
           const int u0 = col0 >> 2;
