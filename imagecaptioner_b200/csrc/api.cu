@@ -561,12 +561,13 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
 
 
 
-// CTAs granted to persistent GEMMs that run on a side stream UNDER a recurrence (B2C_BG_CTAS, 0 = no limit; default 20 = the SMs the
-// chain's <= 128-CTA kernels leave free), and the number of time-step chunks in which the LSTM weight gradients are contracted under
+// CTAs granted to each persistent GEMM that runs on a side stream UNDER a recurrence (B2C_BG_CTAS, 0 = no limit; default 10: two side
+// streams -- this library's and the caller's projector backward -- share the 20 SMs the chain's <= 128-CTA kernels leave free), and the number of time-step chunks in which the LSTM weight gradients are contracted under
 // the reverse recurrence instead of after it (B2C_WGRAD_CHUNKS, 0 = all after the loop).  Measured on B200, same box (KD step):
 // no cap 2.675 ms; cap 20 -> 2.660; cap 20 + 2 / 4 / 5 chunks under the loop -> 2.666 / 2.857 / 3.07 ms (20 CTAs do not finish a chunk
 // before the next one is due, and the post-loop work queues behind them); cap 12 / 32 with 4 chunks -> 3.22 / 2.71 ms.
-inline int bg_ctas() { static int v = -1; if (v < 0) { const char* e = getenv("B2C_BG_CTAS"); v = e ? atoi(e) : 20; } return v; }
+// With the merged recurrent half (2.645 ms without a cap): cap 8 / 10 / 14 / 20 -> 2.628 / 2.626 / 2.648 / 2.634 ms.
+inline int bg_ctas() { static int v = -1; if (v < 0) { const char* e = getenv("B2C_BG_CTAS"); v = e ? atoi(e) : 10; } return v; }
 inline int wgrad_chunks() { static int v = -1; if (v < 0) { const char* e = getenv("B2C_WGRAD_CHUNKS"); v = e ? atoi(e) : 0; } return v; }
 
 // ------------------------------------------------------------------ decoder backward (BPTT), oracle/manual_backward.py v2

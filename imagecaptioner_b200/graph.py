@@ -57,7 +57,7 @@ class GraphedKDStep:
         self._capturing = False
         self.high_priority_chain = os.environ.get("B2C_CHAIN_PRIORITY", "1") != "0"
         self.defer_weight_grad_join = os.environ.get("B2C_DEFER_JOIN", "1") != "0"
-        self.background_ctas = int(os.environ.get("B2C_BG_CTAS", "20"))       # CTA budget of GEMMs that overlap a recurrence (0 = no limit)
+        self.background_ctas = int(os.environ.get("B2C_BG_CTAS", "10"))       # CTA budget of GEMMs that overlap a recurrence (0 = no limit)
         # every trainable parameter here gets exactly one gradient per step from one native backward call, so the kernels may
         # write it directly into the flat all-reduce buffer (saves ~35 accumulate kernels + the buffer zeroing per step)
         self.direct_grads = direct_grads
