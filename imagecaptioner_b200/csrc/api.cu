@@ -568,6 +568,7 @@ int decoder_forward_impl(const B2CShape& s, const B2CParams& p, const T* feats, 
 // before the next one is due, and the post-loop work queues behind them); cap 12 / 32 with 4 chunks -> 3.22 / 2.71 ms.
 // With the merged recurrent half (2.645 ms without a cap): cap 8 / 10 / 14 / 20 -> 2.628 / 2.626 / 2.648 / 2.634 ms.
 inline int bg_ctas() { static int v = -1; if (v < 0) { const char* e = getenv("B2C_BG_CTAS"); v = e ? atoi(e) : 10; } return v; }
+inline bool attn_post_occ3() { static int v = -1; if (v < 0) { const char* e = getenv("B2C_POST_OCC3"); v = (e && e[0] == '0') ? 0 : 1; } return v != 0; }
 inline int wgrad_chunks() { static int v = -1; if (v < 0) { const char* e = getenv("B2C_WGRAD_CHUNKS"); v = e ? atoi(e) : 0; } return v; }
 
 // ------------------------------------------------------------------ decoder backward (BPTT), oracle/manual_backward.py v2
@@ -706,8 +707,14 @@ int decoder_backward_impl(const B2CShape& s, const B2CParams& p, const T* feats,
     // 2 -> 2.79, 4 -> 2.79, 7 -> 2.81)
     const int splits = 1, per = cdiv(S, splits), TP = (Tn + 3) & ~3;
     const size_t psmem = (size_t)2 * per * TP * 4;
-    B2C_TRY(set_smem(attn_post_reg_kernel<T, 24>, psmem));          // > 48 KB only for very long token lists
-    attn_post_reg_kernel<T, 24><<<dim3(B, splits), ATT_THREADS, psmem, st>>>(W.P, W.u, W.dxh0, (long)(E + H), attw, W.ds, Tn, B, S, E, W.dP, dfeats);
+    if (Tn <= 20 && attn_post_occ3()) {        // u / dctx of 20 instead of 24 steps in registers: 64 registers, four CTAs per SM, all B = 512 CTAs in ONE wave
+                                               // (ncu: 52 % long-scoreboard stalls at 25 % occupancy; 85 -> 65 us, KD step 2.63 -> 2.61 ms)
+      B2C_TRY(set_smem(attn_post_reg_kernel<T, 20>, psmem));
+      attn_post_reg_kernel<T, 20><<<dim3(B, splits), ATT_THREADS, psmem, st>>>(W.P, W.u, W.dxh0, (long)(E + H), attw, W.ds, Tn, B, S, E, W.dP, dfeats);
+    } else {
+      B2C_TRY(set_smem(attn_post_reg_kernel<T, 24>, psmem));          // > 48 KB only for very long token lists
+      attn_post_reg_kernel<T, 24><<<dim3(B, splits), ATT_THREADS, psmem, st>>>(W.P, W.u, W.dxh0, (long)(E + H), attw, W.ds, Tn, B, S, E, W.dP, dfeats);
+    }
     B2C_LAUNCH_CHECK("attn_post_reg_kernel");
   } else {
     const size_t smem = (size_t)Tn * (2 * E + 2 * S) * 4;

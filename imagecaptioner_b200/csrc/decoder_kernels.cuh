@@ -335,7 +335,7 @@ attn_post_kernel(const float* __restrict__ P, const float* __restrict__ u /*(T,B
 // stored [token][step]) per four steps plus the MUFU math: ~10 instructions per (token, column, step) instead of ~24 with
 // the operands in shared memory.  grid (B, token splits): blockIdx.y owns a contiguous range of tokens.
 template <typename T, int TMAX>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, TMAX <= 20 ? 4 : 2)
 attn_post_reg_kernel(const float* __restrict__ P, const float* __restrict__ u /*(T,B,E)*/, const float* __restrict__ dctx /*(T,B,.) pitch lddctx*/, long lddctx,
                      const float* __restrict__ attw /*(T,B,S)*/, const float* __restrict__ ds /*(T,B,S)*/,
                      int Tn, int B, int S, int E, T* __restrict__ dP, float* __restrict__ dF) {
