@@ -7,16 +7,28 @@
 
 namespace b2c {
 
+__device__ __forceinline__ float4 ld_nc_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
 template <typename T>
 __global__ void __launch_bounds__(256) cast_f32_kernel(const float* __restrict__ in, T* __restrict__ out, long n) {
   const long n8 = ((((uintptr_t)in) % 16 == 0) && (((uintptr_t)out) % 16 == 0)) ? (n >> 3) : 0;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
-    const float4 a = reinterpret_cast<const float4*>(in)[2 * i], b = reinterpret_cast<const float4*>(in)[2 * i + 1];
-    T* o = out + i * 8;
+  const long stride = (long)gridDim.x * blockDim.x;
+  // two 8-element groups per thread and iteration, all four 16-byte loads issued before the stores
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += 2 * stride) {
+    const long i2 = i + stride;
+    const bool two = i2 < n8;
+    const float4 a = ld_nc_f4(reinterpret_cast<const float4*>(in) + 2 * i), b = ld_nc_f4(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+    float4 c = a, d = b;
+    if (two) { c = ld_nc_f4(reinterpret_cast<const float4*>(in) + 2 * i2); d = ld_nc_f4(reinterpret_cast<const float4*>(in) + 2 * i2 + 1); }
     if (sizeof(T) == 2) {
-      *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+      *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+      if (two) *reinterpret_cast<uint4*>(out + i2 * 8) = make_uint4(pack_bf16(c.x, c.y), pack_bf16(c.z, c.w), pack_bf16(d.x, d.y), pack_bf16(d.z, d.w));
     } else {
-      reinterpret_cast<float4*>(o)[0] = a; reinterpret_cast<float4*>(o)[1] = b;
+      reinterpret_cast<float4*>(out + i * 8)[0] = a; reinterpret_cast<float4*>(out + i * 8)[1] = b;
+      if (two) { reinterpret_cast<float4*>(out + i2 * 8)[0] = c; reinterpret_cast<float4*>(out + i2 * 8)[1] = d; }
     }
   }
   for (long i = n8 * 8 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) out[i] = from_f<T>(in[i]);
