@@ -5,10 +5,11 @@ reference (``/root/reference/src/student_model.py``), so ``train_student_kd.py``
 ``evaluate_student.py`` run unchanged and reference checkpoints load with ``load_state_dict``.
 What differs is the body of the hot path: ``LSTMDecoder.forward`` (reference :205-256) and the
 greedy loop of ``CaptioningStudent.caption_image`` (reference :314-381) are single calls into the
-hand-written sm_100a kernels behind ``include/b2c.h``.  The ResNet encoder and the (once per
-sequence) ``AttentionRefinement`` block keeps its parameters in the reference's stock submodules (same
-``state_dict`` keys) but computes through ``b2c_refinement_forward`` / ``_backward`` (SURVEY.md §8f row 1);
-only the ResNet encoder stays a stock ``torch.nn`` module — SURVEY.md §8 keeps it out of the path.
+hand-written sm_100a kernels behind ``include/b2c.h``.  The (once per sequence) ``AttentionRefinement``
+block keeps its parameters in the reference's stock submodules (same ``state_dict`` keys) but computes
+through ``b2c_refinement_forward`` / ``_backward``; only the ResNet encoder stays a
+stock ``torch.nn`` module — SURVEY.md §8 keeps it out of the path.  ``LSTMDecoder.forward`` also takes the
+reference's optional ``hidden=(h0, c0)`` initial state (``b2c_decoder_set_initial_state``).
 
 Precision mode of the decoder: bf16 (tcgen05 tensor-core tiles) when called under
 ``torch.autocast`` — the reference trains under fp16 autocast, ``train_student_kd.py:271`` — or when
