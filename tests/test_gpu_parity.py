@@ -468,3 +468,18 @@ def test_decoder_forward_with_initial_hidden_state_matches_reference():
         dec(g["feats"].to(DEV), cap, (hidden[0].clone().requires_grad_(True), hidden[1]))
     with pytest.raises(ValueError):
         dec(g["feats"].to(DEV), cap, (hidden[0][:1], hidden[1][:1]))
+
+
+@pytest.mark.parametrize("env,tol", [("B2C_MERGE_REC=1,0", 2e-2), ("B2C_BG_CTAS=10,0", 1.5e-2), ("B2C_POST_OCC3=1,0", 1.5e-2)])
+def test_ab_switches_keep_the_results(env, tol):
+    """Every performance switch that changes the dataflow of the default bf16 path leaves the KD step's outputs and gradients where
+    they were (per-tensor relative L2; not bit-identical: the contraction order changes, and the K-split reductions are fp32 atomics whose
+    order varies from run to run -- two runs of the SAME build differ by up to ~8e-3 on the smallest gradients in bf16 mode): the top
+    layer's recurrent half merged into
+    the query-projection GEMM, the background CTA budget (changes the split-K plans of the capped GEMMs), the attn_post register variant."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "cluster_ab.py"), "--env", env, "--tol", str(tol), "48", "512"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "A/B: OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
