@@ -21,6 +21,8 @@ params = O.init_student_params(V, E, H, L, True, seed=0)
 pparams = O.init_projector_params(cfg["Et"], E, seed=1)
 model, projector = build_student(params, pparams, V, E, H, L, True, cfg["Et"], dev)
 model.decoder.compute_dtype = torch.bfloat16
+if os.environ.get("B2C_TL_TRAIN"):          # training mode (dropout on), like bench.py's value_dropout
+    model.train(); projector.train()
 loss_mod = DistillationLoss(0.7, 0.2, 0.1, 4.0, vocab_size=V)
 opt = FlatAdamW(reference_param_groups(model, projector, 1e-4), weight_decay=0.01, max_grad_norm=1.0)
 host = bench.make_batch(cfg, 1234)
