@@ -278,12 +278,17 @@ __device__ __forceinline__ uint4 epi_combine_f32(uint4 acc, uint4 old, float bet
 // LSTM = true: the instantiation used by the recurrence (fused cell epilogue only); false: the general epilogues only.  Two
 // kernels instead of one with both keep each one's code small: the recurrence's kernels are short and run back to back with
 // other kernels, so every launch starts with a cold instruction cache.
-template <int BN, bool A_MN, bool B_MN, typename TC, bool LSTM = false>
+// EPI selects ONE epilogue flavour per instantiation: 0 = the general store epilogues, 1 = fused LSTM cell, 2 = argmax partials (greedy
+// decode), 3 = validation partials.  Each flavour is its own kernel so none of them carries the others' code: these kernels run back to back
+// with cold instruction caches, and code that is never executed still costs (round 1: 66 -> 23-32 KB per kernel bought 40 us per step;
+// round 2: ~300 inlined instructions of a dropout hash in the general epilogue cost 8 % of the whole step).
+template <int BN, bool A_MN, bool B_MN, typename TC, int EPI = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, float alpha, float beta, TC* __restrict__ C, long ldc,
                const float* __restrict__ bias, int relu, int kb_per_split, int tiles_m, int tiles_n, int splits,
                int row_unperm_h, const __grid_constant__ LstmEpi le) {
+  constexpr bool LSTM = (EPI == 1);
   using Cfg = TcCfg<BN>;
   constexpr int TC_STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_dyn[];
@@ -505,7 +510,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
     constexpr int NCHUNK = BN / CH;                      // 128-byte column chunks per tile row
     constexpr int C_PER = (NCHUNK + 1) / 2;
-    if (le.enabled == 3) {
+    if constexpr (EPI == 3) {
       // ---- validation epilogue (EvalEpi): this thread owns one logits row and C_PER * CH columns of it
       const float* zt = reinterpret_cast<const float*>(le.addend);
       const int64_t* tg = reinterpret_cast<const int64_t*>(le.h_rec);
@@ -575,7 +580,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       continue;
     }
-    if (le.enabled == 2) {
+    if constexpr (EPI == 2) {
       // ---- argmax epilogue (ArgmaxEpi): this thread owns one row and C_PER * CH columns of it: running (max, lowest index)
       float* pmax = le.c_out; int* pidx = reinterpret_cast<int*>(le.gates_out);
       const int nparts = le.H, grow = m0 + q * 32 + lane;
@@ -613,6 +618,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       continue;
     }
+    if constexpr (EPI == 0) {
     // ---- fast path: a full interior tile, written once (beta = 0) or K-split partial sums reduced into fp32 C; 16-byte aligned C.  Straight-line
     // code without per-element predicates: the generic path below spends most of its issue slots (and instruction-cache
     // misses: ncu stall_no_inst + branch_resolving = 24 % of the samples of the vocab-head GEMM) on range / mode checks.
@@ -742,6 +748,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();                         // order this warp's tcgen05.ld before releasing the accumulator stage
     __syncwarp();
     if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }   // EPI == 0
     }   // general epilogues
     }
   }
@@ -853,17 +860,19 @@ int launch_tc(const GemmArgs& g, const TcPlan& plan, cudaStream_t st) {
   CUtensorMap ta, tb;
   if (!A_MN) B2C_TRY(make_tmap_bf16(&ta, g.A, g.K, g.M, g.lda, TC_BM)); else B2C_TRY(make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, 64));
   if (!B_MN) B2C_TRY(make_tmap_bf16(&tb, g.B, g.K, g.N, g.ldb, BN)); else B2C_TRY(make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, 64));
-  constexpr bool CAN_LSTM = !A_MN && !B_MN && sizeof(TC) == 4;
+  constexpr bool CAN_LSTM = !A_MN && !B_MN && sizeof(TC) == 4;       // the special epilogues exist for K-major operands and fp32 "outputs" only
   void (*kern)(const CUtensorMap, const CUtensorMap, int, int, int, float, float, TC*, long, const float*, int, int, int, int, int, int, const LstmEpi) =
-      gemm_tc_kernel<BN, A_MN, B_MN, TC, false>;
-  if (g.lstm) {
-    if constexpr (CAN_LSTM) kern = gemm_tc_kernel<BN, A_MN, B_MN, TC, true>;
-    else return set_err(B2C_EINVAL, "the fused LSTM epilogue needs K-major operands and fp32 accumulators out");
+      gemm_tc_kernel<BN, A_MN, B_MN, TC, 0>;
+  const int flavour = g.lstm ? 1 : (g.amax ? 2 : (g.eval ? 3 : 0));
+  if (flavour != 0) {
+    if constexpr (CAN_LSTM) {
+      kern = flavour == 1 ? gemm_tc_kernel<BN, A_MN, B_MN, TC, 1> : (flavour == 2 ? gemm_tc_kernel<BN, A_MN, B_MN, TC, 2> : gemm_tc_kernel<BN, A_MN, B_MN, TC, 3>);
+    } else return set_err(B2C_EINVAL, "the fused LSTM / argmax / validation epilogues need K-major operands and the fp32 instantiation");
   }
-  static bool attr_set[2] = {false, false};      // per template instantiation and epilogue flavour
-  if (!attr_set[g.lstm ? 1 : 0]) {
+  static bool attr_set[4] = {false, false, false, false};      // per template instantiation and epilogue flavour
+  if (!attr_set[flavour]) {
     B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<BN>::SMEM_BYTES));
-    attr_set[g.lstm ? 1 : 0] = true;
+    attr_set[flavour] = true;
   }
   const int kb_per_split = plan.kb_per_split, splits = plan.splits;
   if (splits > 1 && g.beta == 0.f)
