@@ -618,11 +618,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       continue;
     }
-    if constexpr (EPI == 0) {
+    if constexpr (EPI == 0 || EPI == 4) {
+    // (EPI == 4: every tile of this launch satisfies the fast path's conditions -- the host checked -- so the generic path is not even compiled in)
     // ---- fast path: a full interior tile, written once (beta = 0) or K-split partial sums reduced into fp32 C; 16-byte aligned C.  Straight-line
     // code without per-element predicates: the generic path below spends most of its issue slots (and instruction-cache
     // misses: ncu stall_no_inst + branch_resolving = 24 % of the samples of the vocab-head GEMM) on range / mode checks.
-    if ((split ? sizeof(TC) == 4 : beta == 0.f) && vec_ok && m0 + TC_BM <= M && n0 + BN <= N && (((uintptr_t)bias) & 15) == 0) {
+    if (EPI == 4 || ((split ? sizeof(TC) == 4 : beta == 0.f) && vec_ok && m0 + TC_BM <= M && n0 + BN <= N && (((uintptr_t)bias) & 15) == 0)) {
 #pragma unroll 1
       for (int ci = half * C_PER; ci < (half + 1) * C_PER && ci < NCHUNK; ++ci) {
         const int c0 = ci * CH;
@@ -678,6 +679,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       continue;
     }
+    if constexpr (EPI == 0) {
 #pragma unroll 1
     for (int ci = half * C_PER; ci < (half + 1) * C_PER && ci < NCHUNK; ++ci) {
       const int c0 = ci * CH;
@@ -748,7 +750,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();                         // order this warp's tcgen05.ld before releasing the accumulator stage
     __syncwarp();
     if (lane == 0) mbar_arrive(&tempty_bar[as]);
-    }   // EPI == 0
+    }   // generic path (EPI == 0 only)
+    }   // EPI == 0 || EPI == 4
     }   // general epilogues
     }
   }
@@ -836,6 +839,7 @@ inline TcPlan plan_tc(const GemmArgs& g, int elem_c, int sms) {
   return best;
 }
 
+inline bool fast_only_enabled() { static int on = -1; if (on < 0) { const char* e = getenv("B2C_GEMM_FAST_ONLY"); on = (e && e[0] == '0') ? 0 : 1; } return on != 0; }
 inline int sm_count() {
   static int n = 0;
   if (n == 0) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148; }
@@ -863,13 +867,18 @@ int launch_tc(const GemmArgs& g, const TcPlan& plan, cudaStream_t st) {
   constexpr bool CAN_LSTM = !A_MN && !B_MN && sizeof(TC) == 4;       // the special epilogues exist for K-major operands and fp32 "outputs" only
   void (*kern)(const CUtensorMap, const CUtensorMap, int, int, int, float, float, TC*, long, const float*, int, int, int, int, int, int, const LstmEpi) =
       gemm_tc_kernel<BN, A_MN, B_MN, TC, 0>;
-  const int flavour = g.lstm ? 1 : (g.amax ? 2 : (g.eval ? 3 : 0));
-  if (flavour != 0) {
+  int flavour = g.lstm ? 1 : (g.amax ? 2 : (g.eval ? 3 : 0));
+  if (flavour == 0 && fast_only_enabled() && g.M % TC_BM == 0 && g.N % BN == 0 && (plan.splits > 1 ? sizeof(TC) == 4 : g.beta == 0.f) &&
+      ((uintptr_t)g.C) % 16 == 0 && (g.ldc * (long)sizeof(TC)) % 16 == 0 && (((uintptr_t)g.bias) & 15) == 0) {
+    flavour = 4;                       // every tile takes the straight-line epilogue: the kernel without the generic path
+    kern = gemm_tc_kernel<BN, A_MN, B_MN, TC, 4>;
+  }
+  if (flavour != 0 && flavour != 4) {
     if constexpr (CAN_LSTM) {
       kern = flavour == 1 ? gemm_tc_kernel<BN, A_MN, B_MN, TC, 1> : (flavour == 2 ? gemm_tc_kernel<BN, A_MN, B_MN, TC, 2> : gemm_tc_kernel<BN, A_MN, B_MN, TC, 3>);
     } else return set_err(B2C_EINVAL, "the fused LSTM / argmax / validation epilogues need K-major operands and the fp32 instantiation");
   }
-  static bool attr_set[4] = {false, false, false, false};      // per template instantiation and epilogue flavour
+  static bool attr_set[5] = {false, false, false, false, false};      // per template instantiation and epilogue flavour
   if (!attr_set[flavour]) {
     B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<BN>::SMEM_BYTES));
     attr_set[flavour] = true;
