@@ -253,7 +253,7 @@ int attn_fwd(cudaStream_t st, const B2CShape& s, const float* P, const T* F, con
              long ldu = 0, float* u_save = nullptr) {
   if (ldu == 0) ldu = s.E;
   const size_t smem = (size_t)s.S * s.E * sizeof(T) + (size_t)(s.E + s.S) * 4;
-  const int nq = cdiv(s.E / 4, 32);
+  const int nq = s.S <= ATT_MAXTOK * (ATT_THREADS / 32) ? cdiv(s.E / 4, 32) : 4;       // more tokens than the register rows hold: generic kernel
   // E <= 256: 4 of the <= 7 token rows per warp are fetched in the prologue, the kernel fits 64 registers and all B = 512 CTAs
   // are resident in one wave (measured on B200: 3.23 ms / step vs 3.28 with all 7 rows up front at 80 registers, 3 CTAs / SM)
 #define B2C_ATT_(NQ, KA) do { B2C_TRY(set_smem(attn_step_fwd_kernel<T, NQ, KA>, smem)); \

@@ -130,9 +130,11 @@ attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
   const int E4 = E >> 2;
   constexpr int NQR = NQ > 0 ? NQ : 1;
   constexpr int KB = ATT_MAXTOK - KA > 0 ? ATT_MAXTOK - KA : 1;
-  const bool fast = NQ > 0 && S <= ATT_MAXTOK * nwarp;
+  // NQ > 0 instantiations are launched only when every token fits a warp's register rows (S <= ATT_MAXTOK * nwarp, checked by the
+  // host): the generic loop is then not even compiled in (a third of this kernel's code; it runs 20 times per step from a cold I-cache)
+  constexpr bool fast = NQ > 0;
   float4 pa[KA][NQR];
-  if (fast) {
+  if constexpr (fast) {
 #pragma unroll
     for (int k = 0; k < KA; ++k) {
       const int l = warp + k * nwarp;
@@ -168,7 +170,7 @@ attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
     a = warp_sum(a);
     if (lane == 0) sc[l] = a;
   };
-  if (fast) {
+  if constexpr (fast) {
     float4 pb[KB][NQR];
     if (KA < ATT_MAXTOK) {
 #pragma unroll
@@ -187,7 +189,7 @@ attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
 #pragma unroll
       for (int k = 0; k < KB; ++k) { const int l = warp + (KA + k) * nwarp; if (l < S) score(pb[k], l); }
     }
-  } else {
+  } else if constexpr (!fast) {
     for (int l = warp; l < S; l += nwarp) {
       float a = 0.f;
       for (int q = lane; q < E4; q += 32) {

@@ -288,7 +288,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                int M, int N, int K, float alpha, float beta, TC* __restrict__ C, long ldc,
                const float* __restrict__ bias, int relu, int kb_per_split, int tiles_m, int tiles_n, int splits,
                int row_unperm_h, const __grid_constant__ LstmEpi le) {
-  constexpr bool LSTM = (EPI == 1);
+  constexpr bool LSTM = (EPI == 1 || EPI == 5);          // 5: the cell epilogue without the inter-layer dropout code (eval mode, p = 0)
+  constexpr bool LSTM_DROP = (EPI == 1);
   using Cfg = TcCfg<BN>;
   constexpr int TC_STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_dyn[];
@@ -434,8 +435,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ---- fused LSTM cell: 32 accumulator columns = 8 hidden units x (i,f,g,o); straight from TMEM to the cell state buffers
       const int H = le.H, N4 = N;                        // N == 4H
       const int grow = m0 + q * 32 + lane;
-      const float inv_keep = le.drop_p > 0.f ? 1.0f / (1.0f - le.drop_p) : 1.0f;
-      const uint64_t dseed = le.drop_p > 0.f ? drop_seed(le.seed, le.seed_dev) : 0;
+      [[maybe_unused]] const float inv_keep = (LSTM_DROP && le.drop_p > 0.f) ? 1.0f / (1.0f - le.drop_p) : 1.0f;
+      [[maybe_unused]] const uint64_t dseed = (LSTM_DROP && le.drop_p > 0.f) ? drop_seed(le.seed, le.seed_dev) : 0;
       constexpr int NC32 = BN / 32, C32_PER = (NC32 + 1) / 2;
 #pragma unroll 1
       for (int ci = half * C32_PER; ci < (half + 1) * C32_PER && ci < NC32; ++ci) {
@@ -493,7 +494,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (le.h_top) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(le.h_top) + (long)grow * le.ld_top + u0) = hp;
           if (le.h_next) {
             uint4 hd = hp;
-            if (le.drop_p > 0.f) {
+            if (LSTM_DROP && le.drop_p > 0.f) {
               float hm[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) hm[u] = hn[u] * dropout_scale(dseed, le.site, (uint64_t)((le.row_base + grow) * H + u0 + u), le.drop_p, inv_keep);
@@ -867,7 +868,7 @@ int launch_tc(const GemmArgs& g, const TcPlan& plan, cudaStream_t st) {
   constexpr bool CAN_LSTM = !A_MN && !B_MN && sizeof(TC) == 4;       // the special epilogues exist for K-major operands and fp32 "outputs" only
   void (*kern)(const CUtensorMap, const CUtensorMap, int, int, int, float, float, TC*, long, const float*, int, int, int, int, int, int, const LstmEpi) =
       gemm_tc_kernel<BN, A_MN, B_MN, TC, 0>;
-  int flavour = g.lstm ? 1 : (g.amax ? 2 : (g.eval ? 3 : 0));
+  int flavour = g.lstm ? ((g.lstm->drop_p > 0.f && g.lstm->h_next) ? 1 : 5) : (g.amax ? 2 : (g.eval ? 3 : 0));
   if (flavour == 0 && fast_only_enabled() && g.M % TC_BM == 0 && g.N % BN == 0 && (plan.splits > 1 ? sizeof(TC) == 4 : g.beta == 0.f) &&
       ((uintptr_t)g.C) % 16 == 0 && (g.ldc * (long)sizeof(TC)) % 16 == 0 && (((uintptr_t)g.bias) & 15) == 0) {
     flavour = 4;                       // every tile takes the straight-line epilogue: the kernel without the generic path
@@ -875,10 +876,11 @@ int launch_tc(const GemmArgs& g, const TcPlan& plan, cudaStream_t st) {
   }
   if (flavour != 0 && flavour != 4) {
     if constexpr (CAN_LSTM) {
-      kern = flavour == 1 ? gemm_tc_kernel<BN, A_MN, B_MN, TC, 1> : (flavour == 2 ? gemm_tc_kernel<BN, A_MN, B_MN, TC, 2> : gemm_tc_kernel<BN, A_MN, B_MN, TC, 3>);
+      kern = flavour == 1 ? gemm_tc_kernel<BN, A_MN, B_MN, TC, 1> : (flavour == 5 ? gemm_tc_kernel<BN, A_MN, B_MN, TC, 5> :
+             (flavour == 2 ? gemm_tc_kernel<BN, A_MN, B_MN, TC, 2> : gemm_tc_kernel<BN, A_MN, B_MN, TC, 3>));
     } else return set_err(B2C_EINVAL, "the fused LSTM / argmax / validation epilogues need K-major operands and the fp32 instantiation");
   }
-  static bool attr_set[5] = {false, false, false, false, false};      // per template instantiation and epilogue flavour
+  static bool attr_set[6] = {false, false, false, false, false, false};      // per template instantiation and epilogue flavour
   if (!attr_set[flavour]) {
     B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<BN>::SMEM_BYTES));
     attr_set[flavour] = true;
