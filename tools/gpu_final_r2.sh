@@ -9,7 +9,7 @@ timeout 900 python bench.py > gpurun_out/bench_r2.json 2> gpurun_out/bench_r2.er
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r2_reference.json 2> gpurun_out/bench_r2_reference.err; echo "reference arm exit $?"; cut -c1-300 gpurun_out/bench_r2_reference.json
 tools/gpu_list.sh
 CMD="python bench.py --no-graph --steps 1 --warmup 1 --quick"
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'gemm_tc_kernel<\(int\)64, \(bool\)0, \(bool\)0, float, \(bool\)1>' -s 21 -c 2 -f -o /tmp/prof_r2_e $CMD > gpurun_out/ncu_r2_e.log 2>&1; echo "ncu E exit $?"
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'gemm_tc_kernel<\(int\)64, \(bool\)0, \(bool\)0, float, \(int\)5>' -s 21 -c 2 -f -o /tmp/prof_r2_e $CMD > gpurun_out/ncu_r2_e.log 2>&1; echo "ncu E exit $?"
 B2C_CLUSTER=1 $CMD > gpurun_out/r2_cluster_plain.log 2>&1 && B2C_CLUSTER=1 ncu --set full --clock-control none --import-source on -k regex:'recur_cluster_fwd' -c 1 -f -o /tmp/prof_r2_f $CMD > gpurun_out/ncu_r2_f.log 2>&1; echo "ncu F exit $?"
 for x in e f; do
   ncu -i /tmp/prof_r2_$x.ncu-rep --page raw --csv > gpurun_out/r2_ncu_${x}_raw.csv 2>/dev/null
