@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("B2C_LIB") or os.path.join(_HERE, "lib", "libb2c.so") 
 B2C_MAX_LAYERS = 4
 B2C_F32, B2C_BF16 = 0, 1
 B2C_WS_TRAIN, B2C_WS_DECODE, B2C_WS_ATTN, B2C_WS_REFINE, B2C_WS_PROJ = 0, 1, 2, 3, 4
-ABI_VERSION = 4
+ABI_VERSION = 5
 B2C_BWD_DEFER_JOIN = 1
 
 c_f32p = ctypes.c_void_p
@@ -102,6 +102,7 @@ SYMBOLS = {
     "b2c_greedy_decode": (ctypes.c_int, [_SHP, _PRM, _vp, _i64, _i64, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_attention_step": (ctypes.c_int, [_SHP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "b2c_refinement_forward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CRefineParams), _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
+    "b2c_refinement_forward_dual": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CRefineParams), _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_refinement_backward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CRefineParams), _vp, _vp, ctypes.POINTER(B2CRefineGrads), _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_projector_forward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CProjParams), _vp, _vp, _vp, _sz, ctypes.c_int, _DRP, _vp]),
     "b2c_projector_backward": (ctypes.c_int, [_SHP, ctypes.POINTER(B2CProjParams), _vp, ctypes.POINTER(B2CProjGrads), _vp, _sz, ctypes.c_int, _DRP, _vp]),
@@ -307,6 +308,17 @@ def decoder_prepare(captions: torch.Tensor, S: int, compute_dtype: torch.dtype, 
     return PreparedDecoder(ws, cap, (B, T, S, E, H, L, V, code), side)
 
 
+def compute_copy_of(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """`t` in the compute type, contiguous.  A tensor that a native module produced together with such a copy (RefinementFunction)
+    carries it as `_b2c_compute_copy`; it is used as long as the tensor has not been modified in place since."""
+    tag = getattr(t, "_b2c_compute_copy", None)
+    if tag is not None:
+        c, version = tag
+        if c.dtype == dtype and c.shape == t.shape and c.device == t.device and t._version == version:
+            return c
+    return t.detach().to(dtype).contiguous()
+
+
 class DecoderFunction(torch.autograd.Function):
     """LSTMDecoder.forward (reference src/student_model.py:205-256) as one C-ABI call each way."""
 
@@ -321,7 +333,7 @@ class DecoderFunction(torch.autograd.Function):
         V = params[0].shape[0]
         shape = B2CShape(B, T, S, E, H, L, V)
         code = dtype_code(compute_dtype)
-        f = feats.detach().to(compute_dtype).contiguous()
+        f = compute_copy_of(feats, compute_dtype)
         master = _master(params)
         if prepared is not None:
             if prepared.key != (B, T, S, E, H, L, V, code):
@@ -662,10 +674,15 @@ class RefinementFunction(torch.autograd.Function):
         out = torch.empty(B, S, E, dtype=torch.float32, device=x.device)      # fp32 residual stream in both modes
         prm = _fill_flat(B2CRefineParams(), master)
         drop = _dropout(dropout_p, seed, opts)
-        _check(lib.b2c_refinement_forward(ctypes.byref(shape), ctypes.byref(prm), xf.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                          code, ctypes.byref(drop), _stream()), "b2c_refinement_forward")
+        # bf16 mode: the final LayerNorm also leaves the features in the compute type; the decoder picks that copy up (compute_copy_of)
+        # instead of casting the fp32 output again (one element-wise pass less between the two modules, on the critical path)
+        out_c = torch.empty(B, S, E, dtype=compute_dtype, device=x.device) if compute_dtype != torch.float32 else None
+        _check(lib.b2c_refinement_forward_dual(ctypes.byref(shape), ctypes.byref(prm), xf.data_ptr(), out.data_ptr(), _ptr(out_c), ws.data_ptr(),
+                                               ws.numel(), code, ctypes.byref(drop), _stream()), "b2c_refinement_forward_dual")
         ctx.b2c = (shape, code, drop, ws, master, x.dtype, [p.dtype for p in params], xf, opts)
         ctx.b2c_params = params
+        if out_c is not None:
+            out._b2c_compute_copy = (out_c, out._version)
         return out
 
     @staticmethod

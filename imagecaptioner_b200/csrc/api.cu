@@ -913,7 +913,7 @@ template <> inline bool mha_use_mma<bf16>(int S, int hd) {
 
 template <typename T>
 int refinement_forward_impl(const B2CShape& s, const B2CRefineParams& p, const float* x, float* out, void* ws, size_t ws_bytes,
-                            const B2CDropout& dr, cudaStream_t st) {
+                            const B2CDropout& dr, cudaStream_t st, T* out_compute = nullptr) {
   RefineWs<T> W; W.carve(ws, s);
   B2C_CHECK_ARG(ws_bytes >= W.bytes, "workspace too small: %zu < %zu", ws_bytes, W.bytes);
   const int B = s.B, S = s.S, E = s.E, heads = s.H, hd = E / heads;
@@ -942,7 +942,8 @@ int refinement_forward_impl(const B2CShape& s, const B2CRefineParams& p, const f
     B2C_LAUNCH_CHECK("dropout_inplace_kernel");
   }
   B2C_TRY((gemm<T, T>(st, (int)R, E, 2 * E, W.f1, 2 * E, 0, W.W2, 2 * E, 0, W.f2, E, 0.f, p.ffn3_b)));
-  B2C_TRY((ln_fwd<float, T, float>(st, W.x1f, W.f2, p.n2_w, p.n2_b, (float*)nullptr, out, W.mean2, W.rstd2, R, E)));
+  if (out_compute) B2C_TRY((ln_fwd<float, T, T>(st, W.x1f, W.f2, p.n2_w, p.n2_b, out_compute, out, W.mean2, W.rstd2, R, E)));      // both copies from one pass
+  else B2C_TRY((ln_fwd<float, T, float>(st, W.x1f, W.f2, p.n2_w, p.n2_b, (float*)nullptr, out, W.mean2, W.rstd2, R, E)));
   return 0;
 }
 
@@ -1286,6 +1287,18 @@ int b2c_refinement_forward(const B2CShape* shape, const B2CRefineParams* params,
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2C_F32) return refinement_forward_impl<float>(*shape, *params, x, out, workspace, ws_bytes, dr, st);
   if (dtype == B2C_BF16) return refinement_forward_impl<bf16>(*shape, *params, x, out, workspace, ws_bytes, dr, st);
+  return set_err(B2C_EINVAL, "bad dtype %d", dtype);
+}
+
+int b2c_refinement_forward_dual(const B2CShape* shape, const B2CRefineParams* params, const float* x, float* out, void* out_compute,
+                                void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream) {
+  B2C_TRY(check_refine_shape(shape)); B2C_TRY(check_device());
+  B2C_CHECK_ARG(params && x && out && workspace, "NULL argument");
+  const B2CDropout dr = dropout ? *dropout : B2CDropout{0.f, 0, nullptr};
+  B2C_CHECK_ARG(dr.p >= 0.f && dr.p < 1.f, "dropout p=%f outside [0,1)", dr.p);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2C_F32) return refinement_forward_impl<float>(*shape, *params, x, out, workspace, ws_bytes, dr, st, (float*)nullptr);   // fp32: `out` is the compute copy
+  if (dtype == B2C_BF16) return refinement_forward_impl<bf16>(*shape, *params, x, out, workspace, ws_bytes, dr, st, (bf16*)out_compute);
   return set_err(B2C_EINVAL, "bad dtype %d", dtype);
 }
 

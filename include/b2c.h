@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define B2C_ABI_VERSION 4
+#define B2C_ABI_VERSION 5
 #define B2C_MAX_LAYERS 4
 
 enum { B2C_OK = 0, B2C_EINVAL = -1, B2C_EARCH = -2, B2C_ECUDA = -3, B2C_ENOMEM = -4 };
@@ -180,6 +180,11 @@ typedef struct B2CRefineGrads {
  * dropout->p is the reference's 0.1 in training (attention probabilities and FFN), 0 in eval. */
 int b2c_refinement_forward(const B2CShape* shape, const B2CRefineParams* params, const float* x, float* out,
                            void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream);
+/* The same forward that ALSO leaves the output in the compute type (`out_compute`, (B,S,E) of `dtype`, may be NULL): the decoder
+ * consumes the refined features in the compute type (TMA operands), and taking them from the final LayerNorm saves the separate
+ * fp32 -> bf16 pass over the features that would otherwise sit between the two calls on the critical path. */
+int b2c_refinement_forward_dual(const B2CShape* shape, const B2CRefineParams* params, const float* x, float* out, void* out_compute,
+                                void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream);
 /* x = the forward's input, dout (B,S,E) fp32 -> grads (fp32, overwritten), dx (B,S,E) fp32. */
 int b2c_refinement_backward(const B2CShape* shape, const B2CRefineParams* params, const float* x, const float* dout, const B2CRefineGrads* grads,
                             float* dx, void* workspace, size_t ws_bytes, int dtype, const B2CDropout* dropout, void* stream);

@@ -30,7 +30,7 @@ def test_header_and_binding_agree(lib):
 
 def test_abi_version_and_error_string(lib):
     from imagecaptioner_b200 import _ops
-    assert lib.b2c_abi_version() == _ops.ABI_VERSION == 4
+    assert lib.b2c_abi_version() == _ops.ABI_VERSION == 5
     assert isinstance(lib.b2c_last_error(), bytes)
 
 
