@@ -269,9 +269,9 @@ int attn_bwd(cudaStream_t st, int B, int S, int E, const float* P, const T* F, c
              float* ds, T* du) {
   const size_t smem = (size_t)S * E * sizeof(T) + (size_t)(E + 2 * S) * 4;
   constexpr int PB = 13;            // P rows per batch of the du phase (measured: 8 -> 3.25, 13 -> 3.23, 25 -> 3.32 ms / step)
-#define B2C_ATTB(PB) do { B2C_TRY(set_smem(attn_step_bwd_kernel<T, PB>, smem)); \
-    B2C_CUDA(launch_pdl(attn_step_bwd_kernel<T, PB>, dim3(B), dim3(ATT_THREADS), smem, st, P, F, u, (long)E, attw, dctx, lddctx, S, E, ds, du, (long)E)); } while (0)
-  B2C_ATTB(PB);
+#define B2C_ATTB(PB, SMALL) do { B2C_TRY(set_smem(attn_step_bwd_kernel<T, PB, SMALL>, smem)); \
+    B2C_CUDA(launch_pdl(attn_step_bwd_kernel<T, PB, SMALL>, dim3(B), dim3(ATT_THREADS), smem, st, P, F, u, (long)E, attw, dctx, lddctx, S, E, ds, du, (long)E)); } while (0)
+  if (E <= 256) B2C_ATTB(PB, true); else B2C_ATTB(PB, false);
 #undef B2C_ATTB
   B2C_LAUNCH_CHECK("attn_step_bwd_kernel");
   return 0;

@@ -225,7 +225,7 @@ attn_step_fwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
 //   dw_l = sum_e dctx_e F[l,e];  ds_l = w_l (dw_l - sum_j w_j dw_j);  du_e = sum_l ds_l (1 - tanh^2(P[l,e]+u_e))
 // Shared memory: Fs (S*E) | dcs (E) | dw (S) | ws (S).  The du phase walks P in batches of PB rows, the next batch in flight
 // while the current one goes through the MUFU (the unbatched loop was 49 serialised L2 round trips: 58 % of all stall samples).
-template <typename T, int PB>
+template <typename T, int PB, bool E256 = false>       // E256: E <= 256 known at compile time (one 8-element chunk per lane; the wide loop is not compiled in)
 __global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const float* __restrict__ u, long ldu,
                      const float* __restrict__ attw, const float* __restrict__ dctx, long lddctx,
@@ -262,7 +262,7 @@ attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
   __syncthreads();
   mbar_wait(&bar, 0);
   // dw: warp per token, each lane owns 8-element chunks (one 16-byte shared load per token in bf16)
-  if (E <= 256) {
+  if (E256 || E <= 256) {
     float d[8];
     const int c = lane * 8;
     const bool on = c < E;
@@ -278,7 +278,7 @@ attn_step_bwd_kernel(const float* __restrict__ P, const T* __restrict__ F, const
       a = warp_sum(a);
       if (lane == 0) dw[l] = a;
     }
-  } else {
+  } else if constexpr (!E256) {
     for (int l = warp; l < S; l += nwarp) {
       float a = 0.f;
       for (int c = lane * 8; c < E; c += 256) {
