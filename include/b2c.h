@@ -6,10 +6,13 @@
  *   b2c_decoder_forward   <- LSTMDecoder.forward                    src/student_model.py:205-256
  *                            (attention_mechanism :173-203, nn.LSTM step :244, output_projection :247)
  *   b2c_decoder_prepare / b2c_decoder_forward_prepared <- the same forward split at the point where the image features are first read
+ *   b2c_decoder_set_initial_state <- the optional `hidden=(h0, c0)` argument of LSTMDecoder.forward   src/student_model.py:205,219-222
+ *   b2c_decoder_forward_eval <- validate_student_model's forward + loss + argmax without a logits tensor   src/train_student_kd.py:29-86
  *   b2c_decoder_backward  <- autograd of the above (loss.backward(), src/train_student_kd.py:288)
  *   b2c_greedy_decode     <- CaptioningStudent.caption_image loop   src/student_model.py:339-381 (batched)
  *   b2c_attention_step    <- LSTMDecoder.attention_mechanism          src/student_model.py:173-203 (stand-alone accessor)
  *   b2c_refinement_forward/backward <- AttentionRefinement.forward (+ autograd)   src/student_model.py:72-118
+ *   b2c_refinement_forward_dual <- the same, also emitting the output in the compute type for the decoder that follows (:313-320)
  *   b2c_projector_forward/backward  <- FeatureProjector.forward (+ autograd)      src/distillation_utils.py:203-252
  *   b2c_count_valid       <- CrossEntropyLoss(ignore_index=0) normaliser  src/distillation_utils.py:22
  *   b2c_kd_token_loss     <- token_level_distillation :30-54 + CE term :154 (+ their gradient)
@@ -19,6 +22,7 @@
  *   b2c_loss_finalize     <- the alpha/beta/gamma weighting and loss_dict  :184-198
  *   b2c_scale_inplace     <- the scalar grad_output of loss.backward() (GradScaler / accumulation, train_student_kd.py:285-288)
  *   b2c_optimizer_step    <- scaler.unscale_ + clip_grad_norm_ (x2) + AdamW.step + scaler.update   src/train_student_kd.py:230-236,290-303
+ *   b2c_set_gemm_cta_limit <- (no reference counterpart) CTA budget for calls a host overlaps with the decoder's recurrences
  *   b2c_gemm              <- test hook for the tcgen05 / SIMT contraction tiles used inside the decoder
  *
  * Conventions
