@@ -105,8 +105,9 @@ ln_pool_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, co
   const int lane = threadIdx.x & 31, wpb = LN_THREADS / 32, nch = E >> 3;
   const long total = (long)B * O;
   for (long w = (long)blockIdx.x * wpb + (threadIdx.x >> 5); w < total; w += (long)gridDim.x * wpb) {
-    const long b = w / O; const int o = (int)(w - b * O);
-    const int lo = (int)(((long)o * L) / O), hi = (int)(((long)(o + 1) * L + O - 1) / O);
+    const unsigned wu = (unsigned)w, Ou = (unsigned)O, Lu = (unsigned)L;          // 32-bit index arithmetic (B * O, L * O < 2^31)
+    const long b = (long)(wu / Ou); const int o = (int)(wu - (unsigned)b * Ou);
+    const int lo = (int)(((unsigned)o * Lu) / Ou), hi = (int)((((unsigned)o + 1) * Lu + Ou - 1) / Ou);
     float acc[NC][8];
 #pragma unroll
     for (int c = 0; c < NC; ++c)
@@ -163,8 +164,10 @@ ln_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ dpool, int L
     ln_load_row<TX, TR, NC>(x, res, r, E, nch, lane, v, sum);
     int o_min = 0, o_max = -1; long bo = 0;
     if (POOLED) {
-      const long b = r / L; const int l = (int)(r - b * L);
-      o_min = (int)(((long)l * O) / L); o_max = (int)((((long)(l + 1) * O + L - 1) / L) - 1); bo = b * O;
+      // 32-bit index arithmetic (R, L * O < 2^31): six 64-bit divisions per row made this variant ALU-bound (129 us for 100 864 rows)
+      const unsigned ru = (unsigned)r, Lu = (unsigned)L, Ou = (unsigned)O;
+      const unsigned b = ru / Lu, l = ru - b * Lu;
+      o_min = (int)((l * Ou) / Lu); o_max = (int)(((l + 1) * Ou + Lu - 1) / Lu) - 1; bo = (long)b * O;
     }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -175,7 +178,7 @@ ln_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ dpool, int L
       if (ch < nch) {
         if (POOLED) {
           for (int o = o_min; o <= o_max; ++o) {
-            const int lo = (int)(((long)o * L) / O), hi = (int)(((long)(o + 1) * L + O - 1) / O);
+            const int lo = (int)(((unsigned)o * (unsigned)L) / (unsigned)O), hi = (int)((((unsigned)o + 1) * (unsigned)L + (unsigned)O - 1) / (unsigned)O);
             float t[8]; Vec8<float>::load(dpool + (bo + o) * E + ch * 8, t);
             const float inv = 1.0f / (float)(hi - lo);
 #pragma unroll
