@@ -47,6 +47,7 @@ int check_shape(const B2CShape* s) {
   B2C_CHECK_ARG(s->B > 0 && s->T > 0 && s->S > 0 && s->V > 1, "bad shape B=%d T=%d S=%d V=%d", s->B, s->T, s->S, s->V);
   B2C_CHECK_ARG(s->L >= 1 && s->L <= MAXL, "L=%d outside [1,%d]", s->L, MAXL);
   B2C_CHECK_ARG(s->E > 0 && s->E % 8 == 0 && s->H > 0 && s->H % 8 == 0, "E=%d and H=%d must be positive multiples of 8", s->E, s->H);
+  B2C_CHECK_ARG((long)s->B * 4 * s->H < 2147483647L && (long)s->B * s->S * s->E < 2147483647L, "B*4H and B*S*E must stay below 2^31 (32-bit index arithmetic in the per-step kernels)");
   return 0;
 }
 
@@ -1007,6 +1008,7 @@ int check_proj_shape(const B2CShape* s) {
   B2C_CHECK_ARG(s != nullptr, "shape is NULL");
   B2C_CHECK_ARG(s->B > 0 && s->S > 0 && s->E > 0 && s->H > 0 && s->T > 0 && s->T <= s->S, "bad projector shape B=%d St=%d Et=%d Es=%d So=%d", s->B, s->S, s->E, s->H, s->T);
   B2C_CHECK_ARG(s->E % 8 == 0 && s->H % 8 == 0 && s->H <= 256 * LN_MAXC, "Et=%d / Es=%d must be multiples of 8 and Es <= %d", s->E, s->H, 256 * LN_MAXC);
+  B2C_CHECK_ARG((long)s->B * s->S < 2147483647L && (long)s->S * s->T < 2147483647L, "B*St and St*So must stay below 2^31 (32-bit index arithmetic in the pooled LayerNorm kernels)");
   return 0;
 }
 

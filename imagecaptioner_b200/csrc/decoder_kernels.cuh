@@ -489,7 +489,7 @@ lstm_pointwise_bwd_kernel(const T* __restrict__ gates, const float* __restrict__
   const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   struct Saved { float gt[4]; float tc, cp, dh_fixed, mask; };
   auto load_saved = [&](long idx, Saved& sv) {
-    const long b = idx / H; const int j = (int)(idx - b * H);
+    const long b = (long)((unsigned)idx / (unsigned)H); const int j = (int)(idx - b * H);      // B * H < 2^31: 32-bit division
     Gate4<T>::load(gates + b * 4 * H + 4 * j, sv.gt);
     sv.tc = Math<T>::tanh_(c_cur[idx]);
     sv.cp = c_prev[idx];
@@ -505,7 +505,7 @@ lstm_pointwise_bwd_kernel(const T* __restrict__ gates, const float* __restrict__
   pdl_wait();
   for (long idx = idx0; idx < total; idx += (long)gridDim.x * blockDim.x) {
     if (idx != idx0) load_saved(idx, sv);
-    const long b = idx / H; const int j = (int)(idx - b * H);
+    const long b = (long)((unsigned)idx / (unsigned)H); const int j = (int)(idx - b * H);
     float dh = sv.dh_fixed;
     if (dh_carry) dh += __ldcg(dh_carry + b * ld_carry + j);
     if (dh_above) dh += __ldcg(dh_above + b * ld_above + j) * sv.mask;
