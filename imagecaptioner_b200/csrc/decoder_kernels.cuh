@@ -540,7 +540,17 @@ __global__ void __launch_bounds__(256) dropout_inplace_kernel(T* __restrict__ x,
 // d(pre-ReLU, pre-dropout) = d(o1) * [o1 > 0] / (1-p)      (o1 is the saved post-ReLU, post-dropout activation)
 template <typename T>
 __global__ void __launch_bounds__(256) relu_bwd_inplace_kernel(T* __restrict__ d, const T* __restrict__ act, long n, float inv_keep) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+  // 8 elements (16 bytes in bf16) per thread and iteration; it sits on the main chain between the head's two backward GEMMs
+  // (22 us with one 2-byte element per thread and iteration)
+  const long n8 = ((((uintptr_t)d) & 15) == 0 && (((uintptr_t)act) & 15) == 0) ? (n >> 3) : 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    float dv[8], av[8];
+    Vec8<T>::load(d + i * 8, dv); Vec8<T>::load(act + i * 8, av);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dv[j] = av[j] > 0.f ? dv[j] * inv_keep : 0.f;
+    Vec8<T>::store(d + i * 8, dv);
+  }
+  for (long i = n8 * 8 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     d[i] = from_f<T>(to_f<T>(act[i]) > 0.f ? to_f<T>(d[i]) * inv_keep : 0.f);
 }
 
