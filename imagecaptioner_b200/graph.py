@@ -75,6 +75,9 @@ class GraphedKDStep:
         self._fake_dp = self.world == 1 and os.environ.get("B2C_FAKE_DP", "0") == "1"
         self._multi = self.world > 1 or self._fake_dp
         self.nval = torch.zeros(1, dtype=torch.int32, device=self.static["targets"].device) if self._multi else None
+        # single rank under capture: the non-PAD count is taken off the main chain (it only depends on the targets): counted on the
+        # projector's side stream at the start of the step instead of between the vocabulary head and the token loss
+        self._nval_single = torch.zeros(1, dtype=torch.int32, device=self.static["targets"].device) if not self._multi else None
         # Overlapped exchanges (graph mode, multi-rank): the collectives run on a communication stream, tied to the graph by
         # EXTERNAL events -- the non-PAD count is all-reduced under the forward (graph 1 waits for it just before the loss) and
         # the decoder's gradient segment (90 % of the bytes) is all-reduced under the refinement backward (graph 1 records an
@@ -176,6 +179,10 @@ class GraphedKDStep:
         if self._overlap:
             main = torch.cuda.current_stream()
             self._side.wait_stream(main)
+            if self._nval_single is not None:
+                with torch.cuda.stream(self._side):
+                    _ops.count_valid(inp["targets"], self.loss_module.vocab_size or 2 ** 31 - 1, out=self._nval_single)
+                self.loss_module.n_valid_global = self._nval_single
             with torch.cuda.stream(self._side), ctx:
                 tproj = self.projector(inp["teacher_features"])
             with ctx:                                                  # the reference's loop runs under autocast (train_student_kd.py:271)
@@ -199,6 +206,8 @@ class GraphedKDStep:
             loss.backward()
         finally:
             self._detach_options()
+            if self._nval_single is not None:
+                self.loss_module.n_valid_global = None      # the captured kernels hold the pointer; an eager use of the loss module counts itself
             if self._opts.join_pending:          # the decoder backward deferred its weight-gradient join (B2C_BWD_DEFER_JOIN)
                 self._opts.join_pending = False
                 _ops.join_side_work()
